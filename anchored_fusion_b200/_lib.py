@@ -1,0 +1,126 @@
+"""ctypes binding of libafb200.so (the C ABI declared in include/anchored_fusion.h).
+
+There is no fallback: if the CUDA library cannot be loaded the import of the product fails
+loudly.  The library is built in-tree by anchored_fusion_b200/build.py (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libafb200.so")
+
+c_i32, c_i64, c_u32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
+
+
+class Params(ctypes.Structure):
+    """af_params_t: bwa-mem defaults the reference relies on (Anchored_Fusion.py:182)."""
+    _fields_ = [(n, c_i32) for n in ("k", "A", "B", "clip5", "clip3", "T", "X")]
+
+
+class IndexInfo(ctypes.Structure):
+    _fields_ = [(n, c_i32) for n in ("anchor_len", "k", "kp", "stride", "n_keys", "n_entries", "n_buckets",
+                                      "n_overflow", "table_slots")] + [("filter_mul", c_u32), ("pad_byte", c_i32)]
+
+
+class Layout(ctypes.Structure):
+    _fields_ = [("max_read_len", c_i32), ("words_per_read", c_i32), ("quads_per_pair", c_i32), ("reserved", c_i32),
+                ("n_pairs", c_i64), ("n_tiles", c_i64), ("packed_bytes", c_i64)]
+
+
+class Batch(ctypes.Structure):
+    _fields_ = [("packed", c_vp), ("n_pairs", c_i64), ("max_read_len", c_i32), ("uniform_len", c_i32),
+                ("lens", c_vp), ("nread_ids", c_vp), ("nmask", c_vp), ("n_nreads", c_i64)]
+
+
+class Synth(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64), ("ref_len", c_i64), ("anchor_start", c_i64), ("anchor_len", c_i32),
+                ("read_len", c_i32), ("frag_mean", c_i32), ("frag_sd", c_i32), ("sub_ppm", c_u32),
+                ("fusion_ppm", c_u32), ("n_ppm", c_u32), ("reserved", c_u32)]
+
+
+HIT_DTYPE = np.dtype([("read_id", "<u4"), ("pos", "<i4"), ("clip_l", "<u2"), ("m_len", "<u2"),
+                      ("clip_r", "<u2"), ("score_strand", "<u2")])
+CNT_FLAGGED, CNT_HITS, CNT_STATUS, CNT_SEEDED, N_COUNTS = 0, 1, 2, 3, 8
+NMASK_WORDS = 8
+MAX_READ_LEN = 256
+
+# every symbol include/anchored_fusion.h declares: name -> (restype, argtypes)
+P = ctypes.POINTER
+SIGNATURES = {
+    "af_last_error": (ctypes.c_char_p, []),
+    "af_abi_version": (ctypes.c_int, []),
+    "af_default_params": (None, [P(Params)]),
+    "af_index_build": (ctypes.c_int, [ctypes.c_char_p, c_i64, P(Params), c_i32, P(c_vp)]),
+    "af_index_free": (None, [c_vp]),
+    "af_index_info": (ctypes.c_int, [c_vp, P(IndexInfo)]),
+    "af_index_filter": (c_vp, [c_vp]),
+    "af_index_table": (c_vp, [c_vp]),
+    "af_index_upload": (ctypes.c_int, [c_vp, ctypes.c_int, P(c_vp)]),
+    "af_dev_index_free": (None, [c_vp]),
+    "af_dev_index_device": (ctypes.c_int, [c_vp]),
+    "af_layout": (ctypes.c_int, [c_i32, c_i64, P(Layout)]),
+    "af_pack_pairs": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64,
+                                     P(c_i64), P(c_i32)]),
+    "af_unpack_read": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i32, c_vp]),
+    "af_fastq_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, P(c_vp)]),
+    "af_fastq_close": (None, [c_vp]),
+    "af_fastq_next": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64), P(c_i32),
+                                     P(c_i64)]),
+    "af_fastq_record": (ctypes.c_int, [c_vp, c_i64, P(c_vp), P(c_i32), P(c_vp), P(c_vp), P(c_i32)]),
+    "af_workspace_bytes": (ctypes.c_size_t, [c_i64, c_i64]),
+    "af_anchor_batch": (ctypes.c_int, [c_vp, P(Batch), c_vp, ctypes.c_size_t, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "af_seed_scan": (ctypes.c_int, [c_vp, P(Batch), c_vp, c_vp]),
+    "af_seed_scan_config": (ctypes.c_int, [c_i32, c_i32]),
+    "af_kernel_launches": (c_i64, []),
+    "af_pipeline_create": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, P(c_vp)]),
+    "af_pipeline_free": (None, [c_vp]),
+    "af_pipeline_run": (ctypes.c_int, [c_vp, P(Batch), c_vp, c_i64, P(c_i64), P(c_i64)]),
+    "af_pipeline_launches": (c_i64, [c_vp]),
+    "af_host_alloc": (c_vp, [ctypes.c_size_t]),
+    "af_host_free": (None, [c_vp]),
+    "af_synth_anchor": (ctypes.c_int, [P(Synth), c_vp]),
+    "af_synth_pairs_host": (ctypes.c_int, [P(Synth), c_i64, c_i64, c_vp, c_vp]),
+    "af_synth_pairs_device": (ctypes.c_int, [P(Synth), c_i64, c_i64, c_i32, c_vp, c_vp]),
+}
+
+
+class AnchoredFusionError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libafb200.so; raise if it is missing (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AnchoredFusionError(
+                "libafb200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python anchored_fusion_b200/build.py` (needs nvcc); there is no CPU fallback")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.af_abi_version() != 1:
+            raise AnchoredFusionError("libafb200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise AnchoredFusionError("libafb200 error %d: %s" % (rc, lib().af_last_error().decode(errors="replace")))
+
+
+def ptr(a):
+    """data pointer of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()

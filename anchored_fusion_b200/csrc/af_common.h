@@ -1,0 +1,161 @@
+// af_common.h -- constants and hash functions shared by the host index builder and the
+// sm_100a kernels.  Host and device MUST agree bit for bit on everything in this file.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/anchored_fusion.h"
+
+#ifdef __CUDACC__
+#define AF_HD __host__ __device__ __forceinline__
+#else
+#define AF_HD inline
+#endif
+
+// ---- shared-memory filter ----------------------------------------------------------------
+// bucket word: three 10-bit fingerprint fields (0 = empty; stored fingerprints are odd, so
+// never 0) and a 2-bit state field in bits 30..31: 01 = normal, 00 = overflowed (always hit).
+// The probe tests all four fields for "== 0 after XOR" with one subtract and one LOP3.
+static const uint32_t AF_F_ONES = 0x40100401u;   // low bit of each field
+static const uint32_t AF_F_HIGH = 0xA0080200u;   // high bit of each field
+static const uint32_t AF_F_REP = 0x00100401u;    // replicates a fingerprint into 3 fields
+static const uint32_t AF_F_EMPTY = 0x40000000u;  // empty, normal bucket
+static const int AF_F_SLOTS = 3;
+static const uint32_t AF_MAX_BUCKETS = 53248;    // 208 KB of the 227 KB shared memory
+static const uint32_t AF_MIN_BUCKETS = 2048;
+
+AF_HD uint32_t af_umulhi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+// key -> bucket index and the fingerprint replicated into the three fields (state field 00).
+// One 32-bit multiply: the bucket comes from the top bits of the product, the fingerprint
+// from bits 1..9.  (Taking the fingerprint from the HIGH word of the 64-bit product looked
+// natural but is 5x worse: keys that share a bucket differ by a lattice of deltas whose high
+// words repeat.  Within a bucket the low bits of the product are free.)
+AF_HD void af_filter_hash(uint32_t key, uint32_t fmul, uint32_t nb, uint32_t &bucket, uint32_t &fp3) {
+    uint32_t lo = key * fmul;
+    bucket = af_umulhi(lo, nb);
+    fp3 = (lo & 0x3FEu) * AF_F_REP + AF_F_REP;  // fingerprint = (lo & 0x3FE) + 1, odd, 1..1023
+}
+
+// nonzero iff some field of the bucket equals the fingerprint, or the bucket overflowed
+AF_HD uint32_t af_filter_test(uint32_t word, uint32_t fp3) {
+    uint32_t v = word ^ fp3;
+    return (v - AF_F_ONES) & ~v & AF_F_HIGH;
+}
+
+// ---- exact table (global memory): open addressing, duplicates allowed ---------------------
+static const uint32_t AF_T_EMPTY = 0xFFFFFFFFu;  // k' <= 15 keeps real keys below this
+AF_HD uint32_t af_table_hash(uint32_t key, uint32_t tmask) {
+    uint32_t h = key * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    h ^= h >> 13;
+    return h & tmask;
+}
+
+// ---- synthetic generator ------------------------------------------------------------------
+AF_HD uint64_t af_mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+AF_HD uint32_t af_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    return x ^ (x >> 16);
+}
+// base x of the random reference: 32 bases per 64-bit hash word
+AF_HD uint32_t af_ref_base(uint64_t seed, int64_t x) {
+    uint64_t w = af_mix64(seed ^ ((uint64_t)(x >> 5) * 0xD6E8FEB86659FD93ull));
+    return (uint32_t)(w >> (2 * (x & 31))) & 3u;
+}
+
+struct af_frag {       // one synthetic fragment, a pure function of (seed, pair index)
+    int64_t start;     // reference start of the (left part of the) fragment
+    int64_t start2;    // reference start of the right part when chimeric
+    int32_t len;       // fragment length
+    int32_t junction;  // chimeric: fragment offset where the right part begins; else len
+    int32_t flip;      // 1: the fragment is the reverse complement of the reference interval
+    uint32_t rseed;    // per-pair seed of the substitution / N stream
+};
+
+AF_HD af_frag af_make_frag(const af_synth_t &s, int64_t pair) {
+    af_frag f;
+    uint64_t h0 = af_mix64(s.seed * 0x9E3779B97F4A7C15ull + (uint64_t)pair);
+    uint64_t h1 = af_mix64(h0), h2 = af_mix64(h1), h3 = af_mix64(h2);
+    int64_t u = (int64_t)(h0 & 0xFFFF) + (int64_t)((h0 >> 16) & 0xFFFF) + (int64_t)((h0 >> 32) & 0xFFFF) +
+                (int64_t)((h0 >> 48) & 0xFFFF) - 131070;       // ~N(0, 37837)
+    int64_t len = (int64_t)s.frag_mean + (u * (int64_t)s.frag_sd) / 37837;
+    if (len < s.read_len) len = s.read_len;
+    if (len > s.ref_len / 2) len = s.ref_len / 2;
+    f.len = (int32_t)len;
+    f.flip = (int32_t)((h1 >> 63) & 1);
+    f.rseed = (uint32_t)(h3 >> 32);
+    f.junction = f.len;
+    f.start = (int64_t)(h1 % (uint64_t)(s.ref_len - len));
+    f.start2 = 0;
+    bool fusion = (uint32_t)(h2 % 1000000ull) < s.fusion_ppm;
+    if (fusion && s.anchor_len > 64 && f.len > 60) {
+        // left part ends somewhere inside the anchor, right part starts elsewhere
+        int32_t jx = 30 + (int32_t)((h2 >> 20) % (uint64_t)(f.len - 59));   // 30 .. len-30
+        int64_t aend = s.anchor_start + 32 + (int64_t)((h2 >> 40) % (uint64_t)(s.anchor_len - 63));
+        int64_t st = aend - jx;
+        if (st < 0) st = 0;
+        f.start = st;
+        f.junction = jx;
+        f.start2 = (int64_t)(h3 % (uint64_t)(s.ref_len - len));
+    }
+    return f;
+}
+
+// base i (0..len) of the fragment in fragment orientation
+AF_HD uint32_t af_frag_base(const af_synth_t &s, const af_frag &f, int32_t i) {
+    int32_t j = f.flip ? f.len - 1 - i : i;   // offset in reference orientation
+    int64_t x = (j < f.junction) ? f.start + j : f.start2 + (j - f.junction);
+    uint32_t b = af_ref_base(s.seed, x);
+    return f.flip ? 3u - b : b;
+}
+
+// base i of mate m (0/1) of the pair, with substitutions and Ns; returns 0..4
+AF_HD uint32_t af_read_base(const af_synth_t &s, const af_frag &f, int m, int32_t i) {
+    uint32_t b = m == 0 ? af_frag_base(s, f, i) : 3u - af_frag_base(s, f, f.len - 1 - i);
+    uint32_t e = af_mix32(f.rseed + (uint32_t)(m * 4096 + i) * 0x9E3779B1u);
+    if (s.sub_ppm && (e % 1000003u) < s.sub_ppm) b = (b + 1u + ((e >> 24) % 3u)) & 3u;
+    if (s.n_ppm) {
+        uint32_t e2 = af_mix32(e ^ 0xA5A5A5A5u);
+        if ((e2 % 1000003u) < s.n_ppm) b = 4u;
+    }
+    return b;
+}
+
+// ---- error reporting and host-side objects ------------------------------------------------
+void af_set_error(const char *fmt, ...);
+
+struct af_index {
+    af_params_t P;
+    int32_t kp, stride, G;
+    std::vector<uint8_t> codes;     // anchor base codes 0..4
+    uint32_t fmul, nb;
+    std::vector<uint32_t> filter;   // nb bucket words
+    uint32_t tmask;
+    std::vector<uint32_t> table;    // (tmask+1) x {key, value}; value = strand<<31 | anchor pos
+    int32_t n_keys, n_entries, n_overflow, pad_byte;
+};
+
+static inline uint8_t af_code_of(char c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}

@@ -1,0 +1,285 @@
+// af_host.cpp -- host side of libafb200: anchor index build, batch layout, 2-bit packer,
+// synthetic-read generator (host twin of the device generator), error plumbing.
+// No CUDA here; see af_kernels.cu for the device side.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "af_common.h"
+
+static thread_local char g_err[512] = "";
+
+void af_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *af_last_error(void) { return g_err; }
+extern "C" int af_abi_version(void) { return AF_ABI_VERSION; }
+extern "C" void af_default_params(af_params_t *p) {
+    p->k = 19; p->A = 1; p->B = 4; p->clip5 = 5; p->clip3 = 5; p->T = 30; p->X = 100;
+}
+
+// ------------------------------------------------------------------------------------------
+// anchor index  (replaces `bwa index`, Anchored_Fusion.py:167-172)
+// ------------------------------------------------------------------------------------------
+static int build_filter(const std::vector<uint32_t> &keys, uint32_t fmul, uint32_t nb, std::vector<uint32_t> &out) {
+    out.assign(nb, AF_F_EMPTY);
+    int overflow = 0;
+    for (uint32_t key : keys) {
+        uint32_t b, fp3;
+        af_filter_hash(key, fmul, nb, b, fp3);
+        uint32_t fp = fp3 & 0x3FFu, w = out[b];
+        if (!(w & AF_F_EMPTY)) continue;  // already always-hit
+        bool placed = false;
+        for (int s = 0; s < AF_F_SLOTS && !placed; s++) {
+            uint32_t cur = (w >> (10 * s)) & 0x3FFu;
+            if (cur == fp) placed = true;
+            else if (cur == 0) { w |= fp << (10 * s); placed = true; }
+        }
+        if (!placed) { w = 0; overflow++; }  // state 00: every probe of this bucket hits
+        out[b] = w;
+    }
+    return overflow;
+}
+
+extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t *params, int32_t kp,
+                              af_index_t **out) {
+    if (!anchor || !out || len <= 0 || len >= (1ll << 28)) { af_set_error("af_index_build: bad anchor"); return AF_ERR_ARG; }
+    af_params_t P;
+    if (params) P = *params; else af_default_params(&P);
+    if (kp == 0) kp = 12;
+    if (P.k < 8 || P.k > 32 || kp < 8 || kp > 15 || kp > P.k || P.A <= 0 || P.B < 0 || P.X < 0) {
+        af_set_error("af_index_build: unsupported parameters (k=%d, kp=%d)", P.k, kp);
+        return AF_ERR_ARG;
+    }
+    af_index *idx = new af_index();
+    idx->P = P;
+    idx->kp = kp;
+    idx->stride = P.k - kp + 1;
+    idx->G = (int32_t)len;
+    idx->codes.resize((size_t)len);
+    for (int64_t i = 0; i < len; i++) idx->codes[(size_t)i] = af_code_of(anchor[i]);
+
+    struct Ent { uint32_t key, val; };
+    std::vector<Ent> ents;
+    int run = 0;
+    const uint32_t kmask = (1u << (2 * kp)) - 1;
+    uint32_t kf = 0, kr = 0;  // forward k'-mer (base t at bits 2t) and its reverse complement
+    for (int32_t i = 0; i < idx->G; i++) {
+        uint8_t c = idx->codes[(size_t)i];
+        if (c < 4) {
+            kf = (kf >> 2) | ((uint32_t)c << (2 * (kp - 1)));
+            kr = ((kr << 2) | (uint32_t)(3 - c)) & kmask;
+            run++;
+        } else { run = 0; kf = kr = 0; }
+        if (run >= kp) {
+            uint32_t j = (uint32_t)(i - kp + 1);
+            ents.push_back({kf, j});
+            ents.push_back({kr, (1u << 31) | j});
+        }
+    }
+    idx->n_entries = (int32_t)ents.size();
+
+    uint32_t slots = 1024;
+    while (slots < 2 * ents.size()) slots <<= 1;
+    idx->tmask = slots - 1;
+    idx->table.assign((size_t)slots * 2, AF_T_EMPTY);
+    for (const Ent &e : ents) {
+        uint32_t s = af_table_hash(e.key, idx->tmask);
+        while (idx->table[(size_t)s * 2] != AF_T_EMPTY) s = (s + 1) & idx->tmask;
+        idx->table[(size_t)s * 2] = e.key;
+        idx->table[(size_t)s * 2 + 1] = e.val;
+    }
+
+    std::vector<uint32_t> keys;
+    keys.reserve(ents.size());
+    for (const Ent &e : ents) keys.push_back(e.key);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    idx->n_keys = (int32_t)keys.size();
+
+    uint64_t want = (uint64_t)keys.size() * 4;
+    uint32_t nb = (uint32_t)std::min<uint64_t>(AF_MAX_BUCKETS, std::max<uint64_t>(AF_MIN_BUCKETS, want));
+    nb = (nb + 31u) & ~31u;
+    idx->nb = nb;
+    static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du,
+                                    0xFD7046C5u, 0xB55A4F09u, 0x8DA6B343u, 0xD8163841u, 0xCB1AB31Fu, 0x9C06FAF5u};
+    int best = -1;
+    std::vector<uint32_t> cand;
+    for (uint32_t m : muls) {
+        int ov = build_filter(keys, m, nb, cand);
+        if (best < 0 || ov < best) { best = ov; idx->fmul = m; idx->filter = cand; }
+        if (best == 0) break;
+    }
+    idx->n_overflow = best;
+
+    // 4-base pad pattern whose k'-mers (all 4 phases) are absent from the anchor, so padded
+    // tails and N positions of a read never light the filter up by themselves.
+    idx->pad_byte = 0xE4;
+    for (int t = 0; t < 256; t++) {
+        int b = (0xE4 + t * 37) & 0xFF;
+        bool clean = true;
+        for (int ph = 0; ph < 4 && clean; ph++) {
+            uint32_t key = 0;
+            for (int i = 0; i < kp; i++) key |= (uint32_t)((b >> (2 * ((i + ph) & 3))) & 3) << (2 * i);
+            clean = !std::binary_search(keys.begin(), keys.end(), key);
+        }
+        if (clean) { idx->pad_byte = b; break; }
+    }
+    *out = idx;
+    return AF_OK;
+}
+
+extern "C" void af_index_free(af_index_t *idx) { delete idx; }
+
+extern "C" int af_index_info(const af_index_t *idx, af_index_info_t *info) {
+    if (!idx || !info) { af_set_error("af_index_info: null"); return AF_ERR_ARG; }
+    info->anchor_len = idx->G; info->k = idx->P.k; info->kp = idx->kp; info->stride = idx->stride;
+    info->n_keys = idx->n_keys; info->n_entries = idx->n_entries; info->n_buckets = (int32_t)idx->nb;
+    info->n_overflow = idx->n_overflow; info->table_slots = (int32_t)(idx->tmask + 1);
+    info->filter_mul = idx->fmul; info->pad_byte = idx->pad_byte;
+    return AF_OK;
+}
+extern "C" const uint32_t *af_index_filter(const af_index_t *idx) { return idx ? idx->filter.data() : nullptr; }
+extern "C" const uint32_t *af_index_table(const af_index_t *idx) { return idx ? idx->table.data() : nullptr; }
+
+// ------------------------------------------------------------------------------------------
+// batch layout and the 2-bit packer  (replaces kseq/zlib ingest inside bwa, Anchored_Fusion.py:182)
+// ------------------------------------------------------------------------------------------
+extern "C" int af_layout(int32_t max_read_len, int64_t n_pairs, af_layout_t *out) {
+    if (!out || max_read_len <= 0 || max_read_len > AF_MAX_READ_LEN || n_pairs < 0) {
+        af_set_error("af_layout: max_read_len must be 1..%d", AF_MAX_READ_LEN);
+        return AF_ERR_ARG;
+    }
+    out->max_read_len = max_read_len;
+    out->words_per_read = (max_read_len + 15) / 16;
+    out->quads_per_pair = (2 * out->words_per_read + 3) / 4;
+    out->reserved = 0;
+    out->n_pairs = n_pairs;
+    out->n_tiles = (n_pairs + AF_TILE_PAIRS - 1) / AF_TILE_PAIRS;
+    out->packed_bytes = out->n_tiles * out->quads_per_pair * 512;
+    return AF_OK;
+}
+
+struct SeqRef { const char *p; int32_t len; };
+
+// shared by af_pack_pairs and the FASTQ reader (af_fastq.cpp)
+int af_pack_core(const SeqRef *r1, const SeqRef *r2, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte,
+                 void *packed_out, uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
+                 int64_t *n_nreads_out, int32_t *uniform_len_out) {
+    af_layout_t lay;
+    int rc = af_layout(max_read_len, n_pairs, &lay);
+    if (rc) return rc;
+    const int W = lay.words_per_read, Q = lay.quads_per_pair;
+    uint32_t *out = (uint32_t *)packed_out;
+    uint32_t padw = 0;  // 16 bases of the period-4 pad pattern
+    for (int i = 0; i < 16; i++) padw |= (uint32_t)((pad_byte >> (2 * (i & 3))) & 3) << (2 * i);
+    int64_t nn = 0;
+    int32_t ulen = -1;
+    bool uniform = true;
+    uint32_t words[2 * 16 + 4];
+    for (int64_t p = 0; p < lay.n_tiles * AF_TILE_PAIRS; p++) {
+        for (int i = 0; i < 4 * Q; i++) words[i] = i < 2 * W ? padw : 0u;
+        if (p < n_pairs) {
+            for (int m = 0; m < 2; m++) {
+                const SeqRef &s = m == 0 ? r1[p] : r2[p];
+                if (s.len > max_read_len || s.len < 0) {
+                    af_set_error("af_pack: read %lld/%d has %d bases, max_read_len is %d", (long long)p, m + 1, s.len, max_read_len);
+                    return AF_ERR_ARG;
+                }
+                if (ulen < 0) ulen = s.len; else if (ulen != s.len) uniform = false;
+                if (lens_out) lens_out[2 * p + m] = (uint16_t)s.len;
+                uint32_t *w = words + m * W;
+                uint32_t nm[AF_NMASK_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+                bool hasn = false;
+                for (int32_t i = 0; i < s.len; i++) {
+                    uint8_t c = af_code_of(s.p[i]);
+                    if (c == 4) { hasn = true; nm[i >> 5] |= 1u << (i & 31); continue; }  // keeps the pad base
+                    int sh = 2 * (i & 15);
+                    w[i >> 4] = (w[i >> 4] & ~(3u << sh)) | ((uint32_t)c << sh);
+                }
+                if (hasn) {
+                    if (nn >= ncap || !nread_ids_out || !nmask_out) { af_set_error("af_pack: N-read list capacity %lld exceeded", (long long)ncap); return AF_ERR_CAPACITY; }
+                    nread_ids_out[nn] = (uint32_t)(2 * p + m);
+                    memcpy(nmask_out + nn * AF_NMASK_WORDS, nm, sizeof(nm));
+                    nn++;
+                }
+            }
+        }
+        int64_t tile = p >> 5, lane = p & 31;
+        for (int q = 0; q < Q; q++)
+            memcpy(out + ((tile * Q + q) * 32 + lane) * 4, words + 4 * q, 16);
+    }
+    if (n_nreads_out) *n_nreads_out = nn;
+    if (uniform_len_out) *uniform_len_out = (uniform && ulen > 0) ? ulen : 0;
+    return AF_OK;
+}
+
+extern "C" int af_pack_pairs(const char *seq1, const int64_t *off1, const char *seq2, const int64_t *off2,
+                             int64_t n_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
+                             uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
+                             int64_t *n_nreads_out, int32_t *uniform_len_out) {
+    if (n_pairs < 0 || (n_pairs && (!seq1 || !seq2 || !off1 || !off2)) || !packed_out) { af_set_error("af_pack_pairs: null argument"); return AF_ERR_ARG; }
+    std::vector<SeqRef> r1((size_t)n_pairs), r2((size_t)n_pairs);
+    for (int64_t i = 0; i < n_pairs; i++) {
+        r1[(size_t)i] = {seq1 + off1[i], (int32_t)(off1[i + 1] - off1[i])};
+        r2[(size_t)i] = {seq2 + off2[i], (int32_t)(off2[i + 1] - off2[i])};
+    }
+    return af_pack_core(r1.data(), r2.data(), n_pairs, max_read_len, pad_byte, packed_out, lens_out, nread_ids_out,
+                        nmask_out, ncap, n_nreads_out, uniform_len_out);
+}
+
+extern "C" int af_unpack_read(const void *packed, int32_t max_read_len, int64_t read_id, int32_t len, uint8_t *codes_out) {
+    af_layout_t lay;
+    int rc = af_layout(max_read_len, 0, &lay);
+    if (rc) return rc;
+    if (!packed || !codes_out || len < 0 || len > max_read_len) { af_set_error("af_unpack_read: bad argument"); return AF_ERR_ARG; }
+    const uint32_t *in = (const uint32_t *)packed;
+    int64_t p = read_id >> 1, tile = p >> 5, lane = p & 31;
+    int m = (int)(read_id & 1), W = lay.words_per_read, Q = lay.quads_per_pair;
+    for (int32_t i = 0; i < len; i++) {
+        int wi = m * W + (i >> 4);
+        uint32_t w = in[((tile * Q + (wi >> 2)) * 32 + lane) * 4 + (wi & 3)];
+        codes_out[i] = (uint8_t)((w >> (2 * (i & 15))) & 3);
+    }
+    return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic reads, host twin of the device generator (the reference's own
+// recipe, utils/simulate_reads.py:20, shells out to wgsim, which is absent)
+// ------------------------------------------------------------------------------------------
+static int check_synth(const af_synth_t *s) {
+    if (!s || s->ref_len < 4096 || s->anchor_len <= 0 || s->anchor_start < 0 ||
+        s->anchor_start + s->anchor_len > s->ref_len || s->read_len <= 0 || s->read_len > AF_MAX_READ_LEN ||
+        s->frag_mean < s->read_len || s->frag_sd < 0) {
+        af_set_error("af_synth: bad generator description");
+        return AF_ERR_ARG;
+    }
+    return AF_OK;
+}
+
+extern "C" int af_synth_anchor(const af_synth_t *s, char *ascii_out) {
+    int rc = check_synth(s);
+    if (rc) return rc;
+    for (int32_t i = 0; i < s->anchor_len; i++) ascii_out[i] = "ACGT"[af_ref_base(s->seed, s->anchor_start + i)];
+    return AF_OK;
+}
+
+extern "C" int af_synth_pairs_host(const af_synth_t *s, int64_t first_pair, int64_t n_pairs, uint8_t *mate1, uint8_t *mate2) {
+    int rc = check_synth(s);
+    if (rc) return rc;
+    const int L = s->read_len;
+    for (int64_t p = 0; p < n_pairs; p++) {
+        af_frag f = af_make_frag(*s, first_pair + p);
+        for (int i = 0; i < L; i++) {
+            mate1[p * L + i] = (uint8_t)af_read_base(*s, f, 0, i);
+            mate2[p * L + i] = (uint8_t)af_read_base(*s, f, 1, i);
+        }
+    }
+    return AF_OK;
+}

@@ -1,0 +1,686 @@
+// af_kernels.cu -- sm_100a kernels of the read-anchoring path and their stream-ordered drivers.
+//
+//   k_seed_scan      HBM-bound filter: streams the 2-bit packed tiles with coalesced 128-bit
+//                    loads, cuts every read into k'-mers at stride s (k'+s-1 <= k, so every exact
+//                    match of >= k bases contains one), probes a shared-memory fingerprint table
+//                    of the anchor's k'-mers (both strands), ballots one flag word per 32 reads.
+//                    No false negatives; false positives are removed by k_extend.
+//   k_flag_count /   ballot + prefix-sum stream compaction of the flag words into a candidate
+//   k_flag_scatter   read list ordered by read_id.
+//   k_extend         one warp per candidate: exact k'-mer table lookups (lanes = sample
+//                    positions), match_any de-duplication of diagonals, 256-bit match masks by
+//                    ballot, leftmost >=k run, X-drop extension with warp prefix-max scans.
+//   k_hit_count /    compaction of the per-candidate result slots into the hit list.
+//   k_hit_scatter
+//   k_synth_pairs    seeded synthetic read pairs written straight into packed tiles.
+//
+// Stands in for `bwa mem -M ... | samtools view -F 772` (Anchored_Fusion.py:182,194); the
+// semantics are "Anchoring spec v1" in DESIGN.md, restated on the CPU in oracle/af_oracle.c.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "af_common.h"
+
+#define FULL 0xFFFFFFFFu
+
+static std::atomic<long long> g_launches{0};
+extern "C" int64_t af_kernel_launches(void) { return (int64_t)g_launches.load(); }
+
+#define AF_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            af_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return AF_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+struct af_dev_index {
+    int device;
+    af_params_t P;
+    int32_t kp, stride, G;
+    uint32_t fmul, nb, tmask;
+    uint32_t *d_filter;  // nb words
+    uint2 *d_table;      // tmask+1 entries {key, value}
+    uint8_t *d_anchor;   // G base codes
+    int pad_byte;
+    int num_sms;
+};
+
+// ------------------------------------------------------------------------------------------
+// seed scan
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// All sample positions of one read held in registers w[OFF..OFF+W).  Fully unrolled: every
+// shift and word index is a compile-time constant.
+template <int W, int KP, int OFF, int NW>
+__device__ __forceinline__ uint32_t scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt,
+                                              uint32_t fmul, uint32_t nb) {
+    constexpr int S = 20 - KP;  // k = 19
+    constexpr uint32_t KMASK = (KP == 16) ? 0xFFFFFFFFu : ((1u << (2 * KP)) - 1u);
+    constexpr int NP = (16 * W - KP) / S + 1;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        if (j < nprobe) {
+            const int o = 2 * j * S, wi = o >> 5, sh = o & 31;
+            uint32_t x;
+            if (sh + 2 * KP <= 32) x = (w[OFF + wi] >> sh) & KMASK;
+            else x = __funnelshift_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh) & KMASK;
+            uint32_t b, fp3;
+            af_filter_hash(x, fmul, nb, b, fp3);
+            acc |= af_filter_test(filt[b], fp3);
+        }
+    }
+    return acc;
+}
+
+template <int W, int KP>
+__global__ void __launch_bounds__(1024, 1)
+k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, int nprobe, const uint32_t *__restrict__ g_filter,
+            uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags) {
+    extern __shared__ uint32_t filt[];
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) filt[i] = g_filter[i];
+    __syncthreads();
+    constexpr int Q = (2 * W + 3) / 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const long long stride = (long long)gridDim.x * nwarps;
+    for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < n_tiles; tile += stride) {
+        uint32_t w[4 * Q];
+        const uint4 *src = packed + tile * (Q * 32) + lane;
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            uint4 v = ld_stream_v4(src + q * 32);
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+        uint32_t a1 = scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
+        uint32_t a2 = scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
+        uint32_t b1 = __ballot_sync(FULL, a1 != 0), b2 = __ballot_sync(FULL, a2 != 0);
+        if (lane == 0) flags[tile] = make_uint2(b1, b2);
+    }
+}
+
+static int g_scan_threads = 1024;
+extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t /*blocks_per_sm*/) {
+    if (threads_per_block == 0) threads_per_block = 1024;
+    if (threads_per_block < 64 || threads_per_block > 1024 || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..1024, multiple of 32"); return AF_ERR_ARG; }
+    g_scan_threads = threads_per_block;
+    return AF_OK;
+}
+
+template <int W, int KP>
+static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
+                       cudaStream_t st) {
+    size_t smem = (size_t)d->nb * 4;
+    static bool attr_set[64] = {false};  // per device
+    if (!attr_set[d->device & 63]) {
+        AF_CUDA(cudaFuncSetAttribute(k_seed_scan<W, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[d->device & 63] = true;
+    }
+    int nwarps = g_scan_threads / 32;
+    long long want = (n_tiles + nwarps - 1) / nwarps;
+    int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
+    k_seed_scan<W, KP><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, nprobe, d->d_filter,
+                                                           d->fmul, d->nb, (uint2 *)flags);
+    g_launches++;
+    AF_CUDA(cudaGetLastError());
+    return AF_OK;
+}
+
+#define AF_SCAN_CASE(WW)                                                                       \
+    case WW:                                                                                   \
+        return kp == 12 ? launch_scan<WW, 12>(d, b, n_tiles, nprobe, flags, st)                \
+                        : launch_scan<WW, 13>(d, b, n_tiles, nprobe, flags, st);
+
+static int batch_check(const af_dev_index *d, const af_batch_t *b, af_layout_t *lay) {
+    if (!d || !b) { af_set_error("null index or batch"); return AF_ERR_ARG; }
+    int rc = af_layout(b->max_read_len, b->n_pairs, lay);
+    if (rc) return rc;
+    if (b->n_pairs >= (1ll << 31)) { af_set_error("a batch holds at most 2^31-1 pairs"); return AF_ERR_ARG; }
+    if (b->n_pairs && !b->packed) { af_set_error("batch.packed is null"); return AF_ERR_ARG; }
+    if (b->uniform_len <= 0 && !b->lens && b->n_pairs) { af_set_error("batch needs uniform_len or lens"); return AF_ERR_ARG; }
+    if (b->uniform_len > b->max_read_len) { af_set_error("uniform_len exceeds max_read_len"); return AF_ERR_ARG; }
+    return AF_OK;
+}
+
+static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *flags, cudaStream_t st) {
+    af_layout_t lay;
+    int rc = batch_check(d, b, &lay);
+    if (rc) return rc;
+    if (lay.n_tiles == 0) return AF_OK;
+    const int kp = d->kp;
+    if (d->P.k != 19 || (kp != 12 && kp != 13)) { af_set_error("seed scan is built for k=19, k' in {12,13}"); return AF_ERR_ARG; }
+    // sample positions p = j*s with p + k' <= L (L = longest read of the batch)
+    int L = b->uniform_len > 0 ? b->uniform_len : b->max_read_len;
+    int nprobe = L >= kp ? (L - kp) / d->stride + 1 : 0;
+    long long n_tiles = lay.n_tiles;
+    switch (lay.words_per_read) {
+        AF_SCAN_CASE(1) AF_SCAN_CASE(2) AF_SCAN_CASE(3) AF_SCAN_CASE(4) AF_SCAN_CASE(5) AF_SCAN_CASE(6)
+        AF_SCAN_CASE(7) AF_SCAN_CASE(8) AF_SCAN_CASE(9) AF_SCAN_CASE(10) AF_SCAN_CASE(11) AF_SCAN_CASE(12)
+        AF_SCAN_CASE(13) AF_SCAN_CASE(14) AF_SCAN_CASE(15) AF_SCAN_CASE(16)
+    }
+    af_set_error("unsupported words_per_read %d", lay.words_per_read);
+    return AF_ERR_ARG;
+}
+
+extern "C" int af_seed_scan(const af_dev_index_t *d, const af_batch_t *batch, uint32_t *d_flags, void *stream) {
+    AF_CUDA(cudaSetDevice(d ? d->device : 0));
+    return seed_scan_impl(d, batch, d_flags, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// stream compaction (ballot / popc / prefix sums); deterministic, ordered by read_id
+// ------------------------------------------------------------------------------------------
+static const int CB_THREADS = 256, CB_ITEMS = 8, CB_PER_BLOCK = CB_THREADS * CB_ITEMS;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *smem /*>=9 words*/, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = lane < (CB_THREADS / 32) ? smem[lane] : 0, si = s;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { uint32_t t = __shfl_up_sync(FULL, si, o); if (lane >= o) si += t; }
+        if (lane < (CB_THREADS / 32)) smem[lane] = si - s;
+        if (lane == (CB_THREADS / 32) - 1) smem[8] = si;
+    }
+    __syncthreads();
+    total = smem[8];
+    uint32_t r = smem[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ uint32_t tile_valid_mask(long long tile, long long n_pairs) {
+    long long left = n_pairs - tile * 32;
+    return left >= 32 ? FULL : (left <= 0 ? 0u : ((1u << left) - 1u));
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+k_flag_count(const uint2 *__restrict__ flags, long long n_tiles, long long n_pairs, uint32_t *__restrict__ blk_counts,
+             uint32_t *__restrict__ counts) {
+    __shared__ uint32_t sm[9];
+    uint32_t c = 0;
+    long long t0 = (long long)blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
+#pragma unroll
+    for (int i = 0; i < CB_ITEMS; i++) {
+        long long t = t0 + i;
+        if (t < n_tiles) { uint2 f = flags[t]; uint32_t vm = tile_valid_mask(t, n_pairs); c += __popc(f.x & vm) + __popc(f.y & vm); }
+    }
+    uint32_t total;
+    block_excl_scan(c, sm, total);
+    if (threadIdx.x == 0) { blk_counts[blockIdx.x] = total; atomicAdd(&counts[AF_CNT_FLAGGED], total); }
+}
+
+__device__ __forceinline__ uint32_t sum_before(const uint32_t *blk_counts, int upto, uint32_t *sm) {
+    uint32_t s = 0;
+    for (int i = threadIdx.x; i < upto; i += blockDim.x) s += blk_counts[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    uint32_t r = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) r += sm[i];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+k_flag_scatter(const uint2 *__restrict__ flags, long long n_tiles, long long n_pairs,
+               const uint32_t *__restrict__ blk_counts, uint32_t *__restrict__ cand, uint32_t cand_cap,
+               uint32_t *__restrict__ counts) {
+    __shared__ uint32_t sm[9];
+    uint32_t base = sum_before(blk_counts, blockIdx.x, sm);
+    uint2 f[CB_ITEMS];
+    uint32_t c = 0;
+    long long t0 = (long long)blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
+#pragma unroll
+    for (int i = 0; i < CB_ITEMS; i++) {
+        long long t = t0 + i;
+        f[i] = make_uint2(0, 0);
+        if (t < n_tiles) { uint2 v = flags[t]; uint32_t vm = tile_valid_mask(t, n_pairs); f[i] = make_uint2(v.x & vm, v.y & vm); }
+        c += __popc(f[i].x) + __popc(f[i].y);
+    }
+    uint32_t total, off = base + block_excl_scan(c, sm, total);
+    bool over = false;
+#pragma unroll
+    for (int i = 0; i < CB_ITEMS; i++) {
+        uint32_t any = f[i].x | f[i].y;
+        while (any) {
+            int l = __ffs(any) - 1;
+            any &= any - 1;
+            uint32_t pair = (uint32_t)((t0 + i) * 32 + l);
+            if ((f[i].x >> l) & 1) { if (off < cand_cap) cand[off] = pair * 2; else over = true; off++; }
+            if ((f[i].y >> l) & 1) { if (off < cand_cap) cand[off] = pair * 2 + 1; else over = true; off++; }
+        }
+    }
+    if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_CAND_OVERFLOW);
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+k_hit_count(const uint4 *__restrict__ slots, uint32_t cand_cap, uint32_t *__restrict__ blk_counts, uint32_t *counts) {
+    __shared__ uint32_t sm[9];
+    uint32_t n = min(counts[AF_CNT_FLAGGED], cand_cap), c = 0;
+    uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
+    if (blockIdx.x * CB_PER_BLOCK < n) {
+#pragma unroll
+        for (int i = 0; i < CB_ITEMS; i++)
+            if (i0 + i < n) c += (slots[i0 + i].z >> 16) != 0;  // m_len
+    }
+    uint32_t total;
+    block_excl_scan(c, sm, total);
+    if (threadIdx.x == 0) { blk_counts[blockIdx.x] = total; if (total) atomicAdd(&counts[AF_CNT_HITS], total); }
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cand_cap, const uint32_t *__restrict__ blk_counts,
+              uint4 *__restrict__ hits, uint32_t hits_cap, uint32_t *counts) {
+    __shared__ uint32_t sm[9];
+    uint32_t n = min(counts[AF_CNT_FLAGGED], cand_cap);
+    if (blockIdx.x * CB_PER_BLOCK >= n) return;
+    uint32_t base = sum_before(blk_counts, blockIdx.x, sm);
+    uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS, c = 0;
+    uint4 v[CB_ITEMS];
+#pragma unroll
+    for (int i = 0; i < CB_ITEMS; i++) {
+        v[i] = make_uint4(0, 0, 0, 0);
+        if (i0 + i < n) v[i] = slots[i0 + i];
+        c += (v[i].z >> 16) != 0;
+    }
+    uint32_t total, off = base + block_excl_scan(c, sm, total);
+    bool over = false;
+#pragma unroll
+    for (int i = 0; i < CB_ITEMS; i++)
+        if ((v[i].z >> 16) != 0) { if (off < hits_cap) hits[off] = v[i]; else over = true; off++; }
+    if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
+}
+
+// ------------------------------------------------------------------------------------------
+// verify + extend: one warp per candidate read
+// ------------------------------------------------------------------------------------------
+struct ExtParams {
+    int k, A, B, clip5, clip3, T, X;
+};
+
+#define NEG_INF (-(1 << 29))
+
+// number of set mask bits in positions [0, x), x in [0, 256]; lane t holds word t (mw) and the
+// count of set bits in words < t (cp); lanes >= 8 hold mw = 0, cp = total.
+__device__ __forceinline__ int mask_cum(uint32_t mw, uint32_t cp, int x) {
+    int wi = x >> 5;
+    uint32_t wv = __shfl_sync(FULL, mw, wi), cv = __shfl_sync(FULL, cp, wi);
+    return (int)cv + __popc(wv & ((1u << (x & 31)) - 1u));
+}
+
+// One direction of the ungapped X-drop extension over mask positions start, start+dir, ...
+// (n steps).  Lane = step within a 32-step chunk; scores come from popcounts of the match
+// mask, the running maximum from a warp prefix-max scan.  Mirrors `extend` in the oracle.
+__device__ __forceinline__ void extend_dir(uint32_t mw, uint32_t cp, int start, int dir, int n, int qlen, int h0,
+                                           const ExtParams &P, int lane, int &mx_out, int &off_out, int &g_out) {
+    int mx = h0, off = 0, g = -1;
+    const int base_cum = dir > 0 ? mask_cum(mw, cp, start) : mask_cum(mw, cp, start + 1);
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        const bool valid = j < n;
+        const int jj = valid ? j : 0, pos = start + dir * jj;
+        const int c = mask_cum(mw, cp, dir > 0 ? pos + 1 : pos);
+        const int ones = dir > 0 ? c - base_cum : base_cum - c;
+        int Pj = h0 + P.A * (jj + 1) - (P.A + P.B) * ((jj + 1) - ones);
+        if (!valid) Pj = NEG_INF;
+        const bool dead = valid && Pj <= 0;
+        int pm = Pj;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pm, o); if (lane >= o) pm = max(pm, t); }
+        const int Mj = max(pm, mx);
+        const bool xd = valid && (Mj - Pj > P.X);
+        const uint32_t bd = __ballot_sync(FULL, dead), bx = __ballot_sync(FULL, xd);
+        int endlane = min(32, n - j0);
+        bool stop = false;
+        if (bd) { endlane = min(endlane, __ffs(bd) - 1); stop = true; }
+        if (bx) { endlane = min(endlane, __ffs(bx)); stop = true; }   // the x-drop step itself is processed
+        const bool processed = lane < endlane;
+        int cm = processed ? Pj : NEG_INF;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) cm = max(cm, __shfl_xor_sync(FULL, cm, o));
+        if (cm > mx) {
+            const uint32_t be = __ballot_sync(FULL, processed && Pj == cm);
+            mx = cm;
+            off = j0 + __ffs(be);
+        }
+        if (n == qlen) {
+            const int gl = qlen - 1 - j0;
+            if (gl >= 0 && gl < endlane) g = __shfl_sync(FULL, Pj, gl);
+        }
+        if (stop) break;
+    }
+    mx_out = mx; off_out = off; g_out = g;
+}
+
+// Evaluate diagonal (s, d) of the read held by the warp.  Returns the score or -1 if the
+// diagonal holds no run of k matches.  rw: lane t < W holds packed word t of the read;
+// nw: lane t < 8 holds N-mask word t.
+__device__ __forceinline__ int eval_diag(int s, int d, int L, uint32_t rw, uint32_t nw, bool has_n,
+                                         const uint8_t *__restrict__ anchor, int G, const ExtParams &P, int lane,
+                                         int &qb_out, int &qe_out) {
+    // 256-bit match mask, 32 positions per ballot
+    uint32_t mw = 0;
+    const int nchunks = (L + 31) >> 5;
+    for (int c = 0; c < nchunks; c++) {
+        const int i = c * 32 + lane;
+        const int fi = min(max(s ? L - 1 - i : i, 0), AF_MAX_READ_LEN - 1);   // position in the stored read
+        uint32_t word = __shfl_sync(FULL, rw, fi >> 4);
+        uint32_t base = (word >> (2 * (fi & 15))) & 3u;
+        if (s) base = 3u - base;
+        bool isn = false;
+        if (has_n) { uint32_t nword = __shfl_sync(FULL, nw, fi >> 5); isn = (nword >> (fi & 31)) & 1u; }
+        const int ap = i + d;
+        bool m = false;
+        if (i < L && ap >= 0 && ap < G && !isn) m = anchor[ap] == base;
+        const uint32_t bal = __ballot_sync(FULL, m);
+        if (lane == c) mw = bal;
+    }
+    uint32_t pc = __popc(mw), cp = pc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL, cp, o); if (lane >= o) cp += t; }
+    cp -= pc;  // exclusive: set bits in words before this lane's word
+
+    // leftmost run of k matches
+    const uint32_t kmask = P.k >= 32 ? FULL : ((1u << P.k) - 1u);
+    int qb0 = -1;
+    for (int c = 0; c < nchunks && qb0 < 0; c++) {
+        uint32_t w0 = __shfl_sync(FULL, mw, c), w1 = __shfl_sync(FULL, mw, c + 1);
+        // bits i .. i+31 of the mask, i = c*32 + lane; a run of k <= 32 fits
+        uint32_t win = __funnelshift_r(w0, w1, lane);
+        uint32_t b = __ballot_sync(FULL, (win & kmask) == kmask);
+        if (b) qb0 = c * 32 + __ffs(b) - 1;
+    }
+    if (qb0 < 0 || qb0 + P.k > L) return -1;
+
+    int sc = P.k * P.A, qb = 0, qe = L, mx, off, g;
+    if (qb0 > 0) {
+        const int n = min(qb0, qb0 + d);
+        extend_dir(mw, cp, qb0 - 1, -1, n, qb0, sc, P, lane, mx, off, g);
+        if (g <= 0 || g <= mx - P.clip5) { qb = qb0 - off; sc = mx; } else { qb = 0; sc = g; }
+    }
+    const int qe0 = qb0 + P.k;
+    if (qe0 < L) {
+        const int n = min(L - qe0, G - (qe0 + d));
+        extend_dir(mw, cp, qe0, +1, n, L - qe0, sc, P, lane, mx, off, g);
+        if (g <= 0 || g <= mx - P.clip3) { qe = qe0 + off; sc = mx; } else { qe = L; sc = g; }
+    }
+    qb_out = qb; qe_out = qe;
+    return sc;
+}
+
+__global__ void __launch_bounds__(256)
+k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, const uint16_t *__restrict__ lens,
+         const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
+         const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts, uint32_t cand_cap,
+         const uint2 *__restrict__ table, uint32_t tmask, const uint8_t *__restrict__ anchor, int G, int KP, int S,
+         ExtParams P, uint4 *__restrict__ slots) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t ncand = min(counts[AF_CNT_FLAGGED], cand_cap);
+    const uint32_t kpmask = (1u << (2 * KP)) - 1u;
+    for (uint32_t c = gw; c < ncand; c += nw_total) {
+        const uint32_t rid = cand[c];
+        const uint32_t pair = rid >> 1, mate = rid & 1u;
+        const int L = uniform_len > 0 ? uniform_len : (int)lens[rid];
+        // the read's packed words: lane t < W holds word t (tile-interleaved layout)
+        uint32_t rw = 0;
+        if (lane < W) {
+            const uint32_t wi = mate * W + lane;
+            rw = packed[(((size_t)(pair >> 5) * Q + (wi >> 2)) * 32 + (pair & 31)) * 4 + (wi & 3)];
+        }
+        // N mask: binary search of the sorted N-read list (uniform across the warp)
+        uint32_t nwv = 0;
+        bool has_n = false;
+        if (n_nreads > 0) {
+            int lo = 0, hi = n_nreads;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
+            if (lo < n_nreads && nread_ids[lo] == rid) { has_n = true; if (lane < AF_NMASK_WORDS) nwv = nmask[(size_t)lo * AF_NMASK_WORDS + lane]; }
+        }
+        int best_sc = -1, best_qb = 0, best_qe = 0;
+        uint32_t best_key = 0xFFFFFFFFu;
+        const int nprobe = L >= KP ? (L - KP) / S + 1 : 0;
+        for (int p0 = 0; p0 < nprobe; p0 += 32) {
+            const int pi = p0 + lane, p = pi * S;
+            bool active = pi < nprobe;
+            // this lane's k'-mer (forward read orientation)
+            const int o = 2 * (active ? p : 0), wi = o >> 5;
+            uint32_t w0 = __shfl_sync(FULL, rw, wi), w1 = __shfl_sync(FULL, rw, min(wi + 1, 31));
+            const uint32_t key = __funnelshift_r(w0, w1, o & 31) & kpmask;
+            if (has_n) {
+                const int q = active ? p : 0;
+                uint32_t n0 = __shfl_sync(FULL, nwv, q >> 5), n1 = __shfl_sync(FULL, nwv, min((q >> 5) + 1, 31));
+                if (__funnelshift_r(n0, n1, q & 31) & ((1u << KP) - 1u)) active = false;  // k'-mer overlaps an N
+            }
+            uint32_t slot = af_table_hash(key, tmask), val = 0;
+            bool found = false;
+            // advance to this lane's next table entry with the same key
+            auto next_match = [&]() {
+                found = false;
+                while (active) {
+                    uint2 e = table[slot];
+                    slot = (slot + 1) & tmask;
+                    if (e.x == AF_T_EMPTY) { active = false; break; }
+                    if (e.x == key) { found = true; val = e.y; break; }
+                }
+            };
+            next_match();
+            uint32_t fm;
+            while ((fm = __ballot_sync(FULL, found)) != 0) {
+                uint32_t dkey = 0;
+                bool leader = false;
+                if (found) {
+                    const int s = val >> 31, j = (int)(val & 0x7FFFFFFFu);
+                    const int d = j - (s ? L - p - KP : p);
+                    dkey = ((uint32_t)s << 31) | (uint32_t)(d + 1024);
+                    uint32_t grp = __match_any_sync(fm, dkey);
+                    leader = (__ffs(grp) - 1) == lane;
+                }
+                uint32_t leaders = __ballot_sync(FULL, leader);
+                while (leaders) {
+                    const int src = __ffs(leaders) - 1;
+                    leaders &= leaders - 1;
+                    const uint32_t dk = __shfl_sync(FULL, dkey, src);
+                    const int s = dk >> 31, d = (int)(dk & 0x7FFFFFFFu) - 1024;
+                    int qb, qe;
+                    const int sc = eval_diag(s, d, L, rw, nwv, has_n, anchor, G, P, lane, qb, qe);
+                    if (sc > best_sc || (sc == best_sc && sc >= 0 && dk < best_key)) { best_sc = sc; best_qb = qb; best_qe = qe; best_key = dk; }
+                }
+                if (found) next_match();
+            }
+        }
+        if (lane == 0) {
+            uint4 out = make_uint4(rid, 0, 0, 0);
+            if (best_sc >= P.T) {
+                const int s = best_key >> 31, d = (int)(best_key & 0x7FFFFFFFu) - 1024;
+                out.y = (uint32_t)(best_qb + d + 1);
+                out.z = (uint32_t)best_qb | ((uint32_t)(best_qe - best_qb) << 16);
+                out.w = (uint32_t)(L - best_qe) | ((uint32_t)(best_sc * 2 + s) << 16);
+            }
+            slots[c] = out;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the hot path on one GPU
+// ------------------------------------------------------------------------------------------
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct WsLayout { size_t flags, blk1, cand, slots, blk2, total; int nblk1, nblk2; };
+
+static WsLayout ws_layout(long long n_pairs, long long cand_cap) {
+    WsLayout w;
+    long long n_tiles = (n_pairs + 31) / 32;
+    w.nblk1 = (int)((n_tiles + CB_PER_BLOCK - 1) / CB_PER_BLOCK);
+    w.nblk2 = (int)((cand_cap + CB_PER_BLOCK - 1) / CB_PER_BLOCK);
+    size_t o = 0;
+    w.flags = o; o += align256((size_t)n_tiles * 8);
+    w.blk1 = o; o += align256((size_t)(w.nblk1 + 1) * 4);
+    w.cand = o; o += align256((size_t)cand_cap * 4);
+    w.slots = o; o += align256((size_t)cand_cap * 16);
+    w.blk2 = o; o += align256((size_t)(w.nblk2 + 1) * 4);
+    w.total = o;
+    return w;
+}
+
+extern "C" size_t af_workspace_bytes(int64_t n_pairs, int64_t cand_cap) {
+    if (n_pairs < 0 || cand_cap < 0) return 0;
+    return ws_layout(n_pairs, cand_cap).total + 256;
+}
+
+extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, void *workspace, size_t workspace_bytes,
+                               int64_t cand_cap, af_hit_t *d_hits, int64_t hits_cap, uint32_t *d_counts, void *stream) {
+    af_layout_t lay;
+    int rc = batch_check(d, b, &lay);
+    if (rc) return rc;
+    if (!workspace || !d_counts || (hits_cap > 0 && !d_hits) || cand_cap <= 0 || cand_cap >= (1ll << 32) || hits_cap < 0 || hits_cap >= (1ll << 32)) {
+        af_set_error("af_anchor_batch: bad buffers or capacities");
+        return AF_ERR_ARG;
+    }
+    if (workspace_bytes < af_workspace_bytes(b->n_pairs, cand_cap)) { af_set_error("af_anchor_batch: workspace too small"); return AF_ERR_CAPACITY; }
+    AF_CUDA(cudaSetDevice(d->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    WsLayout w = ws_layout(b->n_pairs, cand_cap);
+    uint32_t *flags = (uint32_t *)(ws + w.flags), *blk1 = (uint32_t *)(ws + w.blk1), *cand = (uint32_t *)(ws + w.cand);
+    uint32_t *blk2 = (uint32_t *)(ws + w.blk2);
+    uint4 *slots = (uint4 *)(ws + w.slots);
+    AF_CUDA(cudaMemsetAsync(d_counts, 0, AF_N_COUNTS * sizeof(uint32_t), st));
+    if (lay.n_tiles == 0) return AF_OK;
+    rc = seed_scan_impl(d, b, flags, st);
+    if (rc) return rc;
+    k_flag_count<<<w.nblk1, CB_THREADS, 0, st>>>((const uint2 *)flags, lay.n_tiles, b->n_pairs, blk1, d_counts);
+    k_flag_scatter<<<w.nblk1, CB_THREADS, 0, st>>>((const uint2 *)flags, lay.n_tiles, b->n_pairs, blk1, cand,
+                                                   (uint32_t)cand_cap, d_counts);
+    ExtParams P = {d->P.k, d->P.A, d->P.B, d->P.clip5, d->P.clip3, d->P.T, d->P.X};
+    long long warps_wanted = cand_cap < (long long)d->num_sms * 64 ? cand_cap : (long long)d->num_sms * 64;
+    int ext_blocks = (int)((warps_wanted + 7) / 8);
+    k_extend<<<ext_blocks, 256, 0, st>>>((const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair,
+                                         b->uniform_len, b->lens, b->nread_ids, b->nmask, (int)b->n_nreads, cand,
+                                         d_counts, (uint32_t)cand_cap, d->d_table, d->tmask, d->d_anchor, d->G, d->kp,
+                                         d->stride, P, slots);
+    k_hit_count<<<w.nblk2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, blk2, d_counts);
+    k_hit_scatter<<<w.nblk2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, blk2, (uint4 *)d_hits, (uint32_t)hits_cap,
+                                                  d_counts);
+    g_launches += 5;
+    AF_CUDA(cudaGetLastError());
+    return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// index upload
+// ------------------------------------------------------------------------------------------
+extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t **out) {
+    if (!idx || !out) { af_set_error("af_index_upload: null"); return AF_ERR_ARG; }
+    int ndev = 0;
+    AF_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { af_set_error("af_index_upload: device %d of %d", device, ndev); return AF_ERR_CUDA; }
+    AF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { af_set_error("af_index_upload: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return AF_ERR_CUDA; }
+    af_dev_index *d = new af_dev_index();
+    d->device = device; d->P = idx->P; d->kp = idx->kp; d->stride = idx->stride; d->G = idx->G;
+    d->fmul = idx->fmul; d->nb = idx->nb; d->tmask = idx->tmask; d->pad_byte = idx->pad_byte;
+    d->num_sms = prop.multiProcessorCount;
+    d->d_filter = nullptr; d->d_table = nullptr; d->d_anchor = nullptr;
+    cudaError_t e = cudaMalloc(&d->d_filter, idx->filter.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_table, idx->table.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_anchor, idx->codes.size() + 256);
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_filter, idx->filter.data(), idx->filter.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_table, idx->table.data(), idx->table.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_anchor, idx->codes.data(), idx->codes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        af_set_error("af_index_upload: %s", cudaGetErrorString(e));
+        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor);
+        delete d;
+        return AF_ERR_CUDA;
+    }
+    *out = d;
+    return AF_OK;
+}
+
+extern "C" int af_dev_index_device(const af_dev_index_t *d) { return d ? d->device : -1; }
+
+extern "C" void af_dev_index_free(af_dev_index_t *d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor);
+    delete d;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic pairs straight into packed tiles
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_synth_pairs(af_synth_t s, long long first_pair, long long n_pairs, long long n_tiles, int W, int Q, uint32_t padw,
+              uint4 *__restrict__ packed) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_tiles * 32) return;
+    const long long tile = p >> 5;
+    const int lane = (int)(p & 31);
+    af_frag f;
+    const bool real = p < n_pairs;
+    if (real) f = af_make_frag(s, first_pair + p);
+    for (int q = 0; q < Q; q++) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int wi = 4 * q + c;
+            uint32_t word = wi < 2 * W ? padw : 0u;
+            if (real && wi < 2 * W) {
+                const int m = wi >= W, w0 = (wi - m * W) * 16;
+                for (int i = 0; i < 16 && w0 + i < s.read_len; i++) {
+                    uint32_t b = af_read_base(s, f, m, w0 + i);
+                    word = (word & ~(3u << (2 * i))) | (b << (2 * i));
+                }
+            }
+            w4[c] = word;
+        }
+        packed[(tile * Q + q) * 32 + lane] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+}
+
+extern "C" int af_synth_pairs_device(const af_synth_t *s, int64_t first_pair, int64_t n_pairs, int32_t pad_byte,
+                                     void *d_packed, void *stream) {
+    if (!s || !d_packed || n_pairs < 0 || s->n_ppm != 0) { af_set_error("af_synth_pairs_device: bad argument (n_ppm must be 0)"); return AF_ERR_ARG; }
+    af_layout_t lay;
+    int rc = af_layout(s->read_len, n_pairs, &lay);
+    if (rc) return rc;
+    if (lay.n_tiles == 0) return AF_OK;
+    uint32_t padw = 0;
+    for (int i = 0; i < 16; i++) padw |= (uint32_t)((pad_byte >> (2 * (i & 3))) & 3) << (2 * i);
+    long long threads = lay.n_tiles * 32;
+    k_synth_pairs<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        *s, first_pair, n_pairs, lay.n_tiles, lay.words_per_read, lay.quads_per_pair, padw, (uint4 *)d_packed);
+    g_launches++;
+    AF_CUDA(cudaGetLastError());
+    return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// pinned host memory
+// ------------------------------------------------------------------------------------------
+extern "C" void *af_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { af_set_error("af_host_alloc: cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+extern "C" void af_host_free(void *p) { if (p) cudaFreeHost(p); }

@@ -1,0 +1,208 @@
+/*
+ * anchored_fusion.h -- C ABI of the B200-native read-anchoring path (libafb200.so).
+ *
+ * The reference (ShenLab-Genomics/Anchored-Fusion) has NO FFI for this path: the pass is
+ * three shell-outs in the driver scripts,
+ *     bwa index <anchor.fa>                                  Anchored_Fusion.py:167-172
+ *     bwa mem -M -t T <anchor.fa> fq1 fq2 | samtools ...     Anchored_Fusion.py:181-182
+ *     samtools view -f 8 -F 260 / -f 4 -F 264 / -F 772       Anchored_Fusion.py:186,187,194
+ * (same lines in Anchored_Fusion_singlecell.py:185-231), glued by files on disk.  The entry
+ * points below are what a binding for that path would bind; each cites the reference step it
+ * replaces.  INTEGRATION.md shows the ctypes stub and the file-level drop-in.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative af_status code, and af_last_error() gives the message (thread-local).  No
+ * exceptions cross the ABI.  There is NO CPU fallback: device entry points fail with
+ * AF_ERR_CUDA when no sm_100 device is usable.  Device entry points are stream-ordered and
+ * re-entrant per (device, stream); `stream` is a cudaStream_t passed as void*.  The caller
+ * owns every device buffer (e.g. torch tensors' data_ptr()); the library owns only the
+ * objects it returns through af_*_build / af_*_create and frees them in af_*_free.
+ */
+#ifndef ANCHORED_FUSION_H
+#define ANCHORED_FUSION_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AF_ABI_VERSION 1
+#define AF_MAX_READ_LEN 256 /* bases; 16 packed words per read */
+#define AF_TILE_PAIRS 32    /* pairs per packed tile == lanes per warp */
+#define AF_NMASK_WORDS 8    /* 256-bit N mask per read that holds an N */
+
+enum af_status {
+    AF_OK = 0,
+    AF_ERR_ARG = -1,      /* bad argument */
+    AF_ERR_CUDA = -2,     /* CUDA runtime error / no usable device */
+    AF_ERR_CAPACITY = -3, /* caller-provided buffer too small (nothing is dropped silently) */
+    AF_ERR_IO = -4,       /* file / zlib error */
+    AF_ERR_NOMEM = -5
+};
+
+/* Alignment parameters == bwa-mem defaults the reference relies on implicitly
+ * (Anchored_Fusion.py:182 passes only "-M -t"): -k 19 -A 1 -B 4 -L 5,5 -T 30 -d 100. */
+typedef struct {
+    int32_t k, A, B, clip5, clip3, T, X;
+} af_params_t;
+
+/* One anchored read == one primary mapped SAM record of `bwa mem -M | samtools view -F 772`
+ * (Anchored_Fusion.py:194): CIGAR is clip_l S, m_len M, clip_r S; pos is SAM POS (1-based,
+ * anchor-forward); strand 1 == FLAG 0x10 (SEQ reverse-complemented).  read_id = pair*2+mate.
+ * These are the fields deal_cigar (functions.py:656) / contact_reads (functions.py:917-930)
+ * turn into type SM/MS and the split point. */
+typedef struct {
+    uint32_t read_id;
+    int32_t pos;
+    uint16_t clip_l;
+    uint16_t m_len;
+    uint16_t clip_r;
+    uint16_t score_strand; /* score*2 + strand */
+} af_hit_t;
+
+typedef struct af_index af_index_t;         /* host-side anchor index */
+typedef struct af_dev_index af_dev_index_t; /* its copy in one GPU's HBM */
+typedef struct af_fastq af_fastq_t;         /* paired FASTQ(.gz) reader */
+typedef struct af_pipeline af_pipeline_t;   /* host->device streaming executor */
+
+typedef struct {
+    int32_t anchor_len;   /* G */
+    int32_t k;            /* semantic seed length (19) */
+    int32_t kp;           /* sampled k-mer length k' */
+    int32_t stride;       /* read sampling stride s, k' + s - 1 <= k */
+    int32_t n_keys;       /* distinct k'-mers over both strands */
+    int32_t n_entries;    /* (k'-mer, strand, position) occurrences */
+    int32_t n_buckets;    /* shared-memory filter buckets (4 B each) */
+    int32_t n_overflow;   /* buckets marked always-hit */
+    int32_t table_slots;  /* exact table slots (8 B each) */
+    uint32_t filter_mul;  /* multiplier chosen for the filter hash */
+    int32_t pad_byte;     /* 4-base pad pattern absent from the anchor's k'-mers */
+} af_index_info_t;
+
+/* Geometry of a packed batch.  Reads are 2 bit/base (A,C,G,T = 0..3, base i of a read in
+ * bits [2i,2i+2) of its word i/16); a pair is W words of mate 1 then W words of mate 2,
+ * zero-extended to Q 16-byte quads; tiles of 32 pairs are stored quad-interleaved:
+ * quad q of pair (tile*32 + lane) lives at ((tile*Q + q)*32 + lane)*16 bytes, so a warp's
+ * 128-bit loads are 512 contiguous bytes. */
+typedef struct {
+    int32_t max_read_len;
+    int32_t words_per_read; /* W = ceil(max_read_len/16) */
+    int32_t quads_per_pair; /* Q = ceil(2W/4) */
+    int32_t reserved;
+    int64_t n_pairs;
+    int64_t n_tiles;      /* ceil(n_pairs/32) */
+    int64_t packed_bytes; /* n_tiles * Q * 512 */
+} af_layout_t;
+
+/* A batch of read pairs.  All pointers are DEVICE pointers for af_anchor_batch and friends,
+ * HOST (ideally pinned) pointers for af_pipeline_run.  Replaces the FASTQ ingest inside
+ * `bwa mem` (Anchored_Fusion.py:182). */
+typedef struct {
+    const void *packed;        /* packed_bytes of af_layout(max_read_len, n_pairs) */
+    int64_t n_pairs;
+    int32_t max_read_len;
+    int32_t uniform_len;       /* > 0: every read has this length and lens is ignored */
+    const uint16_t *lens;      /* [2*n_pairs] by read_id, or NULL when uniform_len > 0 */
+    const uint32_t *nread_ids; /* sorted read_ids of reads holding N (packed as pad there) */
+    const uint32_t *nmask;     /* [n_nreads][AF_NMASK_WORDS], bit i set = base i is N */
+    int64_t n_nreads;
+} af_batch_t;
+
+/* counts written by af_anchor_batch (device memory, AF_N_COUNTS x uint32) */
+enum { AF_CNT_FLAGGED = 0, AF_CNT_HITS = 1, AF_CNT_STATUS = 2, AF_CNT_SEEDED = 3, AF_N_COUNTS = 8 };
+/* bits of counts[AF_CNT_STATUS] */
+#define AF_STATUS_CAND_OVERFLOW 1u
+#define AF_STATUS_HIT_OVERFLOW 2u
+
+const char *af_last_error(void);
+int af_abi_version(void);
+void af_default_params(af_params_t *p);
+
+/* ---- anchor index: replaces `bwa index <anchor.fa>` (Anchored_Fusion.py:167-172) -------- */
+/* anchor: ASCII bases (ACGT any case; anything else is N).  kp = 0 picks the default. */
+int af_index_build(const char *anchor, int64_t len, const af_params_t *params, int32_t kp, af_index_t **out);
+void af_index_free(af_index_t *idx);
+int af_index_info(const af_index_t *idx, af_index_info_t *info);
+/* raw views for tests (host memory owned by the index) */
+const uint32_t *af_index_filter(const af_index_t *idx);
+const uint32_t *af_index_table(const af_index_t *idx); /* table_slots x {key, value} */
+int af_index_upload(const af_index_t *idx, int device, af_dev_index_t **out);
+void af_dev_index_free(af_dev_index_t *d);
+int af_dev_index_device(const af_dev_index_t *d);
+
+/* ---- host ingest: replaces kseq/zlib inside bwa (Anchored_Fusion.py:182) ---------------- */
+int af_layout(int32_t max_read_len, int64_t n_pairs, af_layout_t *out);
+/* seq1/seq2: concatenated ASCII reads, off[i]..off[i+1] delimit read i (n_pairs+1 offsets).
+ * lens_out may be NULL; n-lists are filled up to ncap reads (AF_ERR_CAPACITY beyond).
+ * *uniform_len_out = common length, or 0 when lengths differ. */
+int af_pack_pairs(const char *seq1, const int64_t *off1, const char *seq2, const int64_t *off2,
+                  int64_t n_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
+                  uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
+                  int64_t *n_nreads_out, int32_t *uniform_len_out);
+/* inverse, for tests: codes 0..3 (pad bases come back as their 2-bit value) */
+int af_unpack_read(const void *packed, int32_t max_read_len, int64_t read_id, int32_t len, uint8_t *codes_out);
+
+/* paired FASTQ / FASTQ.gz reader (zlib), two decode threads.  Text of the current batch stays
+ * valid until the next af_fastq_next on the same reader. */
+int af_fastq_open(const char *path1, const char *path2, af_fastq_t **out);
+void af_fastq_close(af_fastq_t *fq);
+/* Reads up to max_pairs pairs; packs them like af_pack_pairs.  *n_pairs_out = 0 at EOF. */
+int af_fastq_next(af_fastq_t *fq, int64_t max_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
+                  uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
+                  int64_t *n_nreads_out, int32_t *uniform_len_out, int64_t *n_pairs_out);
+/* record text of read_id of the current batch: name (up to first blank, /1 /2 stripped as bwa
+ * does), bases, qualities.  Pointers are not NUL-terminated. */
+int af_fastq_record(const af_fastq_t *fq, int64_t read_id, const char **name, int32_t *name_len,
+                    const char **seq, const char **qual, int32_t *len);
+
+/* ---- the hot path on one GPU: replaces `bwa mem -M | samtools view -F 772` -------------- */
+size_t af_workspace_bytes(int64_t n_pairs, int64_t cand_cap);
+/* scan -> compact -> verify -> compact -> extend -> compact, all on `stream`, no host sync.
+ * d_hits[0..counts[AF_CNT_HITS]) come back ordered by read_id. */
+int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *batch, void *workspace, size_t workspace_bytes,
+                    int64_t cand_cap, af_hit_t *d_hits, int64_t hits_cap, uint32_t *d_counts, void *stream);
+/* the stages, exposed for tests, profiling and the roofline measurement */
+int af_seed_scan(const af_dev_index_t *d, const af_batch_t *batch, uint32_t *d_flags /*2 words per tile*/,
+                 void *stream);
+int af_seed_scan_config(int32_t threads_per_block, int32_t blocks_per_sm); /* tuning knob; 0 = default */
+int64_t af_kernel_launches(void); /* kernels this library has launched since it was loaded */
+
+/* ---- host->device streaming executor (pinned staging, cudaMemcpyAsync, N slots) --------- */
+int af_pipeline_create(const af_dev_index_t *d, int64_t slot_pairs, int32_t max_read_len, int32_t n_slots,
+                       af_pipeline_t **out);
+void af_pipeline_free(af_pipeline_t *p);
+/* Anchors a HOST batch of any size: splits it into slot_pairs chunks (tile-aligned), copies
+ * each with cudaMemcpyAsync, runs the kernels, copies the hits back.  h_hits ordered by
+ * read_id; read_ids are relative to the batch. */
+int af_pipeline_run(af_pipeline_t *p, const af_batch_t *host_batch, af_hit_t *h_hits, int64_t hits_cap,
+                    int64_t *n_hits_out, int64_t *n_flagged_out);
+int64_t af_pipeline_launches(const af_pipeline_t *p); /* kernels launched so far */
+void *af_host_alloc(size_t bytes);                    /* cudaHostAlloc (pinned) */
+void af_host_free(void *p);
+
+/* ---- seeded synthetic reads (measurement) --------------------------------- */
+typedef struct {
+    uint64_t seed;
+    int64_t ref_len;       /* random reference, base x = f(seed, x) */
+    int64_t anchor_start;  /* anchor = ref[anchor_start, anchor_start+anchor_len) */
+    int32_t anchor_len;
+    int32_t read_len;
+    int32_t frag_mean, frag_sd;
+    uint32_t sub_ppm;      /* per-base substitution rate, parts per million */
+    uint32_t fusion_ppm;   /* fraction of fragments that are anchor|elsewhere chimeras */
+    uint32_t n_ppm;        /* per-base N rate (host generator only) */
+    uint32_t reserved;
+} af_synth_t;
+int af_synth_anchor(const af_synth_t *s, char *ascii_out);
+/* codes (0..4), n_pairs x read_len each */
+int af_synth_pairs_host(const af_synth_t *s, int64_t first_pair, int64_t n_pairs, uint8_t *mate1, uint8_t *mate2);
+/* packed tiles straight into HBM (n_ppm must be 0); pair p of the batch = global pair first_pair + p */
+int af_synth_pairs_device(const af_synth_t *s, int64_t first_pair, int64_t n_pairs, int32_t pad_byte,
+                          void *d_packed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,147 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle.
+Bit-exact (integer records), on the bundled sample, on seeded synthetic pairs and on edge cases."""
+import numpy as np
+import pytest
+
+from conftest import hits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _interleave(m1, m2):
+    r = np.empty((2 * m1.shape[0], m1.shape[1]), dtype=np.uint8)
+    r[0::2], r[1::2] = m1, m2
+    return r
+
+
+@pytest.fixture(scope="module")
+def af():
+    import torch
+    assert torch.cuda.is_available()
+    import anchored_fusion_b200 as af
+    return af
+
+
+@pytest.mark.parametrize("kp", [12, 13])
+def test_bundled_sample_matches_oracle(af, bundled, kp):
+    """config 1: test/target_gene.fasta + test/test_sample_{1,2}.fastq.gz (11 258 pairs, 2x101)."""
+    from oracle import oracle
+    index = af.AnchorIndex(bundled["anchor"], kp=kp)
+    eng = af.Anchorer(index, 0)
+    host = af.pack_pairs(bundled["seqs1"], bundled["seqs2"], pad_byte=index.pad_byte)
+    hits, stats = eng.anchor(host.to_device(0))
+    assert hits_equal(hits, bundled["oracle_hits"])           # committed golden of the frozen oracle
+    live = oracle.anchor_reads(oracle.encode(bundled["anchor"]), bundled["codes"], threads=4)
+    assert hits_equal(hits, live)
+    assert stats["flagged"] >= len(hits)
+    # wgsim names carry the truth: only EU216071.1 (BCR-ABL1) fragments can anchor to BCR
+    for rid in hits["read_id"]:
+        assert bundled["names1"][rid >> 1].startswith("EU216071.1")
+
+
+def test_device_generator_matches_host_generator(af):
+    spec = af.synth_spec(seed=11, ref_len=100_000, anchor_start=20_000, anchor_len=5000, read_len=150,
+                         sub_ppm=20_000, fusion_ppm=50_000)
+    index = af.AnchorIndex(af.synth_anchor(spec))
+    n = 1000 + 7
+    dev = af.synth_pairs_device(spec, 123, n, index.pad_byte, 0)
+    m1, m2 = af.synth_pairs_host(spec, 123, n)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    host = af.pack_pairs([lut[r].tobytes() for r in m1], [lut[r].tobytes() for r in m2], pad_byte=index.pad_byte)
+    assert np.array_equal(dev.packed.cpu().numpy().view(np.uint32), host.packed)
+
+
+@pytest.mark.parametrize("read_len,kp,n", [(150, 12, 200_000), (101, 12, 50_000), (150, 13, 50_000),
+                                           (250, 12, 20_000), (76, 13, 20_000), (36, 12, 5_000)])
+def test_synthetic_pairs_match_oracle(af, read_len, kp, n):
+    from oracle import oracle
+    spec = af.synth_spec(seed=read_len + kp, ref_len=300_000, anchor_start=100_000, anchor_len=10_000,
+                         read_len=read_len, frag_mean=max(2 * read_len, 300), sub_ppm=15_000, fusion_ppm=30_000)
+    anchor = af.synth_anchor(spec)
+    index = af.AnchorIndex(anchor, kp=kp)
+    eng = af.Anchorer(index, 0)
+    hits, stats = eng.anchor(af.synth_pairs_device(spec, 0, n, index.pad_byte, 0))
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    want = oracle.anchor_reads(oracle.encode(anchor), _interleave(m1, m2), threads=8)
+    assert len(want) > 50
+    assert hits_equal(hits, want)
+
+
+def test_variable_length_reads_with_n(af):
+    """ragged lengths (19..150), Ns (mismatch; no seed across an N), reads off both anchor ends."""
+    from oracle import oracle
+    rng = np.random.default_rng(5)
+    G = 3000
+    anchor = rng.integers(0, 4, G).astype(np.uint8)
+    anchor[[100, 101, 1500]] = 4                       # N in the anchor too
+    n, stride = 4000, 150
+    reads = np.full((2 * n, stride), 4, dtype=np.uint8)
+    lens = rng.integers(19, stride + 1, 2 * n).astype(np.uint16)
+    for i in range(2 * n):
+        L = int(lens[i])
+        kind = i % 4
+        if kind == 0:
+            r = rng.integers(0, 4, L)
+        else:
+            p = int(rng.integers(-40, G - L + 40))
+            r = np.array([anchor[j] if 0 <= j < G and anchor[j] < 4 else rng.integers(0, 4) for j in range(p, p + L)])
+            if kind == 2:
+                j = int(rng.integers(0, L))
+                r[j:] = rng.integers(0, 4, L - j)
+            for _ in range(int(rng.integers(0, 4))):
+                r[rng.integers(0, L)] = rng.integers(0, 5)
+            if i % 8 >= 4:
+                r = np.array([3 - c if c < 4 else 4 for c in r[::-1]])
+        reads[i, :L] = r
+    want = oracle.anchor_reads(anchor, reads, lens=lens)
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    index = af.AnchorIndex(lut[anchor].tobytes())
+    seqs = [lut[reads[i, : lens[i]]].tobytes() for i in range(2 * n)]
+    host = af.pack_pairs(seqs[0::2], seqs[1::2], pad_byte=index.pad_byte)
+    assert host.uniform_len == 0 and host.n_nreads > 100
+    eng = af.Anchorer(index, 0)
+    hits, _ = eng.anchor(host.to_device(0))
+    assert len(want) > 500
+    assert hits_equal(hits, want)
+    # and the same batch through the host-buffer pipeline, in small chunks
+    hits2, _ = eng.anchor_host(host, slot_pairs=512, n_slots=3)
+    assert hits_equal(hits2, want)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1025])
+def test_edge_batch_sizes(af, n):
+    from oracle import oracle
+    spec = af.synth_spec(seed=2, ref_len=20_000, anchor_start=5_000, anchor_len=4000, read_len=101, frag_mean=250)
+    anchor = af.synth_anchor(spec)
+    index = af.AnchorIndex(anchor)
+    eng = af.Anchorer(index, 0)
+    hits, _ = eng.anchor(af.synth_pairs_device(spec, 0, n, index.pad_byte, 0))
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    want = oracle.anchor_reads(oracle.encode(anchor), _interleave(m1, m2))
+    assert hits_equal(hits, want)
+
+
+def test_pipeline_equals_resident_path_and_counts_launches(af):
+    import ctypes
+    from anchored_fusion_b200._lib import lib
+    spec = af.synth_spec(seed=9, ref_len=500_000, anchor_start=100_000, anchor_len=6783, read_len=150,
+                         sub_ppm=10_000, fusion_ppm=10_000)
+    index = af.AnchorIndex(af.synth_anchor(spec))
+    eng = af.Anchorer(index, 0)
+    n = 300_000
+    dev = af.synth_pairs_device(spec, 0, n, index.pad_byte, 0)
+    hits, _ = eng.anchor(dev)
+    host = af.PackedBatch(dev.packed.cpu().numpy().view(np.uint32), n, 150, 150)
+    before = lib().af_kernel_launches()
+    hits2, _ = eng.anchor_host(host, slot_pairs=65_536, n_slots=3)
+    assert hits_equal(hits, hits2)
+    assert lib().af_kernel_launches() - before == 6 * ((n + 65_535) // 65_536)
+
+
+def test_capacity_overflow_is_reported_not_dropped(af):
+    spec = af.synth_spec(seed=4, ref_len=20_000, anchor_start=1_000, anchor_len=15_000, read_len=150)
+    index = af.AnchorIndex(af.synth_anchor(spec))
+    eng = af.Anchorer(index, 0)
+    dev = af.synth_pairs_device(spec, 0, 50_000, index.pad_byte, 0)
+    with pytest.raises(af.AnchoredFusionError):
+        eng.anchor(dev, cand_cap=1000, hits_cap=1000)
