@@ -74,6 +74,8 @@ SIGNATURES = {
     "af_seed_scan": (ctypes.c_int, [c_vp, P(Batch), c_vp, c_vp]),
     "af_seed_scan_config": (ctypes.c_int, [c_i32, c_i32]),
     "af_kernel_launches": (c_i64, []),
+    "af_profile_begin": (None, []),
+    "af_profile_end": (ctypes.c_int, [c_vp, c_vp]),
     "af_pipeline_create": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, P(c_vp)]),
     "af_pipeline_free": (None, [c_vp]),
     "af_pipeline_run": (ctypes.c_int, [c_vp, P(Batch), c_vp, c_i64, P(c_i64), P(c_i64)]),

@@ -147,6 +147,7 @@ struct af_index {
     std::vector<uint32_t> filter;   // nb bucket words
     uint32_t tmask;
     std::vector<uint32_t> table;    // (tmask+1) x {key, value}; value = strand<<31 | anchor pos
+    std::vector<uint32_t> member;   // 4^kp-bit bitmap: bit key set iff key is an anchor k'-mer
     int32_t n_keys, n_entries, n_overflow, pad_byte;
 };
 

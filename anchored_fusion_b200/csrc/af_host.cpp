@@ -52,7 +52,7 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     af_params_t P;
     if (params) P = *params; else af_default_params(&P);
     if (kp == 0) kp = 12;
-    if (P.k < 8 || P.k > 32 || kp < 8 || kp > 15 || kp > P.k || P.A <= 0 || P.B < 0 || P.X < 0) {
+    if (P.k < 8 || P.k > 32 || kp < 8 || kp > 14 || kp > P.k || P.A <= 0 || P.B < 0 || P.X < 0) {
         af_set_error("af_index_build: unsupported parameters (k=%d, kp=%d)", P.k, kp);
         return AF_ERR_ARG;
     }
@@ -85,7 +85,7 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     idx->n_entries = (int32_t)ents.size();
 
     uint32_t slots = 1024;
-    while (slots < 2 * ents.size()) slots <<= 1;
+    while (slots < 4 * ents.size()) slots <<= 1;
     idx->tmask = slots - 1;
     idx->table.assign((size_t)slots * 2, AF_T_EMPTY);
     for (const Ent &e : ents) {
@@ -101,6 +101,8 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     std::sort(keys.begin(), keys.end());
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     idx->n_keys = (int32_t)keys.size();
+    idx->member.assign((size_t)1 << (2 * kp - 5), 0u);   // exact membership, one bit per possible k'-mer
+    for (uint32_t key : keys) idx->member[key >> 5] |= 1u << (key & 31);
 
     uint64_t want = (uint64_t)keys.size() * 4;
     uint32_t nb = (uint32_t)std::min<uint64_t>(AF_MAX_BUCKETS, std::max<uint64_t>(AF_MIN_BUCKETS, want));

@@ -29,6 +29,48 @@
 static std::atomic<long long> g_launches{0};
 extern "C" int64_t af_kernel_launches(void) { return (int64_t)g_launches.load(); }
 
+// ---- optional per-stage timing with CUDA events on the launching stream (bench.py) ---------
+#include <mutex>
+#include <vector>
+enum { ST_SCAN = 0, ST_COMPACT1 = 1, ST_VERIFY = 2, ST_EXTEND = 3, ST_COMPACT2 = 4, ST_N = 5 };
+struct ProfSpan { cudaEvent_t a, b; int stage; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_prof;
+static std::mutex g_prof_mu;
+static void prof_mark(cudaEvent_t *ev, cudaStream_t st) {
+    *ev = nullptr;
+    if (!g_prof_on) return;
+    if (cudaEventCreate(ev) == cudaSuccess) cudaEventRecord(*ev, st);
+}
+static void prof_span(cudaEvent_t a, cudaStream_t st, int stage) {
+    if (!g_prof_on || !a) return;
+    cudaEvent_t b;
+    if (cudaEventCreate(&b) != cudaSuccess) return;
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back({a, b, stage});
+}
+extern "C" void af_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &p : g_prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    g_prof.clear();
+    g_prof_on = true;
+}
+// Call after the stream has been synchronised.  ms_out[5] = summed device time of the seed scan,
+// flag compaction, verify (+ its compaction), extension, hit compaction; calls_out[5] = spans.
+extern "C" int af_profile_end(double *ms_out, int64_t *calls_out) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = false;
+    for (int i = 0; i < ST_N; i++) { ms_out[i] = 0; calls_out[i] = 0; }
+    for (auto &p : g_prof) {
+        float ms = 0;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { ms_out[p.stage] += ms; calls_out[p.stage]++; }
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    g_prof.clear();
+    return AF_OK;
+}
+
 #define AF_CUDA(call)                                                                         \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \
@@ -45,6 +87,7 @@ struct af_dev_index {
     uint32_t fmul, nb, tmask;
     uint32_t *d_filter;  // nb words
     uint2 *d_table;      // tmask+1 entries {key, value}
+    uint32_t *d_member;  // 4^kp-bit exact membership bitmap (L2 resident)
     uint8_t *d_anchor;   // G base codes
     int pad_byte;
     int num_sms;
@@ -62,85 +105,136 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
 }
 
 // All sample positions of one read held in registers w[OFF..OFF+W).  Fully unrolled: every
-// shift and word index is a compile-time constant.
+// shift and word index is a compile-time constant, and there is no branch: the first NPMIN
+// samples exist for every read length this W can hold, the last few are masked by a
+// warp-uniform select, so all probes of a read are independent instructions in one block.
 template <int W, int KP, int OFF, int NW>
 __device__ __forceinline__ uint32_t scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt,
                                               uint32_t fmul, uint32_t nb) {
     constexpr int S = 20 - KP;  // k = 19
-    constexpr uint32_t KMASK = (KP == 16) ? 0xFFFFFFFFu : ((1u << (2 * KP)) - 1u);
-    constexpr int NP = (16 * W - KP) / S + 1;
+    constexpr uint32_t KMASK = (1u << (2 * KP)) - 1u;
+    constexpr int NP = (16 * W - KP) / S + 1;                                // samples when L == 16 W
+    constexpr int LMIN = 16 * (W - 1) + 1;                                   // shortest L with this W
+    constexpr int NPMIN = LMIN >= KP ? (LMIN - KP) / S + 1 : 0;
     uint32_t acc = 0;
 #pragma unroll
     for (int j = 0; j < NP; j++) {
-        if (j < nprobe) {
-            const int o = 2 * j * S, wi = o >> 5, sh = o & 31;
-            uint32_t x;
-            if (sh + 2 * KP <= 32) x = (w[OFF + wi] >> sh) & KMASK;
-            else x = __funnelshift_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh) & KMASK;
-            uint32_t b, fp3;
-            af_filter_hash(x, fmul, nb, b, fp3);
-            acc |= af_filter_test(filt[b], fp3);
-        }
+        const int o = 2 * j * S, wi = o >> 5, sh = o & 31;
+        uint32_t x;
+        if (sh + 2 * KP <= 32) x = (w[OFF + wi] >> sh) & KMASK;
+        else x = __funnelshift_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh) & KMASK;
+        uint32_t b, fp3;
+        af_filter_hash(x, fmul, nb, b, fp3);
+        const uint32_t v = filt[b] ^ fp3;
+        uint32_t t = (v - AF_F_ONES) & ~v;                                   // AF_F_HIGH applied once, below
+        if (j >= NPMIN) t = j < nprobe ? t : 0u;
+        acc |= t;
     }
-    return acc;
+    return acc & AF_F_HIGH;
 }
 
-template <int W, int KP>
-__global__ void __launch_bounds__(1024, 1)
+template <int Q>
+__device__ __forceinline__ void load_tile(uint32_t (&w)[4 * Q], const uint4 *__restrict__ packed, long long tile, int lane) {
+    const uint4 *src = packed + tile * (Q * 32) + lane;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        uint4 v = ld_stream_v4(src + q * 32);
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+}
+
+template <int W, int KP, int Q>
+__device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long tile, int lane, int nprobe,
+                                          const uint32_t *filt, uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags) {
+    uint32_t a1 = scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
+    uint32_t a2 = scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
+    uint32_t b1 = __ballot_sync(FULL, a1 != 0), b2 = __ballot_sync(FULL, a2 != 0);
+    if (lane == 0) flags[tile] = make_uint2(b1, b2);
+}
+
+// Persistent kernel, one CTA per SM: the anchor filter is staged into shared memory once, then
+// each warp walks tiles of 32 pairs (one pair per lane, all of it in registers).
+// PF = true (<= 512 threads, 128 registers): the loads of the warp's NEXT tile are issued before
+// the current tile is scanned (register double buffer), so HBM latency overlaps the probes of
+// the same warp.  PF = false (<= 1024 threads, 64 registers): latency is hidden by occupancy.
+template <int W, int KP, int MAXT, bool PF>
+__global__ void __launch_bounds__(MAXT, 1)
 k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, int nprobe, const uint32_t *__restrict__ g_filter,
             uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags) {
     extern __shared__ uint32_t filt[];
-    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) filt[i] = g_filter[i];
-    __syncthreads();
     constexpr int Q = (2 * W + 3) / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const long long stride = (long long)gridDim.x * nwarps;
-    for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < n_tiles; tile += stride) {
-        uint32_t w[4 * Q];
-        const uint4 *src = packed + tile * (Q * 32) + lane;
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            uint4 v = ld_stream_v4(src + q * 32);
-            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    long long tile = (long long)blockIdx.x * nwarps + warp;
+    if constexpr (PF) {
+        uint32_t wa[4 * Q], wb[4 * Q];
+        if (tile < n_tiles) load_tile<Q>(wa, packed, tile, lane);   // in flight while the filter is staged
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) filt[i] = g_filter[i];
+        __syncthreads();
+        while (tile < n_tiles) {
+            const long long t2 = tile + stride;
+            if (t2 < n_tiles) load_tile<Q>(wb, packed, t2, lane);
+            scan_tile<W, KP, Q>(wa, tile, lane, nprobe, filt, fmul, nb, flags);
+            if (t2 >= n_tiles) break;
+            const long long t3 = t2 + stride;
+            if (t3 < n_tiles) load_tile<Q>(wa, packed, t3, lane);
+            scan_tile<W, KP, Q>(wb, t2, lane, nprobe, filt, fmul, nb, flags);
+            tile = t3;
         }
-        uint32_t a1 = scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
-        uint32_t a2 = scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
-        uint32_t b1 = __ballot_sync(FULL, a1 != 0), b2 = __ballot_sync(FULL, a2 != 0);
-        if (lane == 0) flags[tile] = make_uint2(b1, b2);
+    } else {
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) filt[i] = g_filter[i];
+        __syncthreads();
+        for (; tile < n_tiles; tile += stride) {
+            uint32_t w[4 * Q];
+            load_tile<Q>(w, packed, tile, lane);
+            scan_tile<W, KP, Q>(w, tile, lane, nprobe, filt, fmul, nb, flags);
+        }
     }
 }
 
-static int g_scan_threads = 1024;
-extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t /*blocks_per_sm*/) {
-    if (threads_per_block == 0) threads_per_block = 1024;
-    if (threads_per_block < 64 || threads_per_block > 1024 || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..1024, multiple of 32"); return AF_ERR_ARG; }
+static int g_scan_threads = 512, g_scan_prefetch = 1;
+// tuning knob: threads per CTA (0 = default 512) and mode (0 = default, 1 = register
+// double buffer with <= 512 threads, 2 = no prefetch, up to 1024 threads)
+extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
+    int pf = mode == 2 ? 0 : 1;
+    int maxt = pf ? 512 : 1024;
+    if (threads_per_block == 0) threads_per_block = maxt;
+    if (threads_per_block < 64 || threads_per_block > maxt || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..%d, multiple of 32", maxt); return AF_ERR_ARG; }
     g_scan_threads = threads_per_block;
+    g_scan_prefetch = pf;
     return AF_OK;
 }
 
-template <int W, int KP>
+template <int W, int KP, int MAXT, bool PF>
 static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
                        cudaStream_t st) {
     size_t smem = (size_t)d->nb * 4;
     static bool attr_set[64] = {false};  // per device
     if (!attr_set[d->device & 63]) {
-        AF_CUDA(cudaFuncSetAttribute(k_seed_scan<W, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AF_CUDA(cudaFuncSetAttribute(k_seed_scan<W, KP, MAXT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[d->device & 63] = true;
     }
     int nwarps = g_scan_threads / 32;
     long long want = (n_tiles + nwarps - 1) / nwarps;
     int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
-    k_seed_scan<W, KP><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, nprobe, d->d_filter,
-                                                           d->fmul, d->nb, (uint2 *)flags);
+    k_seed_scan<W, KP, MAXT, PF><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, nprobe, d->d_filter,
+                                                                     d->fmul, d->nb, (uint2 *)flags);
     g_launches++;
     AF_CUDA(cudaGetLastError());
     return AF_OK;
 }
 
+template <int W, int KP>
+static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
+                            cudaStream_t st) {
+    return g_scan_prefetch ? launch_scan<W, KP, 512, true>(d, b, n_tiles, nprobe, flags, st)
+                           : launch_scan<W, KP, 1024, false>(d, b, n_tiles, nprobe, flags, st);
+}
+
 #define AF_SCAN_CASE(WW)                                                                       \
     case WW:                                                                                   \
-        return kp == 12 ? launch_scan<WW, 12>(d, b, n_tiles, nprobe, flags, st)                \
-                        : launch_scan<WW, 13>(d, b, n_tiles, nprobe, flags, st);
+        return kp == 12 ? launch_scan_mode<WW, 12>(d, b, n_tiles, nprobe, flags, st)           \
+                        : launch_scan_mode<WW, 13>(d, b, n_tiles, nprobe, flags, st);
 
 static int batch_check(const af_dev_index *d, const af_batch_t *b, af_layout_t *lay) {
     if (!d || !b) { af_set_error("null index or batch"); return AF_ERR_ARG; }
@@ -273,7 +367,7 @@ k_flag_scatter(const uint2 *__restrict__ flags, long long n_tiles, long long n_p
 __global__ void __launch_bounds__(CB_THREADS)
 k_hit_count(const uint4 *__restrict__ slots, uint32_t cand_cap, uint32_t *__restrict__ blk_counts, uint32_t *counts) {
     __shared__ uint32_t sm[9];
-    uint32_t n = min(counts[AF_CNT_FLAGGED], cand_cap), c = 0;
+    uint32_t n = min(counts[AF_CNT_SEEDED], cand_cap), c = 0;
     uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
     if (blockIdx.x * CB_PER_BLOCK < n) {
 #pragma unroll
@@ -289,7 +383,7 @@ __global__ void __launch_bounds__(CB_THREADS)
 k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cand_cap, const uint32_t *__restrict__ blk_counts,
               uint4 *__restrict__ hits, uint32_t hits_cap, uint32_t *counts) {
     __shared__ uint32_t sm[9];
-    uint32_t n = min(counts[AF_CNT_FLAGGED], cand_cap);
+    uint32_t n = min(counts[AF_CNT_SEEDED], cand_cap);
     if (blockIdx.x * CB_PER_BLOCK >= n) return;
     uint32_t base = sum_before(blk_counts, blockIdx.x, sm);
     uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS, c = 0;
@@ -306,6 +400,136 @@ k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cand_cap, const uint32_t
     for (int i = 0; i < CB_ITEMS; i++)
         if ((v[i].z >> 16) != 0) { if (off < hits_cap) hits[off] = v[i]; else over = true; off++; }
     if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
+}
+
+// compaction of a uint32 list by a per-item keep byte; n lives in counts[n_idx] on the device
+__global__ void __launch_bounds__(CB_THREADS)
+k_sel_count(const uint8_t *__restrict__ keep, uint32_t cap, int n_idx, int out_idx, uint32_t *__restrict__ blk_counts,
+            uint32_t *counts) {
+    __shared__ uint32_t sm[9];
+    uint32_t n = min(counts[n_idx], cap), c = 0;
+    uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
+    if (blockIdx.x * CB_PER_BLOCK < n) {
+#pragma unroll
+        for (int i = 0; i < CB_ITEMS; i++)
+            if (i0 + i < n) c += keep[i0 + i] != 0;
+    }
+    uint32_t total;
+    block_excl_scan(c, sm, total);
+    if (threadIdx.x == 0) { blk_counts[blockIdx.x] = total; if (total) atomicAdd(&counts[out_idx], total); }
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+k_sel_scatter(const uint32_t *__restrict__ items, const uint8_t *__restrict__ keep, uint32_t cap, int n_idx,
+              const uint32_t *__restrict__ blk_counts, uint32_t *__restrict__ out, const uint32_t *counts) {
+    __shared__ uint32_t sm[9];
+    uint32_t n = min(counts[n_idx], cap);
+    if (blockIdx.x * CB_PER_BLOCK >= n) return;
+    uint32_t base = sum_before(blk_counts, blockIdx.x, sm);
+    uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS, c = 0;
+    uint32_t v[CB_ITEMS];
+    bool k[CB_ITEMS];
+#pragma unroll
+    for (int i = 0; i < CB_ITEMS; i++) {
+        k[i] = (i0 + i < n) && keep[i0 + i] != 0;
+        v[i] = k[i] ? items[i0 + i] : 0u;
+        c += k[i];
+    }
+    uint32_t total, off = base + block_excl_scan(c, sm, total);
+#pragma unroll
+    for (int i = 0; i < CB_ITEMS; i++)
+        if (k[i]) out[off++] = v[i];   // out has the capacity of items: cannot overflow
+}
+
+// ------------------------------------------------------------------------------------------
+// verify: one THREAD per flagged read.  Removes the filter's false positives cheaply: exact
+// k'-mer membership from an L2-resident bitmap (independent loads, no probing chain), and for
+// the rare members a table walk plus a check that the exact match around the sample reaches k
+// bases.  A read is kept iff some diagonal holds >= k consecutive matches -- exactly the
+// SEEDED predicate of the spec, so k_extend only ever sees reads it will have to extend.
+// ------------------------------------------------------------------------------------------
+struct ReadRef {
+    const uint32_t *packed;   // tile-interleaved words
+    size_t base;              // word index of word 0 of this read's pair in its quad 0
+    int wofs;                 // mate * W
+    const uint32_t *nm;       // N-mask words of this read or nullptr
+    int L;
+    __device__ __forceinline__ uint32_t word(int t) const {
+        const int wi = wofs + t;
+        return packed[base + (size_t)(wi >> 2) * 128 + (wi & 3)];
+    }
+    __device__ __forceinline__ uint32_t base_at(int i) const { return (word(i >> 4) >> (2 * (i & 15))) & 3u; }
+    __device__ __forceinline__ bool is_n(int i) const { return nm && ((nm[i >> 5] >> (i & 31)) & 1u); }
+};
+
+__device__ __forceinline__ bool diag_match(const ReadRef &r, int s, int i, int d, const uint8_t *__restrict__ anchor, int G) {
+    const int ap = i + d;
+    if (i < 0 || i >= r.L || ap < 0 || ap >= G) return false;
+    const int fi = s ? r.L - 1 - i : i;
+    if (r.is_n(fi)) return false;
+    uint32_t b = r.base_at(fi);
+    if (s) b = 3u - b;
+    return anchor[ap] == b;
+}
+
+__global__ void __launch_bounds__(256)
+k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, const uint16_t *__restrict__ lens,
+         const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
+         const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts, uint32_t cand_cap,
+         const uint32_t *__restrict__ member, const uint2 *__restrict__ table, uint32_t tmask,
+         const uint8_t *__restrict__ anchor, int G, int KP, int S, int K, uint8_t *__restrict__ keep) {
+    const uint32_t ncand = min(counts[AF_CNT_FLAGGED], cand_cap);
+    const uint32_t kpmask = (1u << (2 * KP)) - 1u;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += gridDim.x * blockDim.x) {
+        const uint32_t rid = cand[c], pair = rid >> 1;
+        ReadRef r;
+        r.packed = packed;
+        r.base = ((size_t)(pair >> 5) * Q * 32 + (pair & 31)) * 4;
+        r.wofs = (int)(rid & 1u) * W;
+        r.L = uniform_len > 0 ? uniform_len : (int)lens[rid];
+        r.nm = nullptr;
+        if (n_nreads > 0) {
+            int lo = 0, hi = n_nreads;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
+            if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
+        }
+        const int nprobe = r.L >= KP ? (r.L - KP) / S + 1 : 0;
+        // phase 1: membership bit of every sample (independent loads)
+        unsigned long long hit = 0;
+        uint32_t w0 = nprobe ? r.word(0) : 0u, w1 = (nprobe && W > 1) ? r.word(1) : 0u;
+        int wcur = 0;
+        for (int j = 0; j < nprobe; j++) {
+            const int o = 2 * j * S, wi = o >> 5;
+            if (wi != wcur) { w0 = (wi == wcur + 1) ? w1 : r.word(wi); w1 = wi + 1 < W ? r.word(wi + 1) : 0u; wcur = wi; }
+            const uint32_t key = __funnelshift_r(w0, w1, o & 31) & kpmask;
+            if ((member[key >> 5] >> (key & 31)) & 1u) hit |= 1ull << j;
+        }
+        // phase 2: the rare members -- walk the table, check that the exact run reaches K
+        bool seeded = false;
+        while (hit && !seeded) {
+            const int j = __ffsll((long long)hit) - 1;
+            hit &= hit - 1;
+            const int p = j * S, o = 2 * p;
+            const uint32_t key = __funnelshift_r(r.word(o >> 5), (o >> 5) + 1 < W ? r.word((o >> 5) + 1) : 0u, o & 31) & kpmask;
+            if (r.nm) {   // a k'-mer that overlaps an N is no seed material
+                bool n = false;
+                for (int t = 0; t < KP; t++) n |= r.is_n(p + t);
+                if (n) continue;
+            }
+            for (uint32_t slot = af_table_hash(key, tmask);; slot = (slot + 1) & tmask) {
+                const uint2 e = table[slot];
+                if (e.x == AF_T_EMPTY) break;
+                if (e.x != key) continue;
+                const int s = e.y >> 31, jpos = (int)(e.y & 0x7FFFFFFFu);
+                const int qp = s ? r.L - p - KP : p, d = jpos - qp;
+                int run = KP;
+                for (int i = qp - 1; run < K && diag_match(r, s, i, d, anchor, G); i--) run++;
+                for (int i = qp + KP; run < K && diag_match(r, s, i, d, anchor, G); i++) run++;
+                if (run >= K) { seeded = true; break; }
+            }
+        }
+        keep[c] = seeded ? 1 : 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -433,7 +657,7 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
          ExtParams P, uint4 *__restrict__ slots) {
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw_total = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t ncand = min(counts[AF_CNT_FLAGGED], cand_cap);
+    const uint32_t ncand = min(counts[AF_CNT_SEEDED], cand_cap);
     const uint32_t kpmask = (1u << (2 * KP)) - 1u;
     for (uint32_t c = gw; c < ncand; c += nw_total) {
         const uint32_t rid = cand[c];
@@ -523,7 +747,7 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
 // ------------------------------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct WsLayout { size_t flags, blk1, cand, slots, blk2, total; int nblk1, nblk2; };
+struct WsLayout { size_t flags, blk1, cand, keep, cand2, slots, blk2, total; int nblk1, nblk2; };
 
 static WsLayout ws_layout(long long n_pairs, long long cand_cap) {
     WsLayout w;
@@ -534,6 +758,8 @@ static WsLayout ws_layout(long long n_pairs, long long cand_cap) {
     w.flags = o; o += align256((size_t)n_tiles * 8);
     w.blk1 = o; o += align256((size_t)(w.nblk1 + 1) * 4);
     w.cand = o; o += align256((size_t)cand_cap * 4);
+    w.keep = o; o += align256((size_t)cand_cap);
+    w.cand2 = o; o += align256((size_t)cand_cap * 4);
     w.slots = o; o += align256((size_t)cand_cap * 16);
     w.blk2 = o; o += align256((size_t)(w.nblk2 + 1) * 4);
     w.total = o;
@@ -564,22 +790,42 @@ extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, voi
     uint4 *slots = (uint4 *)(ws + w.slots);
     AF_CUDA(cudaMemsetAsync(d_counts, 0, AF_N_COUNTS * sizeof(uint32_t), st));
     if (lay.n_tiles == 0) return AF_OK;
+    cudaEvent_t ev;
+    prof_mark(&ev, st);
     rc = seed_scan_impl(d, b, flags, st);
     if (rc) return rc;
+    prof_span(ev, st, ST_SCAN);
+    prof_mark(&ev, st);
     k_flag_count<<<w.nblk1, CB_THREADS, 0, st>>>((const uint2 *)flags, lay.n_tiles, b->n_pairs, blk1, d_counts);
     k_flag_scatter<<<w.nblk1, CB_THREADS, 0, st>>>((const uint2 *)flags, lay.n_tiles, b->n_pairs, blk1, cand,
                                                    (uint32_t)cand_cap, d_counts);
+    prof_span(ev, st, ST_COMPACT1);
+    prof_mark(&ev, st);
+    uint8_t *keep = (uint8_t *)(ws + w.keep);
+    uint32_t *cand2 = (uint32_t *)(ws + w.cand2);
+    long long vthreads = cand_cap < (long long)d->num_sms * 2048 ? cand_cap : (long long)d->num_sms * 2048;
+    k_verify<<<(unsigned)((vthreads + 255) / 256), 256, 0, st>>>(
+        (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, b->nread_ids,
+        b->nmask, (int)b->n_nreads, cand, d_counts, (uint32_t)cand_cap, d->d_member, d->d_table, d->tmask, d->d_anchor,
+        d->G, d->kp, d->stride, d->P.k, keep);
+    k_sel_count<<<w.nblk2, CB_THREADS, 0, st>>>(keep, (uint32_t)cand_cap, AF_CNT_FLAGGED, AF_CNT_SEEDED, blk2, d_counts);
+    k_sel_scatter<<<w.nblk2, CB_THREADS, 0, st>>>(cand, keep, (uint32_t)cand_cap, AF_CNT_FLAGGED, blk2, cand2, d_counts);
+    prof_span(ev, st, ST_VERIFY);
+    prof_mark(&ev, st);
     ExtParams P = {d->P.k, d->P.A, d->P.B, d->P.clip5, d->P.clip3, d->P.T, d->P.X};
     long long warps_wanted = cand_cap < (long long)d->num_sms * 64 ? cand_cap : (long long)d->num_sms * 64;
     int ext_blocks = (int)((warps_wanted + 7) / 8);
     k_extend<<<ext_blocks, 256, 0, st>>>((const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair,
-                                         b->uniform_len, b->lens, b->nread_ids, b->nmask, (int)b->n_nreads, cand,
+                                         b->uniform_len, b->lens, b->nread_ids, b->nmask, (int)b->n_nreads, cand2,
                                          d_counts, (uint32_t)cand_cap, d->d_table, d->tmask, d->d_anchor, d->G, d->kp,
                                          d->stride, P, slots);
+    prof_span(ev, st, ST_EXTEND);
+    prof_mark(&ev, st);
     k_hit_count<<<w.nblk2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, blk2, d_counts);
     k_hit_scatter<<<w.nblk2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, blk2, (uint4 *)d_hits, (uint32_t)hits_cap,
                                                   d_counts);
-    g_launches += 5;
+    prof_span(ev, st, ST_COMPACT2);
+    g_launches += 8;
     AF_CUDA(cudaGetLastError());
     return AF_OK;
 }
@@ -600,8 +846,10 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     d->device = device; d->P = idx->P; d->kp = idx->kp; d->stride = idx->stride; d->G = idx->G;
     d->fmul = idx->fmul; d->nb = idx->nb; d->tmask = idx->tmask; d->pad_byte = idx->pad_byte;
     d->num_sms = prop.multiProcessorCount;
-    d->d_filter = nullptr; d->d_table = nullptr; d->d_anchor = nullptr;
+    d->d_filter = nullptr; d->d_table = nullptr; d->d_anchor = nullptr; d->d_member = nullptr;
     cudaError_t e = cudaMalloc(&d->d_filter, idx->filter.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_member, idx->member.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_member, idx->member.data(), idx->member.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_table, idx->table.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_anchor, idx->codes.size() + 256);
     if (e == cudaSuccess) e = cudaMemcpy(d->d_filter, idx->filter.data(), idx->filter.size() * 4, cudaMemcpyHostToDevice);
@@ -609,7 +857,7 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     if (e == cudaSuccess) e = cudaMemcpy(d->d_anchor, idx->codes.data(), idx->codes.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         af_set_error("af_index_upload: %s", cudaGetErrorString(e));
-        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor);
+        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member);
         delete d;
         return AF_ERR_CUDA;
     }
@@ -622,7 +870,7 @@ extern "C" int af_dev_index_device(const af_dev_index_t *d) { return d ? d->devi
 extern "C" void af_dev_index_free(af_dev_index_t *d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor);
+    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member);
     delete d;
 }
 

@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- read pairs/s anchored on B200, seed-scan HBM roofline, CPU baseline.
+
+  python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA path
+  python bench.py --impl reference [...]                     the reference arm on the host cores
+
+A step = one pass of the hot path (seed scan -> compaction -> verify/extend -> compaction)
+over one batch of synthetic 2x150 bp pairs resident in HBM (BASELINE.json configs[1]:
+10M pairs against a 6 783 bp anchored CDS cut from a random 10 Mbp reference).  Under torchrun
+every rank owns its own 10M-pair shard (weak scaling) and the ranks' hit lists are gathered
+with one NCCL all-gather per step.  See DESIGN.md "Measurement".
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_PAIR = {150: 76, 101: 52}   # 2 * ceil(2L/8), SURVEY.md 8d
+METRIC = "read_pairs_per_s_anchored"
+
+
+def alg_bytes(read_len):
+    return 2 * ((2 * read_len + 7) // 8)
+
+
+def workload(args):
+    import anchored_fusion_b200 as af
+    return af.synth_spec(seed=1, ref_len=10_000_000, anchor_start=2_000_000, anchor_len=args.anchor_len,
+                         read_len=args.read_len, frag_mean=2 * args.read_len, frag_sd=30, sub_ppm=args.sub_ppm,
+                         fusion_ppm=args.fusion_ppm)
+
+
+def config_dict(args, n_gpus):
+    return {"workload": "configs[1]: %d synthetic 2x%d bp pairs per GPU, one %d bp anchored CDS on a random 10 Mbp "
+                        "reference (seeded generator, %d ppm substitutions, %d ppm fusion fragments)"
+                        % (args.pairs, args.read_len, args.anchor_len, args.sub_ppm, args.fusion_ppm),
+            "pairs_per_gpu": args.pairs, "read_len": args.read_len, "anchor_len": args.anchor_len,
+            "sharding": "reads x%d, hit lists all-gathered" % n_gpus,
+            "l2_policy": "input per step (%.0f MB) exceeds the 126 MB L2; no flush needed" % (args.pairs * 80 / 1e6)}
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (pynvml == nvidia-smi's source)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(0.02)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_rate(args, n_pairs, threads):
+    """The CPU arm: oracle/af_oracle.c (a port: the reference's own path is bwa/samtools, absent)."""
+    import anchored_fusion_b200 as af
+    from oracle import oracle
+    spec = workload(args)
+    anchor = oracle.encode(af.synth_anchor(spec))
+    m1, m2 = af.synth_pairs_host(spec, 0, n_pairs)
+    reads = np.empty((2 * n_pairs, spec.read_len), dtype=np.uint8)
+    reads[0::2], reads[1::2] = m1, m2
+    oracle.anchor_reads(anchor, reads[:2000], threads=threads)   # warm the library
+    t0 = time.perf_counter()
+    hits = oracle.anchor_reads(anchor, reads, threads=threads)
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt, len(hits)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.ref_pairs
+    rates = []
+    for i in range(args.warmup + args.steps):
+        rate, dt, nh = cpu_reference_rate(args, sample, threads)
+        if i >= args.warmup:
+            rates.append((rate, dt))
+    value = sample * len(rates) / sum(dt for _, dt in rates)
+    desc = "%d of the workload's pairs per step, oracle/af_oracle.c with %d OpenMP threads" % (sample, threads)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(dt for _, dt in rates) / len(rates),
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                      "data": "synthetic", "config": config_dict(args, args.gpus),
+                      "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
+                      "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--anchor-len", type=int, default=6783)
+    ap.add_argument("--sub-ppm", type=int, default=10_000)
+    ap.add_argument("--fusion-ppm", type=int, default=0)
+    ap.add_argument("--kp", type=int, default=0)
+    ap.add_argument("--scan-threads", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-pairs", type=int, default=1_000_000, help="bounded sample for cpu_baseline")
+    ap.add_argument("--ref-pairs", type=int, default=250_000, help="pairs per step of the reference arm")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200 import dist as afdist
+    from anchored_fusion_b200._lib import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib()
+    if args.scan_threads:
+        L.af_seed_scan_config(args.scan_threads, 0)
+
+    spec = workload(args)
+    index = af.AnchorIndex(af.synth_anchor(spec), kp=args.kp)
+    eng = af.Anchorer(index, local)
+    n = args.pairs
+    batch = af.synth_pairs_device(spec, rank * n, n, index.pad_byte, local)   # this rank's shard
+    torch.cuda.synchronize()
+    gather_cap = 1 << 16
+
+    def step():
+        hits, counts = eng.enqueue(batch)
+        if world > 1:
+            return afdist.gather_hits_tensor(hits, counts, gather_cap)
+        return counts, hits
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    stats_counts = eng._ws[2].cpu().numpy().view(np.uint32)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = L.af_kernel_launches()
+    L.af_profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    stage_ms = (ctypes.c_double * 5)()
+    stage_calls = (ctypes.c_int64 * 5)()
+    L.af_profile_end(stage_ms, stage_calls)
+    launches = L.af_kernel_launches() - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (seed scan): algorithmic bytes / its mean launch duration,
+    # CUDA events on the launching stream, inside the timed region above
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    scan_ms = stage_ms[0] / max(stage_calls[0], 1)
+    achieved = alg_bytes(args.read_len) * n / (scan_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "seed_scan_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("pairs") == n and tj.get("read_len") == args.read_len:
+            traffic = tj.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "k_seed_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_pair": alg_bytes(args.read_len), "ms_per_launch": scan_ms,
+                "stage_ms_per_step": {"seed_scan": stage_ms[0] / args.steps, "flag_compaction": stage_ms[1] / args.steps,
+                                      "verify": stage_ms[2] / args.steps, "extend": stage_ms[3] / args.steps,
+                                      "hit_compaction": stage_ms[4] / args.steps}}
+
+    # end to end through the host-buffer C-ABI call: pinned host batch -> H2D -> kernels -> D2H hits
+    e2e = None
+    if not args.no_e2e:
+        lay = af.layout(args.read_len, n)
+        hptr = L.af_host_alloc(lay.packed_bytes)
+        host_packed = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint32)), (lay.packed_bytes // 4,))
+        host_packed[:] = batch.packed.cpu().numpy().view(np.uint32)
+        hb = af.PackedBatch(host_packed, n, args.read_len, args.read_len)
+        hits_out = np.zeros(1 << 20, dtype=af.HIT_DTYPE)
+        eng.anchor_host(hb, hits_out=hits_out)                  # warm-up (allocates the slots)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            h, st = eng.anchor_host(hb, hits_out=hits_out)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * n / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(lay.packed_bytes),
+               "d2h_bytes_per_step": int(len(h) * 16 + 32 * ((n + (1 << 20) - 1) >> 20)), "ms_per_step": dt * 1e3,
+               "path": "af_pipeline_run: pinned host tiles -> cudaMemcpyAsync -> kernels -> hit list on host"}
+        eng.close_pipeline()
+        L.af_host_free(hptr)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, dt, nh = cpu_reference_rate(args, args.cpu_pairs, threads)
+        cpu = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port",
+               "sample": "first %d pairs of the workload, oracle/af_oracle.c, %d OpenMP threads, %.1f s"
+                         % (args.cpu_pairs, threads, dt)}
+
+    if rank == 0:
+        nh = int(stats_counts[1])
+        print(json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": config_dict(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                          "gpu_launches": int(launches), "clocks": clocks,
+                          "per_step": {"flagged_reads": int(stats_counts[0]), "seeded_reads": int(stats_counts[3]),
+                                       "anchored_reads": nh,
+                                       "kp": index.info.kp, "stride": index.info.stride}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -159,7 +159,9 @@ int af_fastq_record(const af_fastq_t *fq, int64_t read_id, const char **name, in
 
 /* ---- the hot path on one GPU: replaces `bwa mem -M | samtools view -F 772` -------------- */
 size_t af_workspace_bytes(int64_t n_pairs, int64_t cand_cap);
-/* scan -> compact -> verify -> compact -> extend -> compact, all on `stream`, no host sync.
+/* seed scan -> compaction -> verify -> compaction -> extend -> compaction (8 kernels), all on
+ * `stream`, no host sync; counts[AF_CNT_FLAGGED] reads passed the scan, counts[AF_CNT_SEEDED] hold a
+ * true >= k-base exact match, counts[AF_CNT_HITS] are anchored (score >= T).
  * d_hits[0..counts[AF_CNT_HITS]) come back ordered by read_id. */
 int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *batch, void *workspace, size_t workspace_bytes,
                     int64_t cand_cap, af_hit_t *d_hits, int64_t hits_cap, uint32_t *d_counts, void *stream);
@@ -168,6 +170,11 @@ int af_seed_scan(const af_dev_index_t *d, const af_batch_t *batch, uint32_t *d_f
                  void *stream);
 int af_seed_scan_config(int32_t threads_per_block, int32_t blocks_per_sm); /* tuning knob; 0 = default */
 int64_t af_kernel_launches(void); /* kernels this library has launched since it was loaded */
+/* per-stage device time of af_anchor_batch, CUDA events on the launching stream: begin, run,
+ * synchronise the stream, end.  ms_out[5] / calls_out[5]: seed scan, flag compaction, verify
+ * (+ its compaction), extension, hit compaction. */
+void af_profile_begin(void);
+int af_profile_end(double *ms_out, int64_t *calls_out);
 
 /* ---- host->device streaming executor (pinned staging, cudaMemcpyAsync, N slots) --------- */
 int af_pipeline_create(const af_dev_index_t *d, int64_t slot_pairs, int32_t max_read_len, int32_t n_slots,

@@ -1,0 +1,33 @@
+"""numpy emulation of the seed-scan kernel's filter probes (test helper): which reads must the
+kernel flag, bit for bit, given the index's filter words and hash."""
+import numpy as np
+
+
+def expected_flags(index, codes, lens=None):
+    """codes: (n_reads, stride) base codes with N/pad positions already replaced by the pad
+    pattern (i.e. what the packed words hold).  Returns bool[n_reads]."""
+    info = index.info
+    KP, S, nb, fm = info.kp, info.stride, info.n_buckets, info.filter_mul
+    filt = index.filter_words().astype(np.uint64)
+    n, stride = codes.shape
+    Lmax = int(lens.max()) if lens is not None else stride
+    flag = np.zeros(n, bool)
+    W = (stride + 15) // 16
+    pad = [(info.pad_byte >> (2 * k)) & 3 for k in range(4)]
+    full = np.empty((n, 16 * W), dtype=np.uint64)
+    full[:, :stride] = codes
+    for i in range(stride, 16 * W):
+        full[:, i] = pad[i & 3]
+    if lens is not None:
+        for i in range(stride):
+            full[lens <= i, i] = pad[i & 3]
+    for p in range(0, Lmax - KP + 1, S):          # the kernel samples up to the batch's longest read
+        key = np.zeros(n, np.uint64)
+        for t in range(KP):
+            key |= full[:, p + t] << np.uint64(2 * t)
+        lo = (key * np.uint64(fm)) & np.uint64(0xFFFFFFFF)
+        b = ((lo * np.uint64(nb)) >> np.uint64(32)).astype(np.int64)
+        fp3 = ((lo & np.uint64(0x3FE)) * np.uint64(0x00100401) + np.uint64(0x00100401)) & np.uint64(0xFFFFFFFF)
+        v = filt[b] ^ fp3
+        flag |= (((v - np.uint64(0x40100401)) & ~v & np.uint64(0xA0080200)) & np.uint64(0xFFFFFFFF)) != 0
+    return flag

@@ -39,6 +39,30 @@ def test_bundled_sample_matches_oracle(af, bundled, kp):
         assert bundled["names1"][rid >> 1].startswith("EU216071.1")
 
 
+@pytest.mark.parametrize("kp,mode,threads", [(12, 1, 512), (13, 1, 256), (12, 2, 1024), (13, 2, 768)])
+def test_seed_scan_flags_equal_the_filter_emulation(af, bundled, kp, mode, threads):
+    """The scan kernel alone: its flag words equal a numpy emulation of the filter probes bit for
+    bit (so false positives are exactly the filter's, and every oracle hit is flagged)."""
+    from filter_emulator import expected_flags
+    from anchored_fusion_b200._lib import check, lib
+    index = af.AnchorIndex(bundled["anchor"], kp=kp)
+    eng = af.Anchorer(index, 0)
+    host = af.pack_pairs(bundled["seqs1"], bundled["seqs2"], pad_byte=index.pad_byte)
+    check(lib().af_seed_scan_config(threads, mode))
+    try:
+        flags = eng.seed_scan(host.to_device(0)).cpu().numpy().view(np.uint32)
+    finally:
+        check(lib().af_seed_scan_config(0, 0))
+    n = host.n_pairs
+    got = np.zeros(2 * n, bool)
+    for mate in (0, 1):
+        bits = (flags[:, mate][:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1
+        got[mate::2] = bits.reshape(-1)[:n].astype(bool)
+    want = expected_flags(index, bundled["codes"])
+    assert np.array_equal(got, want)
+    assert got[bundled["oracle_hits"]["read_id"]].all()
+
+
 def test_device_generator_matches_host_generator(af):
     spec = af.synth_spec(seed=11, ref_len=100_000, anchor_start=20_000, anchor_len=5000, read_len=150,
                          sub_ppm=20_000, fusion_ppm=50_000)
@@ -135,7 +159,7 @@ def test_pipeline_equals_resident_path_and_counts_launches(af):
     before = lib().af_kernel_launches()
     hits2, _ = eng.anchor_host(host, slot_pairs=65_536, n_slots=3)
     assert hits_equal(hits, hits2)
-    assert lib().af_kernel_launches() - before == 6 * ((n + 65_535) // 65_536)
+    assert lib().af_kernel_launches() - before == 9 * ((n + 65_535) // 65_536)
 
 
 def test_capacity_overflow_is_reported_not_dropped(af):

@@ -1,0 +1,95 @@
+"""The oracle pinned: C restatement vs the index-free pure-Python brute force, hand-checked
+known answers of the spec, and the committed golden of the bundled sample."""
+import numpy as np
+
+from conftest import hits_equal
+
+
+def _rc(r):
+    return [3 - c if c < 4 else 4 for c in reversed(r)]
+
+
+def test_c_oracle_equals_bruteforce_on_random_cases():
+    from oracle import bruteforce, oracle
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 4, 400).astype(np.uint8)
+    a[[50, 300]] = 4
+    reads = []
+    for t in range(240):
+        L = 60
+        kind = t % 5
+        if kind == 0:
+            r = rng.integers(0, 4, L)
+        else:
+            p = int(rng.integers(-20, 360))
+            r = np.array([a[i] if 0 <= i < 400 and a[i] < 4 else rng.integers(0, 4) for i in range(p, p + L)])
+            j = int(rng.integers(5, L - 5))
+            if kind == 2:
+                r[j:] = rng.integers(0, 4, L - j)
+            if kind == 3:
+                r[:j] = rng.integers(0, 4, j)
+            for _ in range(int(rng.integers(0, 4))):
+                r[rng.integers(0, L)] = rng.integers(0, 5)
+            if t % 2:
+                r = np.array(_rc(list(r)))
+        reads.append(r.astype(np.uint8))
+    hits = oracle.anchor_reads(a, np.stack(reads))
+    got = {int(h["read_id"]): (int(h["pos"]), int(h["clip_l"]), int(h["m_len"]), int(h["clip_r"]),
+                               int(h["score_strand"]) & 1, int(h["score_strand"]) >> 1) for h in hits}
+    assert len(got) > 80
+    for i, r in enumerate(reads):
+        assert bruteforce.anchor_read(list(r), list(a)) == got.get(i), i
+
+
+def test_spec_known_answers():
+    """Hand-worked cases of 'Anchoring spec v1' (bwa-mem scores: +1/-4, clip 5, T 30, k 19)."""
+    from oracle import oracle
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 4, 500).astype(np.uint8)
+
+    def one(read):
+        h = oracle.anchor_reads(a, np.array([read], dtype=np.uint8))
+        if not len(h):
+            return None
+        h = h[0]
+        return int(h["pos"]), int(h["clip_l"]), int(h["m_len"]), int(h["clip_r"]), int(h["score_strand"]) & 1, int(h["score_strand"]) >> 1
+
+    exact = a[100:200].copy()
+    assert one(exact) == (101, 0, 100, 0, 0, 100)                       # full match: 100M
+    assert one(np.array(_rc(list(exact)))) == (101, 0, 100, 0, 1, 100)  # reverse strand, same POS/CIGAR
+    assert one(a[100:129]) is None                                       # 29 < T=30
+    assert one(a[100:130]) == (101, 0, 30, 0, 0, 30)
+    # one mismatch 2 bases from the 5' end: local best 97 (clip 3) vs end-to-end 95 > 97-5 -> no clip
+    mm = exact.copy(); mm[2] = (mm[2] + 1) % 4
+    assert one(mm) == (101, 0, 100, 0, 0, 95)
+    # two mismatches at 1 and 3: local best 96 (clip 4) vs end-to-end 90 <= 96-5 -> soft clip 4
+    mm = exact.copy(); mm[1] = (mm[1] + 1) % 4; mm[3] = (mm[3] + 1) % 4
+    assert one(mm) == (105, 4, 96, 0, 0, 96)
+    mm = exact.copy(); mm[98] = (mm[98] + 1) % 4; mm[96] = (mm[96] + 1) % 4
+    assert one(mm) == (101, 0, 96, 4, 0, 96)
+    # a fusion junction: 60 anchor bases then foreign sequence -> 60M40S, split point POS+60-1
+    junction = exact.copy(); junction[60:] = (a[160:200] + 1 + np.arange(40) % 3) % 4
+    assert one(junction) == (101, 0, 60, 40, 0, 60)
+    assert one(np.array(_rc(list(junction)))) == (101, 0, 60, 40, 1, 60)
+    # a read hanging off the anchor's start / end is clipped at the boundary
+    off = np.concatenate([(a[0:10] + 2) % 4, a[0:90]]).astype(np.uint8)
+    assert one(off) == (1, 10, 90, 0, 0, 90)
+    off = np.concatenate([a[440:500], (a[0:40] + 1) % 4]).astype(np.uint8)
+    assert one(off) == (441, 0, 60, 40, 0, 60)
+    # N is a mismatch and cannot sit inside a seed
+    n = exact.copy(); n[50] = 4
+    assert one(n) == (101, 0, 100, 0, 0, 95)
+    n = a[100:136].copy(); n[18] = 4          # 36 bases, N in the middle: no 19-mer without N
+    assert one(n) is None
+
+
+def test_bundled_golden_is_what_the_oracle_computes(bundled):
+    from oracle import oracle
+    hits = oracle.anchor_reads(oracle.encode(bundled["anchor"]), bundled["codes"], threads=4)
+    assert hits_equal(hits, bundled["oracle_hits"])
+    assert len(hits) == 1261 and len(set(hits["read_id"] >> 1)) == 647
+    # multi-thread == single-thread, and lens == stride is the same as lens=None
+    sub = bundled["codes"][:4000]
+    h1 = oracle.anchor_reads(oracle.encode(bundled["anchor"]), sub, threads=1)
+    h2 = oracle.anchor_reads(oracle.encode(bundled["anchor"]), sub, lens=np.full(4000, 101, np.uint16), threads=3)
+    assert hits_equal(h1, h2)
