@@ -60,8 +60,8 @@ class AnchorIndex:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            lib().af_index_free(h)
+        if h and _lib._lib is not None:
+            _lib._lib.af_index_free(h)
 
 
 class DeviceIndex:
@@ -74,8 +74,8 @@ class DeviceIndex:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            lib().af_dev_index_free(h)
+        if h and _lib._lib is not None:
+            _lib._lib.af_dev_index_free(h)
 
 
 class PackedBatch:
@@ -225,8 +225,8 @@ class Anchorer:
         return self._pipe
 
     def close_pipeline(self):
-        if self._pipe:
-            lib().af_pipeline_free(self._pipe)
+        if self._pipe and _lib._lib is not None:
+            _lib._lib.af_pipeline_free(self._pipe)
         self._pipe, self._pipe_key = None, None
 
     def anchor_host(self, batch, slot_pairs=1 << 20, n_slots=3, hits_out=None):

@@ -1,0 +1,180 @@
+"""Command-line drivers with the reference's flags (Anchored_Fusion.py:15-30,
+Anchored_Fusion_singlecell.py:16-29), running the anchoring stage on the GPU.
+
+Scope: these drivers do what the reference scripts do up to and including the anchoring stage
+(gene-name parsing, per-gene anchor FASTA, the stage's output files) and then add the
+record interpretation that sits directly on those records (split points via contact_reads).
+The later stages (genome bwa, BLAT, the CNN/Transformer filter) are out of scope; because every
+stage of the reference is guarded by the existence of its output file, running the reference
+script afterwards on the same --out_folder picks up from here.
+"""
+import argparse
+import os
+import re
+import sys
+import time
+
+from .functions import combine_split_reads, split_records
+from .stage import anchor_stage
+
+
+def _common_flags(p):
+    p.add_argument('--file_anchored_cds', type=str, required=True, default='', help='Target gene fasta file of anchored transcript')
+    p.add_argument('--gene_names', type=str, default='', help='The file of target gene names')
+    return p
+
+
+def _tail_flags(p):
+    p.add_argument('--out_folder', type=str, default='./', help='The folder of the output file')
+    p.add_argument('--file_ref_seq', type=str, default='', help='The reference sequence file (used by later stages only)')
+    p.add_argument('--file_ref_ann', type=str, default='', help='The reference annotation file (used by later stages only)')
+    p.add_argument('--not_filter_false_positive', action='store_true', help='Accepted for compatibility; the filter is a later stage.')
+    p.add_argument('--not_train_filter_model', action='store_true', help='Accepted for compatibility; the filter is a later stage.')
+    p.add_argument('--model_file', type=str, default='./data/model.pt', help='Accepted for compatibility.')
+    p.add_argument('--positive_samples', type=str, default='./data/positive_samples.txt', help='Accepted for compatibility.')
+    p.add_argument('--homo_gene_file', type=str, default='./data/homo_gene.npy', help='Accepted for compatibility.')
+    p.add_argument('--negative_samples', type=str, default='./Model/negative_samples.txt', help='Accepted for compatibility.')
+    p.add_argument('--thread', type=str, default='1', help='The threads number you want use.')
+    p.add_argument('--gpu_number', type=str, default='-1', help="The gpu number you want use ('-1': first visible GPU).")
+    return p
+
+
+_NOISE = re.compile(r'gene|specie|trans|for|homo|sapiens', re.IGNORECASE)
+
+
+def parse_gene_names(file_anchored_cds, gene_names_file=''):
+    """Gene names as the reference derives them (Anchored_Fusion.py:58-80): from --gene_names, one per
+    line, else from the FASTA headers with accession-like tokens and annotation words dropped."""
+    if gene_names_file and os.path.exists(gene_names_file):
+        with open(gene_names_file) as fh:
+            return [l.rstrip() for l in fh if l.rstrip() != '']
+    names = []
+    with open(file_anchored_cds) as fh:
+        for line in fh:
+            if not line.startswith('>'):
+                continue
+            tokens = [t for t in line.rstrip()[1:].split(' ')
+                      if not re.match(r'[a-zA-Z]+_\d+\.\d+', t) and not _NOISE.search(t)]
+            names.append(tokens[0])
+    return names
+
+
+def split_anchor_fasta(file_anchored_cds, gene_names, path_of):
+    """Write one <work>_anchored_gene_sequence.fa per gene (Anchored_Fusion.py:123-165).  QUIRK kept:
+    the reference starts at line 1 and skips exactly one header per gene, i.e. the i-th FASTA
+    record goes to the i-th gene name."""
+    with open(file_anchored_cds) as fh:
+        lines = fh.readlines()
+    i, out = 1, []
+    for gene in gene_names:
+        path = path_of(gene)
+        with open(path, 'w') as o:
+            o.write('>' + gene + '\n')
+            while i < len(lines) and not lines[i].startswith('>'):
+                o.write(lines[i])
+                i += 1
+        i += 1
+        out.append(path)
+    return out
+
+
+def _mkdir(p):
+    os.makedirs(p, exist_ok=True)
+
+
+def write_split_points(stats, gene, path):
+    """type / split point / support table from the raw anchored records (contact_reads semantics,
+    functions.py:892-952, before the genome-contiguity filter of del_too_many_reads)."""
+    rows = []
+    with open(stats['raw_sam']) as fh:
+        for line in fh:
+            a = line.rstrip('\n').split('\t')
+            rows.append((a[0], a[2], a[3], a[5], a[9]))
+    groups = combine_split_reads(split_records(rows))
+    with open(path, 'w') as o:
+        o.write('gene\tsplit_point\ttype\tsupport\tseq_left\tseq_right\n')
+        for g in sorted(groups, key=lambda g: (-g.cnt, g.breakpoint)):
+            o.write('%s\t%d\t%s\t%d\t%s\t%s\n' % (gene, g.breakpoint, g.type_, g.cnt, g.seq_left, g.seq_right))
+    return groups
+
+
+def run_gene_sample(file_anchored_seq, gene, fastq1, fastq2, out_dir_name, args):
+    done = out_dir_name + '_anchored_reads.bam'
+    if os.path.exists(done) and os.path.exists(out_dir_name + '_realign_reads.bam'):
+        print('[anchoring] %s: outputs exist, skipping (same existence guard as the reference)' % out_dir_name)
+        return None
+    t0 = time.time()
+    stats = anchor_stage(file_anchored_seq, fastq1, fastq2, out_dir_name, thread=args.thread,
+                         gpu_number=args.gpu_number, gene_name=gene)
+    groups = write_split_points(stats, gene, out_dir_name + '_split_points.txt')
+    dt = time.time() - t0
+    print('[anchoring] %s: %d pairs, %d anchored reads, %d half-anchored pairs, %d split-point groups, %.2f s (%.0f pairs/s)'
+          % (gene, stats['pairs'], stats['anchored'], stats['half_anchored_pairs'], len(groups), dt, stats['pairs'] / max(dt, 1e-9)))
+    return stats
+
+
+def main_bulk(argv=None):
+    p = argparse.ArgumentParser(description='Anchor Gene Fusion Detection (c) -- B200 anchoring stage')
+    _common_flags(p)
+    p.add_argument('--fastq1', type=str, default='fastq_1.fastq', help='The fastq1 file to scan')
+    p.add_argument('--fastq2', type=str, default='fastq_2.fastq', help='The fastq2 file to scan')
+    _tail_flags(p)
+    args = p.parse_args(argv)
+    gene_names = parse_gene_names(args.file_anchored_cds, args.gene_names)
+    _mkdir(args.out_folder)
+
+    def work_prefix(gene):      # <out>/<gene>_fusion/work_dir/<gene>_fusion   (Anchored_Fusion.py:127-131)
+        folder = args.out_folder + '/' + gene + '_fusion'
+        _mkdir(folder + '/work_dir/')
+        _mkdir(folder + '/model_dir/')
+        return folder + '/work_dir/' + gene + '_fusion'
+
+    fastas = split_anchor_fasta(args.file_anchored_cds, gene_names, lambda g: work_prefix(g) + '_anchored_gene_sequence.fa')
+    for gene, fa in zip(gene_names, fastas):
+        run_gene_sample(fa, gene, args.fastq1, args.fastq2, work_prefix(gene), args)
+    return 0
+
+
+def discover_cells(fastq_dir):
+    """(cell, file_1, file_2) triples as the reference finds them (Anchored_Fusion_singlecell.py:86-113):
+    sorted directory listing, `<cell>_1.<ext>` immediately followed by `<cell>_2.<ext>`."""
+    names = sorted(os.listdir(fastq_dir + '/'))
+    cells = []
+    for i, f in enumerate(names):
+        for ext in ('.fastq', '.fastq.gz', '.fq.gz', '.fq'):
+            m = re.findall(r'(\S+)_1' + re.escape(ext) + '$', f)
+            if m:
+                nxt = names[i + 1] if i + 1 < len(names) else ''
+                if nxt == m[0] + '_2' + ext:
+                    cells.append((m[0], f, nxt))
+                break
+    return cells
+
+
+def main_singlecell(argv=None):
+    p = argparse.ArgumentParser(description='Anchor Gene Fusion Detection, single cell (c) -- B200 anchoring stage')
+    _common_flags(p)
+    p.add_argument('--fastq_dir', type=str, required=True, default='', help='The folder of fastq files, one <cell>_1/<cell>_2 pair per cell')
+    _tail_flags(p)
+    args = p.parse_args(argv)
+    gene_names = parse_gene_names(args.file_anchored_cds, args.gene_names)
+    cells = discover_cells(args.fastq_dir)
+    _mkdir(args.out_folder)
+
+    def gene_prefix(gene):      # <out>/<gene>/work_dir/<gene>_fusion   (Anchored_Fusion_singlecell.py:156-160)
+        folder = args.out_folder + '/' + gene
+        _mkdir(folder + '/work_dir/')
+        _mkdir(folder + '/model_dir/')
+        return folder + '/work_dir/' + gene + '_fusion'
+
+    fastas = split_anchor_fasta(args.file_anchored_cds, gene_names, lambda g: gene_prefix(g) + '_anchored_gene_sequence.fa')
+    for gene, fa in zip(gene_names, fastas):
+        for cell, f1, f2 in cells:
+            cell_dir = args.out_folder + '/' + gene + '/work_dir/' + cell
+            _mkdir(cell_dir)
+            run_gene_sample(fa, gene, args.fastq_dir + '/' + f1, args.fastq_dir + '/' + f2, cell_dir + '/' + gene + '_fusion', args)
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main_bulk())

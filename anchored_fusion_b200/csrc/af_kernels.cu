@@ -96,6 +96,8 @@ struct af_dev_index {
 // ------------------------------------------------------------------------------------------
 // seed scan
 // ------------------------------------------------------------------------------------------
+static const int CB_THREADS = 256, CB_ITEMS = 8, CB_PER_BLOCK = CB_THREADS * CB_ITEMS;   // compaction chunk
+
 __device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -143,82 +145,115 @@ __device__ __forceinline__ void load_tile(uint32_t (&w)[4 * Q], const uint4 *__r
     }
 }
 
+__device__ __forceinline__ uint32_t tile_valid_mask(long long tile, long long n_pairs) {
+    long long left = n_pairs - tile * 32;
+    return left >= 32 ? FULL : (left <= 0 ? 0u : ((1u << left) - 1u));
+}
+
+static const int SCAN_LOCAL_CHUNKS = 64;
+
+// flags[tile] = (ballot of mate-1 flags, ballot of mate-2 flags), lanes past n_pairs cleared.
+// The number of flagged reads per compaction chunk is accumulated in shared memory (cc_local,
+// chunks relative to the CTA's first chunk) and flushed once per CTA: every CTA owns a
+// contiguous tile range, so concurrent CTAs never hammer the same global counter.
 template <int W, int KP, int Q>
-__device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long tile, int lane, int nprobe,
-                                          const uint32_t *filt, uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags) {
+__device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long tile, long long n_pairs, int lane,
+                                          int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
+                                          uint2 *__restrict__ flags, uint32_t *cc_local, long long chunk0,
+                                          uint32_t *__restrict__ chunk_counts) {
     uint32_t a1 = scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
     uint32_t a2 = scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
-    uint32_t b1 = __ballot_sync(FULL, a1 != 0), b2 = __ballot_sync(FULL, a2 != 0);
-    if (lane == 0) flags[tile] = make_uint2(b1, b2);
+    const uint32_t vm = tile_valid_mask(tile, n_pairs);
+    const uint32_t b1 = __ballot_sync(FULL, a1 != 0) & vm, b2 = __ballot_sync(FULL, a2 != 0) & vm;
+    if (lane == 0) {
+        flags[tile] = make_uint2(b1, b2);
+        const uint32_t c = __popc(b1) + __popc(b2);
+        if (chunk_counts && c) {
+            const long long rel = tile / CB_PER_BLOCK - chunk0;
+            if (rel < SCAN_LOCAL_CHUNKS) atomicAdd(&cc_local[rel], c);
+            else atomicAdd(&chunk_counts[tile / CB_PER_BLOCK], c);
+        }
+    }
 }
 
 // Persistent kernel, one CTA per SM: the anchor filter is staged into shared memory once, then
-// each warp walks tiles of 32 pairs (one pair per lane, all of it in registers).
-// PF = true (<= 512 threads, 128 registers): the loads of the warp's NEXT tile are issued before
-// the current tile is scanned (register double buffer), so HBM latency overlaps the probes of
-// the same warp.  PF = false (<= 1024 threads, 64 registers): latency is hidden by occupancy.
+// the CTA's warps walk its contiguous range of tiles (32 pairs per tile, one pair per lane, all
+// of it in registers).
+// PF = true (<= 768 threads): the loads of the warp's NEXT tile are issued before the current
+// tile is scanned (register double buffer), so HBM latency overlaps the probes of the same warp.
+// PF = false (<= 1024 threads, 64 registers): latency is hidden by occupancy alone.
 template <int W, int KP, int MAXT, bool PF>
 __global__ void __launch_bounds__(MAXT, 1)
-k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, int nprobe, const uint32_t *__restrict__ g_filter,
-            uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags) {
+k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pairs, int nprobe,
+            const uint32_t *__restrict__ g_filter, uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags,
+            uint32_t *__restrict__ chunk_counts) {
     extern __shared__ uint32_t filt[];
+    __shared__ uint32_t cc_local[SCAN_LOCAL_CHUNKS];
     constexpr int Q = (2 * W + 3) / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const long long stride = (long long)gridDim.x * nwarps;
-    long long tile = (long long)blockIdx.x * nwarps + warp;
+    const long long t_begin = n_tiles * blockIdx.x / gridDim.x, t_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+    const long long chunk0 = t_begin / CB_PER_BLOCK;
+    const long long stride = nwarps;
+    long long tile = t_begin + warp;
+    if (threadIdx.x < SCAN_LOCAL_CHUNKS) cc_local[threadIdx.x] = 0;
     if constexpr (PF) {
         uint32_t wa[4 * Q], wb[4 * Q];
-        if (tile < n_tiles) load_tile<Q>(wa, packed, tile, lane);   // in flight while the filter is staged
+        if (tile < t_end) load_tile<Q>(wa, packed, tile, lane);   // in flight while the filter is staged
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) filt[i] = g_filter[i];
         __syncthreads();
-        while (tile < n_tiles) {
+        while (tile < t_end) {
             const long long t2 = tile + stride;
-            if (t2 < n_tiles) load_tile<Q>(wb, packed, t2, lane);
-            scan_tile<W, KP, Q>(wa, tile, lane, nprobe, filt, fmul, nb, flags);
-            if (t2 >= n_tiles) break;
+            if (t2 < t_end) load_tile<Q>(wb, packed, t2, lane);
+            scan_tile<W, KP, Q>(wa, tile, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
+            if (t2 >= t_end) break;
             const long long t3 = t2 + stride;
-            if (t3 < n_tiles) load_tile<Q>(wa, packed, t3, lane);
-            scan_tile<W, KP, Q>(wb, t2, lane, nprobe, filt, fmul, nb, flags);
+            if (t3 < t_end) load_tile<Q>(wa, packed, t3, lane);
+            scan_tile<W, KP, Q>(wb, t2, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
             tile = t3;
         }
     } else {
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) filt[i] = g_filter[i];
         __syncthreads();
-        for (; tile < n_tiles; tile += stride) {
+        for (; tile < t_end; tile += stride) {
             uint32_t w[4 * Q];
             load_tile<Q>(w, packed, tile, lane);
-            scan_tile<W, KP, Q>(w, tile, lane, nprobe, filt, fmul, nb, flags);
+            scan_tile<W, KP, Q>(w, tile, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
         }
+    }
+    if (chunk_counts) {
+        __syncthreads();
+        if (threadIdx.x < SCAN_LOCAL_CHUNKS && cc_local[threadIdx.x]) atomicAdd(&chunk_counts[chunk0 + threadIdx.x], cc_local[threadIdx.x]);
     }
 }
 
-static int g_scan_threads = 512, g_scan_prefetch = 1;
-// tuning knob: threads per CTA (0 = default 512) and mode (0 = default, 1 = register
-// double buffer with <= 512 threads, 2 = no prefetch, up to 1024 threads)
+static int g_scan_threads = 512, g_scan_mode = 1;
+// tuning knob: mode 0/1 = register double buffer (threads <= 512, default 512), 2 = no prefetch
+// (threads <= 1024), 3 = register double buffer under an 85-register cap (threads <= 768)
 extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
-    int pf = mode == 2 ? 0 : 1;
-    int maxt = pf ? 512 : 1024;
+    if (mode == 0) mode = 1;
+    if (mode < 1 || mode > 3) { af_set_error("af_seed_scan_config: mode must be 0..3"); return AF_ERR_ARG; }
+    const int maxt = mode == 1 ? 512 : (mode == 2 ? 1024 : 768);
     if (threads_per_block == 0) threads_per_block = maxt;
     if (threads_per_block < 64 || threads_per_block > maxt || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..%d, multiple of 32", maxt); return AF_ERR_ARG; }
     g_scan_threads = threads_per_block;
-    g_scan_prefetch = pf;
+    g_scan_mode = mode;
     return AF_OK;
 }
 
 template <int W, int KP, int MAXT, bool PF>
 static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
-                       cudaStream_t st) {
+                       uint32_t *chunk_counts, cudaStream_t st) {
     size_t smem = (size_t)d->nb * 4;
     static bool attr_set[64] = {false};  // per device
     if (!attr_set[d->device & 63]) {
-        AF_CUDA(cudaFuncSetAttribute(k_seed_scan<W, KP, MAXT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AF_CUDA(cudaFuncSetAttribute(k_seed_scan<W, KP, MAXT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));  // + 256 B static counters
         attr_set[d->device & 63] = true;
     }
     int nwarps = g_scan_threads / 32;
     long long want = (n_tiles + nwarps - 1) / nwarps;
     int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
-    k_seed_scan<W, KP, MAXT, PF><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, nprobe, d->d_filter,
-                                                                     d->fmul, d->nb, (uint2 *)flags);
+    k_seed_scan<W, KP, MAXT, PF><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
+                                                                     d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts);
     g_launches++;
     AF_CUDA(cudaGetLastError());
     return AF_OK;
@@ -226,15 +261,16 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
 
 template <int W, int KP>
 static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
-                            cudaStream_t st) {
-    return g_scan_prefetch ? launch_scan<W, KP, 512, true>(d, b, n_tiles, nprobe, flags, st)
-                           : launch_scan<W, KP, 1024, false>(d, b, n_tiles, nprobe, flags, st);
+                            uint32_t *cc, cudaStream_t st) {
+    if (g_scan_mode == 2) return launch_scan<W, KP, 1024, false>(d, b, n_tiles, nprobe, flags, cc, st);
+    if (g_scan_mode == 3) return launch_scan<W, KP, 768, true>(d, b, n_tiles, nprobe, flags, cc, st);
+    return launch_scan<W, KP, 512, true>(d, b, n_tiles, nprobe, flags, cc, st);
 }
 
 #define AF_SCAN_CASE(WW)                                                                       \
     case WW:                                                                                   \
-        return kp == 12 ? launch_scan_mode<WW, 12>(d, b, n_tiles, nprobe, flags, st)           \
-                        : launch_scan_mode<WW, 13>(d, b, n_tiles, nprobe, flags, st);
+        return kp == 12 ? launch_scan_mode<WW, 12>(d, b, n_tiles, nprobe, flags, cc, st)       \
+                        : launch_scan_mode<WW, 13>(d, b, n_tiles, nprobe, flags, cc, st);
 
 static int batch_check(const af_dev_index *d, const af_batch_t *b, af_layout_t *lay) {
     if (!d || !b) { af_set_error("null index or batch"); return AF_ERR_ARG; }
@@ -247,7 +283,7 @@ static int batch_check(const af_dev_index *d, const af_batch_t *b, af_layout_t *
     return AF_OK;
 }
 
-static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *flags, cudaStream_t st) {
+static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *flags, uint32_t *cc, cudaStream_t st) {
     af_layout_t lay;
     int rc = batch_check(d, b, &lay);
     if (rc) return rc;
@@ -269,15 +305,16 @@ static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *
 
 extern "C" int af_seed_scan(const af_dev_index_t *d, const af_batch_t *batch, uint32_t *d_flags, void *stream) {
     AF_CUDA(cudaSetDevice(d ? d->device : 0));
-    return seed_scan_impl(d, batch, d_flags, (cudaStream_t)stream);
+    return seed_scan_impl(d, batch, d_flags, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------
-// stream compaction (ballot / popc / prefix sums); deterministic, ordered by read_id
+// stream compaction (ballot / popc / prefix sums); deterministic, ordered by read_id.
+// Every producer kernel leaves per-chunk counts (chunk = CB_PER_BLOCK items) behind with a
+// handful of atomics, so each compaction is ONE scatter kernel: chunk base = sum of the counts
+// of the chunks before it, offsets inside the chunk by a block-wide exclusive scan.
 // ------------------------------------------------------------------------------------------
-static const int CB_THREADS = 256, CB_ITEMS = 8, CB_PER_BLOCK = CB_THREADS * CB_ITEMS;
-
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *smem /*>=9 words*/, uint32_t &total) {
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *smem /*>=9 words*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -289,39 +326,16 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *smem /
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) { uint32_t t = __shfl_up_sync(FULL, si, o); if (lane >= o) si += t; }
         if (lane < (CB_THREADS / 32)) smem[lane] = si - s;
-        if (lane == (CB_THREADS / 32) - 1) smem[8] = si;
     }
     __syncthreads();
-    total = smem[8];
     uint32_t r = smem[warp] + inc - v;
     __syncthreads();
     return r;
 }
 
-__device__ __forceinline__ uint32_t tile_valid_mask(long long tile, long long n_pairs) {
-    long long left = n_pairs - tile * 32;
-    return left >= 32 ? FULL : (left <= 0 ? 0u : ((1u << left) - 1u));
-}
-
-__global__ void __launch_bounds__(CB_THREADS)
-k_flag_count(const uint2 *__restrict__ flags, long long n_tiles, long long n_pairs, uint32_t *__restrict__ blk_counts,
-             uint32_t *__restrict__ counts) {
-    __shared__ uint32_t sm[9];
-    uint32_t c = 0;
-    long long t0 = (long long)blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
-#pragma unroll
-    for (int i = 0; i < CB_ITEMS; i++) {
-        long long t = t0 + i;
-        if (t < n_tiles) { uint2 f = flags[t]; uint32_t vm = tile_valid_mask(t, n_pairs); c += __popc(f.x & vm) + __popc(f.y & vm); }
-    }
-    uint32_t total;
-    block_excl_scan(c, sm, total);
-    if (threadIdx.x == 0) { blk_counts[blockIdx.x] = total; atomicAdd(&counts[AF_CNT_FLAGGED], total); }
-}
-
-__device__ __forceinline__ uint32_t sum_before(const uint32_t *blk_counts, int upto, uint32_t *sm) {
+__device__ __forceinline__ uint32_t sum_before(const uint32_t *chunk_counts, uint32_t upto, uint32_t *sm) {
     uint32_t s = 0;
-    for (int i = threadIdx.x; i < upto; i += blockDim.x) s += blk_counts[i];
+    for (uint32_t i = threadIdx.x; i < upto; i += blockDim.x) s += chunk_counts[i];
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -332,121 +346,103 @@ __device__ __forceinline__ uint32_t sum_before(const uint32_t *blk_counts, int u
     return r;
 }
 
+// flag words -> candidate read_ids; total -> counts[AF_CNT_FLAGGED]
 __global__ void __launch_bounds__(CB_THREADS)
-k_flag_scatter(const uint2 *__restrict__ flags, long long n_tiles, long long n_pairs,
-               const uint32_t *__restrict__ blk_counts, uint32_t *__restrict__ cand, uint32_t cand_cap,
-               uint32_t *__restrict__ counts) {
+k_flag_scatter(const uint2 *__restrict__ flags, long long n_tiles, const uint32_t *__restrict__ chunk_counts,
+               uint32_t n_chunks, uint32_t *__restrict__ cand, uint32_t cand_cap, uint32_t *counts) {
     __shared__ uint32_t sm[9];
-    uint32_t base = sum_before(blk_counts, blockIdx.x, sm);
-    uint2 f[CB_ITEMS];
-    uint32_t c = 0;
-    long long t0 = (long long)blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
+    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const uint32_t mine = chunk_counts[chunk];
+        if (mine == 0) continue;                       // uniform across the block
+        const uint32_t base = sum_before(chunk_counts, chunk, sm);
+        if (threadIdx.x == 0) atomicAdd(&counts[AF_CNT_FLAGGED], mine);
+        uint2 f[CB_ITEMS];
+        uint32_t c = 0;
+        const long long t0 = (long long)chunk * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
 #pragma unroll
-    for (int i = 0; i < CB_ITEMS; i++) {
-        long long t = t0 + i;
-        f[i] = make_uint2(0, 0);
-        if (t < n_tiles) { uint2 v = flags[t]; uint32_t vm = tile_valid_mask(t, n_pairs); f[i] = make_uint2(v.x & vm, v.y & vm); }
-        c += __popc(f[i].x) + __popc(f[i].y);
-    }
-    uint32_t total, off = base + block_excl_scan(c, sm, total);
-    bool over = false;
-#pragma unroll
-    for (int i = 0; i < CB_ITEMS; i++) {
-        uint32_t any = f[i].x | f[i].y;
-        while (any) {
-            int l = __ffs(any) - 1;
-            any &= any - 1;
-            uint32_t pair = (uint32_t)((t0 + i) * 32 + l);
-            if ((f[i].x >> l) & 1) { if (off < cand_cap) cand[off] = pair * 2; else over = true; off++; }
-            if ((f[i].y >> l) & 1) { if (off < cand_cap) cand[off] = pair * 2 + 1; else over = true; off++; }
+        for (int i = 0; i < CB_ITEMS; i++) {
+            f[i] = (t0 + i < n_tiles) ? flags[t0 + i] : make_uint2(0, 0);
+            c += __popc(f[i].x) + __popc(f[i].y);
         }
+        uint32_t off = base + block_excl_scan(c, sm);
+        bool over = false;
+#pragma unroll
+        for (int i = 0; i < CB_ITEMS; i++) {
+            uint32_t any = f[i].x | f[i].y;
+            while (any) {
+                const int l = __ffs(any) - 1;
+                any &= any - 1;
+                const uint32_t pair = (uint32_t)((t0 + i) * 32 + l);
+                if ((f[i].x >> l) & 1) { if (off < cand_cap) cand[off] = pair * 2; else over = true; off++; }
+                if ((f[i].y >> l) & 1) { if (off < cand_cap) cand[off] = pair * 2 + 1; else over = true; off++; }
+            }
+        }
+        if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_CAND_OVERFLOW);
     }
-    if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_CAND_OVERFLOW);
 }
 
+// candidates kept by k_verify -> seeded list; total -> counts[AF_CNT_SEEDED]
 __global__ void __launch_bounds__(CB_THREADS)
-k_hit_count(const uint4 *__restrict__ slots, uint32_t cand_cap, uint32_t *__restrict__ blk_counts, uint32_t *counts) {
+k_sel_scatter(const uint32_t *__restrict__ items, const uint8_t *__restrict__ keep, uint32_t cap,
+              const uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ out, uint32_t *counts) {
     __shared__ uint32_t sm[9];
-    uint32_t n = min(counts[AF_CNT_SEEDED], cand_cap), c = 0;
-    uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
-    if (blockIdx.x * CB_PER_BLOCK < n) {
+    const uint32_t n = min(counts[AF_CNT_FLAGGED], cap), n_chunks = (n + CB_PER_BLOCK - 1) / CB_PER_BLOCK;
+    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const uint32_t mine = chunk_counts[chunk];
+        if (mine == 0) continue;
+        const uint32_t base = sum_before(chunk_counts, chunk, sm);
+        if (threadIdx.x == 0) atomicAdd(&counts[AF_CNT_SEEDED], mine);
+        const uint32_t i0 = chunk * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
+        uint32_t v[CB_ITEMS], c = 0;
+        bool k[CB_ITEMS];
+#pragma unroll
+        for (int i = 0; i < CB_ITEMS; i++) {
+            k[i] = (i0 + i < n) && keep[i0 + i] != 0;
+            v[i] = k[i] ? items[i0 + i] : 0u;
+            c += k[i];
+        }
+        uint32_t off = base + block_excl_scan(c, sm);
 #pragma unroll
         for (int i = 0; i < CB_ITEMS; i++)
-            if (i0 + i < n) c += (slots[i0 + i].z >> 16) != 0;  // m_len
+            if (k[i]) out[off++] = v[i];   // out has the capacity of items: cannot overflow
     }
-    uint32_t total;
-    block_excl_scan(c, sm, total);
-    if (threadIdx.x == 0) { blk_counts[blockIdx.x] = total; if (total) atomicAdd(&counts[AF_CNT_HITS], total); }
 }
 
+// result slots of k_extend with m_len != 0 -> hit list; total -> counts[AF_CNT_HITS]
 __global__ void __launch_bounds__(CB_THREADS)
-k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cand_cap, const uint32_t *__restrict__ blk_counts,
+k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cap, const uint32_t *__restrict__ chunk_counts,
               uint4 *__restrict__ hits, uint32_t hits_cap, uint32_t *counts) {
     __shared__ uint32_t sm[9];
-    uint32_t n = min(counts[AF_CNT_SEEDED], cand_cap);
-    if (blockIdx.x * CB_PER_BLOCK >= n) return;
-    uint32_t base = sum_before(blk_counts, blockIdx.x, sm);
-    uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS, c = 0;
-    uint4 v[CB_ITEMS];
+    const uint32_t n = min(counts[AF_CNT_SEEDED], cap), n_chunks = (n + CB_PER_BLOCK - 1) / CB_PER_BLOCK;
+    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const uint32_t mine = chunk_counts[chunk];
+        if (mine == 0) continue;
+        const uint32_t base = sum_before(chunk_counts, chunk, sm);
+        if (threadIdx.x == 0) atomicAdd(&counts[AF_CNT_HITS], mine);
+        const uint32_t i0 = chunk * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
+        uint4 v[CB_ITEMS];
+        uint32_t c = 0;
 #pragma unroll
-    for (int i = 0; i < CB_ITEMS; i++) {
-        v[i] = make_uint4(0, 0, 0, 0);
-        if (i0 + i < n) v[i] = slots[i0 + i];
-        c += (v[i].z >> 16) != 0;
-    }
-    uint32_t total, off = base + block_excl_scan(c, sm, total);
-    bool over = false;
-#pragma unroll
-    for (int i = 0; i < CB_ITEMS; i++)
-        if ((v[i].z >> 16) != 0) { if (off < hits_cap) hits[off] = v[i]; else over = true; off++; }
-    if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
-}
-
-// compaction of a uint32 list by a per-item keep byte; n lives in counts[n_idx] on the device
-__global__ void __launch_bounds__(CB_THREADS)
-k_sel_count(const uint8_t *__restrict__ keep, uint32_t cap, int n_idx, int out_idx, uint32_t *__restrict__ blk_counts,
-            uint32_t *counts) {
-    __shared__ uint32_t sm[9];
-    uint32_t n = min(counts[n_idx], cap), c = 0;
-    uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
-    if (blockIdx.x * CB_PER_BLOCK < n) {
+        for (int i = 0; i < CB_ITEMS; i++) {
+            v[i] = (i0 + i < n) ? slots[i0 + i] : make_uint4(0, 0, 0, 0);
+            c += (v[i].z >> 16) != 0;   // m_len
+        }
+        uint32_t off = base + block_excl_scan(c, sm);
+        bool over = false;
 #pragma unroll
         for (int i = 0; i < CB_ITEMS; i++)
-            if (i0 + i < n) c += keep[i0 + i] != 0;
+            if ((v[i].z >> 16) != 0) { if (off < hits_cap) hits[off] = v[i]; else over = true; off++; }
+        if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
     }
-    uint32_t total;
-    block_excl_scan(c, sm, total);
-    if (threadIdx.x == 0) { blk_counts[blockIdx.x] = total; if (total) atomicAdd(&counts[out_idx], total); }
-}
-
-__global__ void __launch_bounds__(CB_THREADS)
-k_sel_scatter(const uint32_t *__restrict__ items, const uint8_t *__restrict__ keep, uint32_t cap, int n_idx,
-              const uint32_t *__restrict__ blk_counts, uint32_t *__restrict__ out, const uint32_t *counts) {
-    __shared__ uint32_t sm[9];
-    uint32_t n = min(counts[n_idx], cap);
-    if (blockIdx.x * CB_PER_BLOCK >= n) return;
-    uint32_t base = sum_before(blk_counts, blockIdx.x, sm);
-    uint32_t i0 = blockIdx.x * CB_PER_BLOCK + threadIdx.x * CB_ITEMS, c = 0;
-    uint32_t v[CB_ITEMS];
-    bool k[CB_ITEMS];
-#pragma unroll
-    for (int i = 0; i < CB_ITEMS; i++) {
-        k[i] = (i0 + i < n) && keep[i0 + i] != 0;
-        v[i] = k[i] ? items[i0 + i] : 0u;
-        c += k[i];
-    }
-    uint32_t total, off = base + block_excl_scan(c, sm, total);
-#pragma unroll
-    for (int i = 0; i < CB_ITEMS; i++)
-        if (k[i]) out[off++] = v[i];   // out has the capacity of items: cannot overflow
 }
 
 // ------------------------------------------------------------------------------------------
 // verify: one THREAD per flagged read.  Removes the filter's false positives cheaply: exact
-// k'-mer membership from an L2-resident bitmap (independent loads, no probing chain), and for
-// the rare members a table walk plus a check that the exact match around the sample reaches k
-// bases.  A read is kept iff some diagonal holds >= k consecutive matches -- exactly the
-// SEEDED predicate of the spec, so k_extend only ever sees reads it will have to extend.
+// k'-mer membership from an L2-resident bitmap -- every sample's bit is loaded before any is
+// used, so one thread keeps ~18 loads in flight -- and for the rare members a table walk plus
+// a check that the exact match around the sample reaches k bases.  A read is kept iff some
+// diagonal holds >= k consecutive matches: exactly the SEEDED predicate of the spec, so
+// k_extend only ever sees reads it has to extend.
 // ------------------------------------------------------------------------------------------
 struct ReadRef {
     const uint32_t *packed;   // tile-interleaved words
@@ -472,68 +468,84 @@ __device__ __forceinline__ bool diag_match(const ReadRef &r, int s, int i, int d
     return anchor[ap] == b;
 }
 
+template <int KP>
 __global__ void __launch_bounds__(256)
 k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, const uint16_t *__restrict__ lens,
          const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
          const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts, uint32_t cand_cap,
          const uint32_t *__restrict__ member, const uint2 *__restrict__ table, uint32_t tmask,
-         const uint8_t *__restrict__ anchor, int G, int KP, int S, int K, uint8_t *__restrict__ keep) {
+         const uint8_t *__restrict__ anchor, int G, int K, uint8_t *__restrict__ keep,
+         uint32_t *__restrict__ chunk_counts) {
+    constexpr int S = 20 - KP;
+    constexpr int NPMAX = (AF_MAX_READ_LEN - KP) / S + 1;
+    constexpr uint32_t kpmask = (1u << (2 * KP)) - 1u;
     const uint32_t ncand = min(counts[AF_CNT_FLAGGED], cand_cap);
-    const uint32_t kpmask = (1u << (2 * KP)) - 1u;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += gridDim.x * blockDim.x) {
-        const uint32_t rid = cand[c], pair = rid >> 1;
-        ReadRef r;
-        r.packed = packed;
-        r.base = ((size_t)(pair >> 5) * Q * 32 + (pair & 31)) * 4;
-        r.wofs = (int)(rid & 1u) * W;
-        r.L = uniform_len > 0 ? uniform_len : (int)lens[rid];
-        r.nm = nullptr;
-        if (n_nreads > 0) {
-            int lo = 0, hi = n_nreads;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
-            if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
-        }
-        const int nprobe = r.L >= KP ? (r.L - KP) / S + 1 : 0;
-        // phase 1: membership bit of every sample (independent loads)
-        unsigned long long hit = 0;
-        uint32_t w0 = nprobe ? r.word(0) : 0u, w1 = (nprobe && W > 1) ? r.word(1) : 0u;
-        int wcur = 0;
-        for (int j = 0; j < nprobe; j++) {
-            const int o = 2 * j * S, wi = o >> 5;
-            if (wi != wcur) { w0 = (wi == wcur + 1) ? w1 : r.word(wi); w1 = wi + 1 < W ? r.word(wi + 1) : 0u; wcur = wi; }
-            const uint32_t key = __funnelshift_r(w0, w1, o & 31) & kpmask;
-            if ((member[key >> 5] >> (key & 31)) & 1u) hit |= 1ull << j;
-        }
-        // phase 2: the rare members -- walk the table, check that the exact run reaches K
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count so the ballots below are well defined
+    for (uint32_t c0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; c0 < ncand; c0 += gridDim.x * blockDim.x) {
+        const uint32_t c = c0 + lane;
         bool seeded = false;
-        while (hit && !seeded) {
-            const int j = __ffsll((long long)hit) - 1;
-            hit &= hit - 1;
-            const int p = j * S, o = 2 * p;
-            const uint32_t key = __funnelshift_r(r.word(o >> 5), (o >> 5) + 1 < W ? r.word((o >> 5) + 1) : 0u, o & 31) & kpmask;
-            if (r.nm) {   // a k'-mer that overlaps an N is no seed material
-                bool n = false;
-                for (int t = 0; t < KP; t++) n |= r.is_n(p + t);
-                if (n) continue;
+        if (c < ncand) {
+            const uint32_t rid = cand[c], pair = rid >> 1;
+            ReadRef r;
+            r.packed = packed;
+            r.base = ((size_t)(pair >> 5) * Q * 32 + (pair & 31)) * 4;
+            r.wofs = (int)(rid & 1u) * W;
+            r.L = uniform_len > 0 ? uniform_len : (int)lens[rid];
+            r.nm = nullptr;
+            if (n_nreads > 0) {
+                int lo = 0, hi = n_nreads;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
+                if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
             }
-            for (uint32_t slot = af_table_hash(key, tmask);; slot = (slot + 1) & tmask) {
-                const uint2 e = table[slot];
-                if (e.x == AF_T_EMPTY) break;
-                if (e.x != key) continue;
-                const int s = e.y >> 31, jpos = (int)(e.y & 0x7FFFFFFFu);
-                const int qp = s ? r.L - p - KP : p, d = jpos - qp;
-                int run = KP;
-                for (int i = qp - 1; run < K && diag_match(r, s, i, d, anchor, G); i--) run++;
-                for (int i = qp + KP; run < K && diag_match(r, s, i, d, anchor, G); i++) run++;
-                if (run >= K) { seeded = true; break; }
+            const int nprobe = r.L >= KP ? (r.L - KP) / S + 1 : 0;
+            uint32_t w[17];
+#pragma unroll
+            for (int t = 0; t < 16; t++) w[t] = t < W ? r.word(t) : 0u;
+            w[16] = 0;
+            // phase 1: membership bit of every sample; all loads are independent
+            uint32_t mbits[NPMAX];
+#pragma unroll
+            for (int j = 0; j < NPMAX; j++) {
+                const int o = 2 * j * S, wi = o >> 5;
+                const uint32_t key = __funnelshift_r(w[wi], w[wi + 1], o & 31) & kpmask;
+                mbits[j] = j < nprobe ? ((member[key >> 5] >> (key & 31)) & 1u) : 0u;
             }
+            unsigned long long hit = 0;
+#pragma unroll
+            for (int j = 0; j < NPMAX; j++) hit |= (unsigned long long)mbits[j] << j;
+            // phase 2: the rare members -- walk the table, check that the exact run reaches K
+            while (hit && !seeded) {
+                const int j = __ffsll((long long)hit) - 1;
+                hit &= hit - 1;
+                const int p = j * S, o = 2 * p;
+                const uint32_t key = __funnelshift_r(r.word(o >> 5), (o >> 5) + 1 < W ? r.word((o >> 5) + 1) : 0u, o & 31) & kpmask;
+                if (r.nm) {   // a k'-mer that overlaps an N is no seed material
+                    bool n = false;
+                    for (int t = 0; t < KP; t++) n |= r.is_n(p + t);
+                    if (n) continue;
+                }
+                for (uint32_t slot = af_table_hash(key, tmask);; slot = (slot + 1) & tmask) {
+                    const uint2 e = table[slot];
+                    if (e.x == AF_T_EMPTY) break;
+                    if (e.x != key) continue;
+                    const int s = e.y >> 31, jpos = (int)(e.y & 0x7FFFFFFFu);
+                    const int qp = s ? r.L - p - KP : p, d = jpos - qp;
+                    int run = KP;
+                    for (int i = qp - 1; run < K && diag_match(r, s, i, d, anchor, G); i--) run++;
+                    for (int i = qp + KP; run < K && diag_match(r, s, i, d, anchor, G); i++) run++;
+                    if (run >= K) { seeded = true; break; }
+                }
+            }
+            keep[c] = seeded ? 1 : 0;
         }
-        keep[c] = seeded ? 1 : 0;
+        const uint32_t bal = __ballot_sync(FULL, seeded);
+        if (lane == 0 && bal) atomicAdd(&chunk_counts[c0 / CB_PER_BLOCK], __popc(bal));
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// verify + extend: one warp per candidate read
+// extend: one warp per seeded read
 // ------------------------------------------------------------------------------------------
 struct ExtParams {
     int k, A, B, clip5, clip3, T, X;
@@ -654,7 +666,7 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
          const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
          const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts, uint32_t cand_cap,
          const uint2 *__restrict__ table, uint32_t tmask, const uint8_t *__restrict__ anchor, int G, int KP, int S,
-         ExtParams P, uint4 *__restrict__ slots) {
+         ExtParams P, uint4 *__restrict__ slots, uint32_t *__restrict__ chunk_counts) {
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t ncand = min(counts[AF_CNT_SEEDED], cand_cap);
@@ -736,6 +748,7 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
                 out.y = (uint32_t)(best_qb + d + 1);
                 out.z = (uint32_t)best_qb | ((uint32_t)(best_qe - best_qb) << 16);
                 out.w = (uint32_t)(L - best_qe) | ((uint32_t)(best_sc * 2 + s) << 16);
+                atomicAdd(&chunk_counts[c / CB_PER_BLOCK], 1u);
             }
             slots[c] = out;
         }
@@ -747,21 +760,22 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
 // ------------------------------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct WsLayout { size_t flags, blk1, cand, keep, cand2, slots, blk2, total; int nblk1, nblk2; };
+struct WsLayout { size_t flags, cc, cand, keep, cand2, slots, total, cc_bytes; uint32_t nch1, nch2; };
 
 static WsLayout ws_layout(long long n_pairs, long long cand_cap) {
     WsLayout w;
     long long n_tiles = (n_pairs + 31) / 32;
-    w.nblk1 = (int)((n_tiles + CB_PER_BLOCK - 1) / CB_PER_BLOCK);
-    w.nblk2 = (int)((cand_cap + CB_PER_BLOCK - 1) / CB_PER_BLOCK);
+    w.nch1 = (uint32_t)((n_tiles + CB_PER_BLOCK - 1) / CB_PER_BLOCK);
+    w.nch2 = (uint32_t)((cand_cap + CB_PER_BLOCK - 1) / CB_PER_BLOCK);
     size_t o = 0;
     w.flags = o; o += align256((size_t)n_tiles * 8);
-    w.blk1 = o; o += align256((size_t)(w.nblk1 + 1) * 4);
+    w.cc = o;                                            // chunk counts of the three compactions, zeroed per call
+    w.cc_bytes = align256(((size_t)w.nch1 + 2 * (size_t)w.nch2 + 3) * 4);
+    o += w.cc_bytes;
     w.cand = o; o += align256((size_t)cand_cap * 4);
     w.keep = o; o += align256((size_t)cand_cap);
     w.cand2 = o; o += align256((size_t)cand_cap * 4);
     w.slots = o; o += align256((size_t)cand_cap * 16);
-    w.blk2 = o; o += align256((size_t)(w.nblk2 + 1) * 4);
     w.total = o;
     return w;
 }
@@ -785,47 +799,47 @@ extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, voi
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     WsLayout w = ws_layout(b->n_pairs, cand_cap);
-    uint32_t *flags = (uint32_t *)(ws + w.flags), *blk1 = (uint32_t *)(ws + w.blk1), *cand = (uint32_t *)(ws + w.cand);
-    uint32_t *blk2 = (uint32_t *)(ws + w.blk2);
+    uint32_t *flags = (uint32_t *)(ws + w.flags), *cand = (uint32_t *)(ws + w.cand), *cand2 = (uint32_t *)(ws + w.cand2);
+    uint32_t *cc1 = (uint32_t *)(ws + w.cc), *cc2 = cc1 + w.nch1 + 1, *cc3 = cc2 + w.nch2 + 1;
+    uint8_t *keep = (uint8_t *)(ws + w.keep);
     uint4 *slots = (uint4 *)(ws + w.slots);
     AF_CUDA(cudaMemsetAsync(d_counts, 0, AF_N_COUNTS * sizeof(uint32_t), st));
     if (lay.n_tiles == 0) return AF_OK;
+    AF_CUDA(cudaMemsetAsync(cc1, 0, w.cc_bytes, st));
+    const int scatter_grid = d->num_sms * 4;
     cudaEvent_t ev;
     prof_mark(&ev, st);
-    rc = seed_scan_impl(d, b, flags, st);
+    rc = seed_scan_impl(d, b, flags, cc1, st);
     if (rc) return rc;
     prof_span(ev, st, ST_SCAN);
     prof_mark(&ev, st);
-    k_flag_count<<<w.nblk1, CB_THREADS, 0, st>>>((const uint2 *)flags, lay.n_tiles, b->n_pairs, blk1, d_counts);
-    k_flag_scatter<<<w.nblk1, CB_THREADS, 0, st>>>((const uint2 *)flags, lay.n_tiles, b->n_pairs, blk1, cand,
-                                                   (uint32_t)cand_cap, d_counts);
+    k_flag_scatter<<<(int)(w.nch1 < (uint32_t)scatter_grid ? w.nch1 : scatter_grid), CB_THREADS, 0, st>>>(
+        (const uint2 *)flags, lay.n_tiles, cc1, w.nch1, cand, (uint32_t)cand_cap, d_counts);
     prof_span(ev, st, ST_COMPACT1);
     prof_mark(&ev, st);
-    uint8_t *keep = (uint8_t *)(ws + w.keep);
-    uint32_t *cand2 = (uint32_t *)(ws + w.cand2);
     long long vthreads = cand_cap < (long long)d->num_sms * 2048 ? cand_cap : (long long)d->num_sms * 2048;
-    k_verify<<<(unsigned)((vthreads + 255) / 256), 256, 0, st>>>(
-        (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, b->nread_ids,
-        b->nmask, (int)b->n_nreads, cand, d_counts, (uint32_t)cand_cap, d->d_member, d->d_table, d->tmask, d->d_anchor,
-        d->G, d->kp, d->stride, d->P.k, keep);
-    k_sel_count<<<w.nblk2, CB_THREADS, 0, st>>>(keep, (uint32_t)cand_cap, AF_CNT_FLAGGED, AF_CNT_SEEDED, blk2, d_counts);
-    k_sel_scatter<<<w.nblk2, CB_THREADS, 0, st>>>(cand, keep, (uint32_t)cand_cap, AF_CNT_FLAGGED, blk2, cand2, d_counts);
+    const unsigned vgrid = (unsigned)((vthreads + 255) / 256);
+#define AF_VERIFY_ARGS (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, \
+        b->nread_ids, b->nmask, (int)b->n_nreads, cand, d_counts, (uint32_t)cand_cap, d->d_member, d->d_table,         \
+        d->tmask, d->d_anchor, d->G, d->P.k, keep, cc2
+    if (d->kp == 12) k_verify<12><<<vgrid, 256, 0, st>>>(AF_VERIFY_ARGS);
+    else k_verify<13><<<vgrid, 256, 0, st>>>(AF_VERIFY_ARGS);
+    const int sg2 = (int)(w.nch2 < (uint32_t)scatter_grid ? w.nch2 : scatter_grid);
+    k_sel_scatter<<<sg2, CB_THREADS, 0, st>>>(cand, keep, (uint32_t)cand_cap, cc2, cand2, d_counts);
     prof_span(ev, st, ST_VERIFY);
     prof_mark(&ev, st);
     ExtParams P = {d->P.k, d->P.A, d->P.B, d->P.clip5, d->P.clip3, d->P.T, d->P.X};
-    long long warps_wanted = cand_cap < (long long)d->num_sms * 64 ? cand_cap : (long long)d->num_sms * 64;
+    long long warps_wanted = cand_cap < (long long)d->num_sms * 40 ? cand_cap : (long long)d->num_sms * 40;
     int ext_blocks = (int)((warps_wanted + 7) / 8);
     k_extend<<<ext_blocks, 256, 0, st>>>((const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair,
                                          b->uniform_len, b->lens, b->nread_ids, b->nmask, (int)b->n_nreads, cand2,
                                          d_counts, (uint32_t)cand_cap, d->d_table, d->tmask, d->d_anchor, d->G, d->kp,
-                                         d->stride, P, slots);
+                                         d->stride, P, slots, cc3);
     prof_span(ev, st, ST_EXTEND);
     prof_mark(&ev, st);
-    k_hit_count<<<w.nblk2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, blk2, d_counts);
-    k_hit_scatter<<<w.nblk2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, blk2, (uint4 *)d_hits, (uint32_t)hits_cap,
-                                                  d_counts);
+    k_hit_scatter<<<sg2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, cc3, (uint4 *)d_hits, (uint32_t)hits_cap, d_counts);
     prof_span(ev, st, ST_COMPACT2);
-    g_launches += 8;
+    g_launches += 5;
     AF_CUDA(cudaGetLastError());
     return AF_OK;
 }
