@@ -163,32 +163,41 @@ class Anchorer:
         self.device = int(device)
         self.dev = torch.device("cuda", self.device)
         self.dindex = index.upload(self.device)
-        self._ws = None
-        self._ws_key = None
+        self._ws = {}
         self._pipe = None
         self._pipe_key = None
 
     # -- device-resident path -----------------------------------------------------------
-    def _workspace(self, n_pairs, cand_cap, hits_cap):
+    def _workspace(self, n_pairs, cand_cap, hits_cap, slot=0):
         key = (n_pairs, cand_cap, hits_cap)
-        if self._ws_key != key:
+        cur = self._ws.get(slot) if isinstance(self._ws, dict) else None
+        if cur is None or cur[0] != key:
             torch = self.torch
+            if not isinstance(self._ws, dict):
+                self._ws = {}
             nbytes = lib().af_workspace_bytes(n_pairs, cand_cap)
-            self._ws = (torch.empty(nbytes, dtype=torch.uint8, device=self.dev),
-                        torch.empty((max(hits_cap, 1), 4), dtype=torch.int32, device=self.dev),
-                        torch.zeros(_lib.N_COUNTS, dtype=torch.int32, device=self.dev))
-            self._ws_key = key
-        return self._ws
+            cur = (key, torch.empty(nbytes, dtype=torch.uint8, device=self.dev),
+                   torch.empty((max(hits_cap, 1), 4), dtype=torch.int32, device=self.dev),
+                   torch.zeros(_lib.N_COUNTS, dtype=torch.int32, device=self.dev),
+                   torch.cuda.Stream(device=self.dev) if slot else None)
+            self._ws[slot] = cur
+        return cur[1:]
 
-    def enqueue(self, batch, cand_cap=None, hits_cap=None, stream=None):
+    def slot_stream(self, slot):
+        """The side stream of workspace slot `slot` (> 0), created on first use."""
+        return self._ws[slot][4]
+
+    def enqueue(self, batch, cand_cap=None, hits_cap=None, stream=None, slot=0):
         """Launch the whole path on the current (or given) stream; no host sync.
+        `slot` selects an independent workspace so that consecutive batches can be in flight on
+        different streams (slot > 0 owns a side stream, used when `stream` is None).
         Returns (hits tensor [cap,4] int32 raw records, counts tensor)."""
         torch = self.torch
         n = batch.n_pairs
         cand_cap = int(cand_cap or 2 * max(n, 1))
         hits_cap = int(hits_cap or cand_cap)
-        ws, hits, counts = self._workspace(n, cand_cap, hits_cap)
-        st = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        ws, hits, counts, side = self._workspace(n, cand_cap, hits_cap, slot)
+        st = stream if stream is not None else (side if side is not None else torch.cuda.current_stream(self.dev))
         cb = batch.c_struct()
         check(lib().af_anchor_batch(self.dindex._h, ctypes.byref(cb), ws.data_ptr(), ws.numel(), cand_cap,
                                     hits.data_ptr(), hits_cap, counts.data_ptr(), ctypes.c_void_p(st.cuda_stream)))

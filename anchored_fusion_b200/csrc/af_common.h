@@ -22,7 +22,7 @@ static const uint32_t AF_F_HIGH = 0xA0080200u;   // high bit of each field
 static const uint32_t AF_F_REP = 0x00100401u;    // replicates a fingerprint into 3 fields
 static const uint32_t AF_F_EMPTY = 0x40000000u;  // empty, normal bucket
 static const int AF_F_SLOTS = 3;
-static const uint32_t AF_MAX_BUCKETS = 53248;    // 208 KB of the 227 KB shared memory
+static const uint32_t AF_MAX_BUCKETS = 53248;    // 208 KB of the 227 KB shared memory per CTA
 static const uint32_t AF_MIN_BUCKETS = 2048;
 
 AF_HD uint32_t af_umulhi(uint32_t a, uint32_t b) {

@@ -226,11 +226,12 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     }
 }
 
-static int g_scan_threads = 512, g_scan_mode = 1;
-// tuning knob: mode 0/1 = register double buffer (threads <= 512, default 512), 2 = no prefetch
-// (threads <= 1024), 3 = register double buffer under an 85-register cap (threads <= 768)
+static int g_scan_threads = 768, g_scan_mode = 3;
+// tuning knob: mode 0/3 = register double buffer under an 85-register cap (threads <= 768, the
+// default: 24 warps per SM), 1 = register double buffer with 128 registers (threads <= 512),
+// 2 = no prefetch (threads <= 1024)
 extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
-    if (mode == 0) mode = 1;
+    if (mode == 0) mode = 3;
     if (mode < 1 || mode > 3) { af_set_error("af_seed_scan_config: mode must be 0..3"); return AF_ERR_ARG; }
     const int maxt = mode == 1 ? 512 : (mode == 2 ? 1024 : 768);
     if (threads_per_block == 0) threads_per_block = maxt;

@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.02)
+            self._halt.wait(0.002)
 
     def stop(self):
         self._halt.set()
@@ -138,6 +138,9 @@ def main():
     ap.add_argument("--fusion-ppm", type=int, default=0)
     ap.add_argument("--kp", type=int, default=0)
     ap.add_argument("--scan-threads", type=int, default=0)
+    ap.add_argument("--scan-mode", type=int, default=0)
+    ap.add_argument("--slots", type=int, default=1, help="workspace slots / streams consecutive steps alternate between")
+    ap.add_argument("--cand-cap", type=int, default=0, help="candidate capacity per batch (default 2 x pairs: every read)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs", type=int, default=1_000_000, help="bounded sample for cpu_baseline")
     ap.add_argument("--ref-pairs", type=int, default=250_000, help="pairs per step of the reference arm")
@@ -148,6 +151,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
     import torch
     import anchored_fusion_b200 as af
     from anchored_fusion_b200 import dist as afdist
@@ -162,8 +167,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     L = lib()
-    if args.scan_threads:
-        L.af_seed_scan_config(args.scan_threads, 0)
+    if args.scan_threads or args.scan_mode:
+        from anchored_fusion_b200._lib import check
+        check(L.af_seed_scan_config(args.scan_threads, args.scan_mode))
 
     spec = workload(args)
     index = af.AnchorIndex(af.synth_anchor(spec), kp=args.kp)
@@ -173,10 +179,23 @@ def main():
     torch.cuda.synchronize()
     gather_cap = 1 << 16
 
-    def step():
-        hits, counts = eng.enqueue(batch)
+    n_slots = max(1, args.slots)
+    cand_cap = args.cand_cap or 2 * n
+    streams = []
+    for sl in range(n_slots):               # slot 0 runs on the current stream, the others own side streams
+        eng.enqueue(batch, cand_cap=cand_cap, slot=sl)
+        streams.append(eng.slot_stream(sl) if sl else torch.cuda.current_stream(dev))
+    torch.cuda.synchronize()
+
+    def step(i):
+        """One pass of the hot path over this rank's batch.  Consecutive steps are independent
+        batches, so they alternate between workspace slots / streams and may overlap, the way a
+        run over many batches is pipelined; everything is complete before the clock stops."""
+        sl = i % n_slots
+        hits, counts = eng.enqueue(batch, cand_cap=cand_cap, slot=sl)
         if world > 1:
-            return afdist.gather_hits_tensor(hits, counts, gather_cap)
+            with torch.cuda.stream(streams[sl]):
+                return afdist.gather_hits_tensor(hits, counts, gather_cap)
         return counts, hits
 
     def barrier():
@@ -184,10 +203,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        out = step()
+    def run_steps(k):
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for st in streams[1:]:
+            st.wait_event(fork)
+        for i in range(k):
+            out = step(i)
+        for st in streams[1:]:
+            join = torch.cuda.Event()
+            join.record(st)
+            cur.wait_event(join)
+        return out
+
+    out = run_steps(args.warmup)
     barrier()
-    stats_counts = eng._ws[2].cpu().numpy().view(np.uint32)
+    stats_counts = eng._ws[0][3].cpu().numpy().view(np.uint32)
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = L.af_kernel_launches()
@@ -195,8 +227,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        out = step()
+    out = run_steps(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)

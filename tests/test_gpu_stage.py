@@ -85,7 +85,7 @@ def test_bulk_cli_on_the_bundled_sample(bundled, tmp_path):
     golden = json.load(open(os.path.join(GOLDEN, "ref_functions.json")))
     assert got == next(c for c in golden["contact_reads"] if c["name"] == "bundled_c1")["out"]
     sp = open(w + "_split_points.txt").read().split("\n")
-    assert sp[1].split("\t")[:4] == ["BCR", "3235", "MS", "52"]
+    assert sp[1].split("\t")[:4] == ["BCR", "3235", "MS", "49"]
     # second run: outputs exist -> skipped, like the reference's existence guards
     assert main_bulk(["--file_anchored_cds", fa, "--fastq1", p1, "--fastq2", p2, "--out_folder", out]) == 0
 
