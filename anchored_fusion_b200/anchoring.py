@@ -176,12 +176,17 @@ class Anchorer:
             if not isinstance(self._ws, dict):
                 self._ws = {}
             nbytes = lib().af_workspace_bytes(n_pairs, cand_cap)
-            cur = (key, torch.empty(nbytes, dtype=torch.uint8, device=self.dev),
-                   torch.empty((max(hits_cap, 1), 4), dtype=torch.int32, device=self.dev),
-                   torch.zeros(_lib.N_COUNTS, dtype=torch.int32, device=self.dev),
-                   torch.cuda.Stream(device=self.dev) if slot else None)
+            # counts (8 x int32 = 2 rows) and the hit records share one tensor, so that the multi-GPU
+            # gather can ship (count, first records) as one contiguous slice with no packing kernel
+            hc = torch.zeros((2 + max(hits_cap, 1), 4), dtype=torch.int32, device=self.dev)
+            cur = (key, torch.empty(nbytes, dtype=torch.uint8, device=self.dev), hc[2:], hc[:2].view(-1),
+                   torch.cuda.Stream(device=self.dev) if slot else None, hc)
             self._ws[slot] = cur
-        return cur[1:]
+        return cur[1:5]
+
+    def counts_and_hits(self, slot=0):
+        """The slot's [2 + cap, 4] int32 tensor: rows 0..1 are the counters, rows 2.. the hit records."""
+        return self._ws[slot][5]
 
     def slot_stream(self, slot):
         """The side stream of workspace slot `slot` (> 0), created on first use."""

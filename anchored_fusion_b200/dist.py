@@ -15,21 +15,19 @@ def shard_range(n_pairs, rank, world):
     return min(lo, n_pairs), min(hi, n_pairs)
 
 
-def gather_hits_tensor(hits, counts, cap, group=None):
-    """One all-gather of (count, first `cap` records) per rank.  hits: [>=cap, 4] int32 tensor on
-    this rank's device, counts: int32 tensor with the hit count at index 1 (AF_CNT_HITS).
+def gather_hits_tensor(counts_and_hits, cap, group=None):
+    """One all-gather of (counters, first `cap` records) per rank.  counts_and_hits: the engine's
+    [2 + capacity, 4] int32 tensor (Anchorer.counts_and_hits): rows 0..1 hold the 8 counters (hit count
+    at flat index 1, AF_CNT_HITS), rows 2.. the records -- contiguous, so nothing is packed first.
     Returns (all_counts [world] int32, all_hits [world, cap, 4] int32) tensors, asynchronously on
     the current stream for NCCL."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    payload = torch.empty((cap + 1, 4), dtype=torch.int32, device=hits.device)
-    payload[0].zero_()
-    payload[0, 0] = counts[1]
-    payload[1:] = hits[:cap]
-    out = torch.empty((world, cap + 1, 4), dtype=torch.int32, device=hits.device)
-    dist.all_gather_into_tensor(out.view(-1, 4), payload, group=group)
-    return out[:, 0, 0], out[:, 1:]
+    src = counts_and_hits[: 2 + cap]
+    out = torch.empty((world, 2 + cap, 4), dtype=torch.int32, device=src.device)
+    dist.all_gather_into_tensor(out.view(-1, 4), src, group=group)
+    return out[:, 0, 1], out[:, 2:]
 
 
 def merge_gathered(all_counts, all_hits, pair_offsets):

@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs", type=int, default=1_000_000, help="bounded sample for cpu_baseline")
     ap.add_argument("--ref-pairs", type=int, default=250_000, help="pairs per step of the reference arm")
+    ap.add_argument("--gather-cap", type=int, default=0, help="hit records per rank in the per-step all-gather "
+                    "(0: sized from a probe pass, 1.25 x the largest per-rank hit count, rounded up to 4096)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -151,8 +153,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version
+    # there) are sent to stderr while we run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import anchored_fusion_b200 as af
     from anchored_fusion_b200 import dist as afdist
@@ -177,7 +182,12 @@ def main():
     n = args.pairs
     batch = af.synth_pairs_device(spec, rank * n, n, index.pad_byte, local)   # this rank's shard
     torch.cuda.synchronize()
-    gather_cap = 1 << 16
+    gather_cap = args.gather_cap
+    if world > 1 and gather_cap <= 0:
+        _, probe = eng.anchor(batch)
+        t = torch.tensor([probe["hits"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_cap = (int(t.item()) * 5 // 4 + 4095) // 4096 * 4096
 
     n_slots = max(1, args.slots)
     cand_cap = args.cand_cap or 2 * n
@@ -195,7 +205,7 @@ def main():
         hits, counts = eng.enqueue(batch, cand_cap=cand_cap, slot=sl)
         if world > 1:
             with torch.cuda.stream(streams[sl]):
-                return afdist.gather_hits_tensor(hits, counts, gather_cap)
+                return afdist.gather_hits_tensor(eng.counts_and_hits(sl), gather_cap)
         return counts, hits
 
     def barrier():
@@ -219,7 +229,7 @@ def main():
 
     out = run_steps(args.warmup)
     barrier()
-    stats_counts = eng._ws[0][3].cpu().numpy().view(np.uint32)
+    stats_counts = eng.counts_and_hits(0)[:2].reshape(-1).cpu().numpy().view(np.uint32)
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = L.af_kernel_launches()
@@ -319,14 +329,15 @@ def main():
 
     if rank == 0:
         nh = int(stats_counts[1])
-        print(json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                           "config": dict(config_dict(args, world), streams=n_slots), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                           "gpu_launches": int(launches), "clocks": clocks,
                           "per_step": {"flagged_reads": int(stats_counts[0]), "seeded_reads": int(stats_counts[3]),
                                        "anchored_reads": nh,
-                                       "kp": index.info.kp, "stride": index.info.stride}}))
+                                       "kp": index.info.kp, "stride": index.info.stride}}) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -28,11 +28,10 @@ def _worker(rank, world, port, n_pairs, q):
     hits = np.zeros(len(ids), dtype=HIT_DTYPE)
     hits["read_id"], hits["pos"], hits["m_len"] = ids, (2 * lo + ids) % 1000 + 1, 50
     cap = 4096
-    buf = torch.zeros((cap, 4), dtype=torch.int32)
-    buf[: len(hits)] = torch.from_numpy(hits.view(np.int32).reshape(-1, 4))
-    counts = torch.zeros(8, dtype=torch.int32)
-    counts[1] = len(hits)
-    all_counts, all_hits = afdist.gather_hits_tensor(buf, counts, cap)
+    buf = torch.zeros((2 + cap, 4), dtype=torch.int32)        # engine layout: 2 counter rows, then records
+    buf[2: 2 + len(hits)] = torch.from_numpy(hits.view(np.int32).reshape(-1, 4))
+    buf[0, 1] = len(hits)
+    all_counts, all_hits = afdist.gather_hits_tensor(buf, cap)
     offsets = [afdist.shard_range(n_pairs, r, world)[0] for r in range(world)]
     merged = afdist.merge_gathered(all_counts, all_hits, offsets)
     q.put((rank, lo, hi, merged.tobytes()))
