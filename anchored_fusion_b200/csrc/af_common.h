@@ -14,7 +14,7 @@
 #endif
 
 // ---- shared-memory filter ----------------------------------------------------------------
-// bucket word: three 10-bit fingerprint fields (0 = empty; stored fingerprints are odd, so
+// bucket word: three 10-bit fingerprint fields (0 = empty; stored fingerprints are 1..512, so
 // never 0) and a 2-bit state field in bits 30..31: 01 = normal, 00 = overflowed (always hit).
 // The probe tests all four fields for "== 0 after XOR" with one subtract and one LOP3.
 static const uint32_t AF_F_ONES = 0x40100401u;   // low bit of each field
@@ -34,14 +34,17 @@ AF_HD uint32_t af_umulhi(uint32_t a, uint32_t b) {
 }
 
 // key -> bucket index and the fingerprint replicated into the three fields (state field 00).
-// One 32-bit multiply: the bucket comes from the top bits of the product, the fingerprint
-// from bits 1..9.  (Taking the fingerprint from the HIGH word of the 64-bit product looked
-// natural but is 5x worse: keys that share a bucket differ by a lattice of deltas whose high
-// words repeat.  Within a bucket the low bits of the product are free.)
-AF_HD void af_filter_hash(uint32_t key, uint32_t fmul, uint32_t nb, uint32_t &bucket, uint32_t &fp3) {
-    uint32_t lo = key * fmul;
+// One 32-bit multiply by (mul << shift), shift = 32 - 2k': the product is
+// ((key mod 4^k') * mul) << shift, so bits of `key` above the k'-mer never matter and the kernel can
+// feed unmasked register windows.  The bucket comes from the top bits of the product, the
+// fingerprint from the 9 bits just above the shifted-in zeros (+1, so it is never 0).  (Taking the fingerprint from the
+// HIGH word of a 64-bit product looked natural but is 5x worse: keys that share a bucket differ by
+// a lattice of deltas whose high words repeat.  Within a bucket the low bits are free.)
+AF_HD void af_filter_hash(uint32_t key, uint32_t fmul_shifted, int shift, uint32_t nb, uint32_t &bucket, uint32_t &fp3) {
+    const uint32_t lo = key * fmul_shifted;
     bucket = af_umulhi(lo, nb);
-    fp3 = (lo & 0x3FEu) * AF_F_REP + AF_F_REP;  // fingerprint = (lo & 0x3FE) + 1, odd, 1..1023
+    // (((lo >> shift) & 0x1FF) + 1) * REP without the shift: high word of a 64-bit product
+    fp3 = af_umulhi(lo & (0x1FFu << shift), AF_F_REP << (32 - shift)) + AF_F_REP;   // fingerprint 1..512
 }
 
 // nonzero iff some field of the bucket equals the fingerprint, or the bucket overflowed

@@ -26,12 +26,12 @@ extern "C" void af_default_params(af_params_t *p) {
 // ------------------------------------------------------------------------------------------
 // anchor index  (replaces `bwa index`, Anchored_Fusion.py:167-172)
 // ------------------------------------------------------------------------------------------
-static int build_filter(const std::vector<uint32_t> &keys, uint32_t fmul, uint32_t nb, std::vector<uint32_t> &out) {
+static int build_filter(const std::vector<uint32_t> &keys, uint32_t fmul, int shift, uint32_t nb, std::vector<uint32_t> &out) {
     out.assign(nb, AF_F_EMPTY);
     int overflow = 0;
     for (uint32_t key : keys) {
         uint32_t b, fp3;
-        af_filter_hash(key, fmul, nb, b, fp3);
+        af_filter_hash(key, fmul << shift, shift, nb, b, fp3);
         uint32_t fp = fp3 & 0x3FFu, w = out[b];
         if (!(w & AF_F_EMPTY)) continue;  // already always-hit
         bool placed = false;
@@ -117,13 +117,14 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     long best = -1;
     std::vector<uint32_t> cand;
     for (uint32_t m : muls) {
-        int ov = build_filter(keys, m, nb, cand);
+        const int shift = 32 - 2 * kp;
+        int ov = build_filter(keys, m, shift, nb, cand);
         long fp = 0;
         uint32_t x = 0x12345678u;
         for (int t = 0; t < (1 << 18); t++) {
             x = af_mix32(x + 0x9E3779B9u);
             uint32_t b, fp3;
-            af_filter_hash(x & kmask, m, nb, b, fp3);
+            af_filter_hash(x & kmask, m << shift, shift, nb, b, fp3);
             fp += af_filter_test(cand[b], fp3) != 0;
         }
         if (best < 0 || fp < best) { best = fp; idx->fmul = m; idx->filter = cand; idx->n_overflow = ov; }

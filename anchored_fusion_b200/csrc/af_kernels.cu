@@ -114,7 +114,7 @@ template <int W, int KP, int OFF, int NW>
 __device__ __forceinline__ uint32_t scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt,
                                               uint32_t fmul, uint32_t nb) {
     constexpr int S = 20 - KP;  // k = 19
-    constexpr uint32_t KMASK = (1u << (2 * KP)) - 1u;
+    constexpr int SHIFT = 32 - 2 * KP;                                       // the hash ignores bits above the k'-mer
     constexpr int NP = (16 * W - KP) / S + 1;                                // samples when L == 16 W
     constexpr int LMIN = 16 * (W - 1) + 1;                                   // shortest L with this W
     constexpr int NPMIN = LMIN >= KP ? (LMIN - KP) / S + 1 : 0;
@@ -122,11 +122,12 @@ __device__ __forceinline__ uint32_t scan_read(const uint32_t (&w)[NW], int nprob
 #pragma unroll
     for (int j = 0; j < NP; j++) {
         const int o = 2 * j * S, wi = o >> 5, sh = o & 31;
-        uint32_t x;
-        if (sh + 2 * KP <= 32) x = (w[OFF + wi] >> sh) & KMASK;
-        else x = __funnelshift_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh) & KMASK;
+        uint32_t x;                                                          // k'-mer in the low 2k' bits, junk above
+        if (sh == 0) x = w[OFF + wi];
+        else if (sh + 2 * KP <= 32) x = w[OFF + wi] >> sh;
+        else x = __funnelshift_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh);
         uint32_t b, fp3;
-        af_filter_hash(x, fmul, nb, b, fp3);
+        af_filter_hash(x, fmul, SHIFT, nb, b, fp3);
         const uint32_t v = filt[b] ^ fp3;
         uint32_t t = (v - AF_F_ONES) & ~v;                                   // AF_F_HIGH applied once, below
         if (j >= NPMIN) t = j < nprobe ? t : 0u;
@@ -254,7 +255,7 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
     long long want = (n_tiles + nwarps - 1) / nwarps;
     int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
     k_seed_scan<W, KP, MAXT, PF><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
-                                                                     d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts);
+                                                                     d->d_filter, d->fmul << (32 - 2 * KP), d->nb, (uint2 *)flags, chunk_counts);
     g_launches++;
     AF_CUDA(cudaGetLastError());
     return AF_OK;

@@ -3,6 +3,16 @@ kernel flag, bit for bit, given the index's filter words and hash."""
 import numpy as np
 
 
+def filter_hash(key, fmul, kp, nb):
+    """af_filter_hash (csrc/af_common.h) on uint64 numpy arrays: (bucket as int64, fp3 as uint64)."""
+    shift = np.uint64(32 - 2 * kp)
+    m32 = np.uint64(0xFFFFFFFF)
+    lo = (key * ((np.uint64(fmul) << shift) & m32)) & m32
+    b = ((lo * np.uint64(nb)) >> np.uint64(32)).astype(np.int64)
+    fp3 = ((((lo >> shift) & np.uint64(0x1FF)) * np.uint64(0x00100401)) + np.uint64(0x00100401)) & m32
+    return b, fp3
+
+
 def expected_flags(index, codes, lens=None):
     """codes: (n_reads, stride) base codes with N/pad positions already replaced by the pad
     pattern (i.e. what the packed words hold).  Returns bool[n_reads]."""
@@ -25,9 +35,7 @@ def expected_flags(index, codes, lens=None):
         key = np.zeros(n, np.uint64)
         for t in range(KP):
             key |= full[:, p + t] << np.uint64(2 * t)
-        lo = (key * np.uint64(fm)) & np.uint64(0xFFFFFFFF)
-        b = ((lo * np.uint64(nb)) >> np.uint64(32)).astype(np.int64)
-        fp3 = ((lo & np.uint64(0x3FE)) * np.uint64(0x00100401) + np.uint64(0x00100401)) & np.uint64(0xFFFFFFFF)
+        b, fp3 = filter_hash(key, fm, KP, nb)
         v = filt[b] ^ fp3
         flag |= (((v - np.uint64(0x40100401)) & ~v & np.uint64(0xA0080200)) & np.uint64(0xFFFFFFFF)) != 0
     return flag

@@ -98,9 +98,8 @@ def test_index_contents(bundled):
         # filter membership of every key
         filt = idx.filter_words().astype(np.uint64)
         keys = np.array(sorted(set(k for k, _ in want)), dtype=np.uint64)
-        lo = (keys * np.uint64(info.filter_mul)) & np.uint64(0xFFFFFFFF)
-        b = ((lo * np.uint64(info.n_buckets)) >> np.uint64(32)).astype(np.int64)
-        fp3 = ((lo & np.uint64(0x3FE)) * np.uint64(0x00100401) + np.uint64(0x00100401)) & np.uint64(0xFFFFFFFF)
+        from filter_emulator import filter_hash
+        b, fp3 = filter_hash(keys, info.filter_mul, kp, info.n_buckets)
         v = filt[b] ^ fp3
         hit = ((v - np.uint64(0x40100401)) & ~v & np.uint64(0xA0080200)) != 0
         assert hit.all()
