@@ -14,7 +14,7 @@
 #endif
 
 // ---- shared-memory filter ----------------------------------------------------------------
-// bucket word: three 10-bit fingerprint fields (0 = empty; stored fingerprints are 1..512, so
+// bucket word: three 10-bit fingerprint fields (0 = empty; stored fingerprints are odd, so
 // never 0) and a 2-bit state field in bits 30..31: 01 = normal, 00 = overflowed (always hit).
 // The probe tests all four fields for "== 0 after XOR" with one subtract and one LOP3.
 static const uint32_t AF_F_ONES = 0x40100401u;   // low bit of each field
@@ -34,23 +34,58 @@ AF_HD uint32_t af_umulhi(uint32_t a, uint32_t b) {
 }
 
 // key -> bucket index and the fingerprint replicated into the three fields (state field 00).
-// One 32-bit multiply by (mul << shift), shift = 32 - 2k': the product is
-// ((key mod 4^k') * mul) << shift, so bits of `key` above the k'-mer never matter and the kernel can
-// feed unmasked register windows.  The bucket comes from the top bits of the product, the
-// fingerprint from the 9 bits just above the shifted-in zeros (+1, so it is never 0).  (Taking the fingerprint from the
-// HIGH word of a 64-bit product looked natural but is 5x worse: keys that share a bucket differ by
-// a lattice of deltas whose high words repeat.  Within a bucket the low bits are free.)
-AF_HD void af_filter_hash(uint32_t key, uint32_t fmul_shifted, int shift, uint32_t nb, uint32_t &bucket, uint32_t &fp3) {
-    const uint32_t lo = key * fmul_shifted;
+// One 32-bit multiply: the bucket comes from the top bits of the product, the fingerprint
+// from bits 1..9.  (Taking the fingerprint from the HIGH word of the 64-bit product looked
+// natural but is 5x worse: keys that share a bucket differ by a lattice of deltas whose high
+// words repeat.  Within a bucket the low bits of the product are free.)
+AF_HD void af_filter_hash(uint32_t key, uint32_t fmul, uint32_t nb, uint32_t &bucket, uint32_t &fp3) {
+    uint32_t lo = key * fmul;
     bucket = af_umulhi(lo, nb);
-    // (((lo >> shift) & 0x1FF) + 1) * REP without the shift: high word of a 64-bit product
-    fp3 = af_umulhi(lo & (0x1FFu << shift), AF_F_REP << (32 - shift)) + AF_F_REP;   // fingerprint 1..512
+    fp3 = (lo & 0x3FEu) * AF_F_REP + AF_F_REP;  // fingerprint = (lo & 0x3FE) + 1, odd, 1..1023
 }
 
 // nonzero iff some field of the bucket equals the fingerprint, or the bucket overflowed
 AF_HD uint32_t af_filter_test(uint32_t word, uint32_t fp3) {
     uint32_t v = word ^ fp3;
     return (v - AF_F_ONES) & ~v & AF_F_HIGH;
+}
+
+AF_HD uint32_t af_funnel_r(uint32_t lo, uint32_t hi, int sh) {   // bits [sh, sh+32) of hi:lo, 0 <= sh < 32
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+// ---- the seed-scan probe sequence of one read (shared by k_seed_scan and its host twin) ------
+// All sample positions of one read held in registers w[OFF..OFF+W).  Fully unrolled: every
+// shift and word index is a compile-time constant, and there is no branch: the first NPMIN
+// samples exist for every read length this W can hold, the last few are masked by a
+// warp-uniform select, so all probes of a read are independent instructions in one block.
+template <int W, int KP, int OFF, int NW>
+AF_HD uint32_t af_scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul,
+                              uint32_t nb) {
+    constexpr int S = 20 - KP;  // k = 19
+    constexpr uint32_t KMASK = (1u << (2 * KP)) - 1u;
+    constexpr int NP = (16 * W - KP) / S + 1;                                // samples when L == 16 W
+    constexpr int LMIN = 16 * (W - 1) + 1;                                   // shortest L with this W
+    constexpr int NPMIN = LMIN >= KP ? (LMIN - KP) / S + 1 : 0;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        const int o = 2 * j * S, wi = o >> 5, sh = o & 31;
+        uint32_t x;
+        if (sh + 2 * KP <= 32) x = (w[OFF + wi] >> sh) & KMASK;
+        else x = af_funnel_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh) & KMASK;
+        uint32_t b, fp3;
+        af_filter_hash(x, fmul, nb, b, fp3);
+        const uint32_t v = filt[b] ^ fp3;
+        uint32_t t = (v - AF_F_ONES) & ~v;                                   // AF_F_HIGH applied once, below
+        if (j >= NPMIN) t = j < nprobe ? t : 0u;
+        acc |= t;
+    }
+    return acc & AF_F_HIGH;
 }
 
 // ---- exact table (global memory): open addressing, duplicates allowed ---------------------

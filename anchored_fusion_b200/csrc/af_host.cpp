@@ -26,12 +26,12 @@ extern "C" void af_default_params(af_params_t *p) {
 // ------------------------------------------------------------------------------------------
 // anchor index  (replaces `bwa index`, Anchored_Fusion.py:167-172)
 // ------------------------------------------------------------------------------------------
-static int build_filter(const std::vector<uint32_t> &keys, uint32_t fmul, int shift, uint32_t nb, std::vector<uint32_t> &out) {
+static int build_filter(const std::vector<uint32_t> &keys, uint32_t fmul, uint32_t nb, std::vector<uint32_t> &out) {
     out.assign(nb, AF_F_EMPTY);
     int overflow = 0;
     for (uint32_t key : keys) {
         uint32_t b, fp3;
-        af_filter_hash(key, fmul << shift, shift, nb, b, fp3);
+        af_filter_hash(key, fmul, nb, b, fp3);
         uint32_t fp = fp3 & 0x3FFu, w = out[b];
         if (!(w & AF_F_EMPTY)) continue;  // already always-hit
         bool placed = false;
@@ -117,14 +117,13 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     long best = -1;
     std::vector<uint32_t> cand;
     for (uint32_t m : muls) {
-        const int shift = 32 - 2 * kp;
-        int ov = build_filter(keys, m, shift, nb, cand);
+        int ov = build_filter(keys, m, nb, cand);
         long fp = 0;
         uint32_t x = 0x12345678u;
         for (int t = 0; t < (1 << 18); t++) {
             x = af_mix32(x + 0x9E3779B9u);
             uint32_t b, fp3;
-            af_filter_hash(x & kmask, m << shift, shift, nb, b, fp3);
+            af_filter_hash(x & kmask, m, nb, b, fp3);
             fp += af_filter_test(cand[b], fp3) != 0;
         }
         if (best < 0 || fp < best) { best = fp; idx->fmul = m; idx->filter = cand; idx->n_overflow = ov; }
@@ -295,4 +294,35 @@ extern "C" int af_synth_pairs_host(const af_synth_t *s, int64_t first_pair, int6
         }
     }
     return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host twin of the seed-scan probe sequence: runs the SAME template the kernel runs
+// (af_scan_read in af_common.h) on one pair's packed words.  For tests only -- it lets the CPU
+// suite check the kernel's probe logic for every W without a GPU; no product path calls it.
+// ------------------------------------------------------------------------------------------
+template <int W, int KP>
+static void scan_pair_host(const af_index *idx, const uint32_t *words, int nprobe, int *f1, int *f2) {
+    uint32_t w[2 * W];
+    for (int i = 0; i < 2 * W; i++) w[i] = words[i];
+    const uint32_t fm = idx->fmul;
+    *f1 = af_scan_read<W, KP, 0, 2 * W>(w, nprobe, idx->filter.data(), fm, idx->nb) != 0;
+    *f2 = af_scan_read<W, KP, W, 2 * W>(w, nprobe, idx->filter.data(), fm, idx->nb) != 0;
+}
+
+#define AF_HOST_SCAN_CASE(WW) \
+    case WW: if (idx->kp == 12) scan_pair_host<WW, 12>(idx, words, nprobe, flag1, flag2); else scan_pair_host<WW, 13>(idx, words, nprobe, flag1, flag2); return AF_OK;
+
+extern "C" int af_debug_scan_pair(const af_index_t *idx, const uint32_t *words, int32_t words_per_read, int32_t read_len,
+                                  int32_t *flag1, int32_t *flag2) {
+    if (!idx || !words || !flag1 || !flag2 || (idx->kp != 12 && idx->kp != 13) || idx->P.k != 19) { af_set_error("af_debug_scan_pair: bad argument"); return AF_ERR_ARG; }
+    const int nprobe = read_len >= idx->kp ? (read_len - idx->kp) / idx->stride + 1 : 0;
+    switch (words_per_read) {
+        AF_HOST_SCAN_CASE(1) AF_HOST_SCAN_CASE(2) AF_HOST_SCAN_CASE(3) AF_HOST_SCAN_CASE(4) AF_HOST_SCAN_CASE(5)
+        AF_HOST_SCAN_CASE(6) AF_HOST_SCAN_CASE(7) AF_HOST_SCAN_CASE(8) AF_HOST_SCAN_CASE(9) AF_HOST_SCAN_CASE(10)
+        AF_HOST_SCAN_CASE(11) AF_HOST_SCAN_CASE(12) AF_HOST_SCAN_CASE(13) AF_HOST_SCAN_CASE(14) AF_HOST_SCAN_CASE(15)
+        AF_HOST_SCAN_CASE(16)
+    }
+    af_set_error("af_debug_scan_pair: words_per_read %d", words_per_read);
+    return AF_ERR_ARG;
 }

@@ -106,36 +106,6 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
     return r;
 }
 
-// All sample positions of one read held in registers w[OFF..OFF+W).  Fully unrolled: every
-// shift and word index is a compile-time constant, and there is no branch: the first NPMIN
-// samples exist for every read length this W can hold, the last few are masked by a
-// warp-uniform select, so all probes of a read are independent instructions in one block.
-template <int W, int KP, int OFF, int NW>
-__device__ __forceinline__ uint32_t scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt,
-                                              uint32_t fmul, uint32_t nb) {
-    constexpr int S = 20 - KP;  // k = 19
-    constexpr int SHIFT = 32 - 2 * KP;                                       // the hash ignores bits above the k'-mer
-    constexpr int NP = (16 * W - KP) / S + 1;                                // samples when L == 16 W
-    constexpr int LMIN = 16 * (W - 1) + 1;                                   // shortest L with this W
-    constexpr int NPMIN = LMIN >= KP ? (LMIN - KP) / S + 1 : 0;
-    uint32_t acc = 0;
-#pragma unroll
-    for (int j = 0; j < NP; j++) {
-        const int o = 2 * j * S, wi = o >> 5, sh = o & 31;
-        uint32_t x;                                                          // k'-mer in the low 2k' bits, junk above
-        if (sh == 0) x = w[OFF + wi];
-        else if (sh + 2 * KP <= 32) x = w[OFF + wi] >> sh;
-        else x = __funnelshift_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh);
-        uint32_t b, fp3;
-        af_filter_hash(x, fmul, SHIFT, nb, b, fp3);
-        const uint32_t v = filt[b] ^ fp3;
-        uint32_t t = (v - AF_F_ONES) & ~v;                                   // AF_F_HIGH applied once, below
-        if (j >= NPMIN) t = j < nprobe ? t : 0u;
-        acc |= t;
-    }
-    return acc & AF_F_HIGH;
-}
-
 template <int Q>
 __device__ __forceinline__ void load_tile(uint32_t (&w)[4 * Q], const uint4 *__restrict__ packed, long long tile, int lane) {
     const uint4 *src = packed + tile * (Q * 32) + lane;
@@ -162,8 +132,8 @@ __device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long 
                                           int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
                                           uint2 *__restrict__ flags, uint32_t *cc_local, long long chunk0,
                                           uint32_t *__restrict__ chunk_counts) {
-    uint32_t a1 = scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
-    uint32_t a2 = scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
+    uint32_t a1 = af_scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
+    uint32_t a2 = af_scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
     const uint32_t vm = tile_valid_mask(tile, n_pairs);
     const uint32_t b1 = __ballot_sync(FULL, a1 != 0) & vm, b2 = __ballot_sync(FULL, a2 != 0) & vm;
     if (lane == 0) {
@@ -255,7 +225,7 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
     long long want = (n_tiles + nwarps - 1) / nwarps;
     int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
     k_seed_scan<W, KP, MAXT, PF><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
-                                                                     d->d_filter, d->fmul << (32 - 2 * KP), d->nb, (uint2 *)flags, chunk_counts);
+                                                                     d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts);
     g_launches++;
     AF_CUDA(cudaGetLastError());
     return AF_OK;

@@ -5,11 +5,10 @@ import numpy as np
 
 def filter_hash(key, fmul, kp, nb):
     """af_filter_hash (csrc/af_common.h) on uint64 numpy arrays: (bucket as int64, fp3 as uint64)."""
-    shift = np.uint64(32 - 2 * kp)
     m32 = np.uint64(0xFFFFFFFF)
-    lo = (key * ((np.uint64(fmul) << shift) & m32)) & m32
+    lo = (key * np.uint64(fmul)) & m32
     b = ((lo * np.uint64(nb)) >> np.uint64(32)).astype(np.int64)
-    fp3 = ((((lo >> shift) & np.uint64(0x1FF)) * np.uint64(0x00100401)) + np.uint64(0x00100401)) & m32
+    fp3 = ((lo & np.uint64(0x3FE)) * np.uint64(0x00100401) + np.uint64(0x00100401)) & m32
     return b, fp3
 
 

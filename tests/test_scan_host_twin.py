@@ -1,0 +1,47 @@
+"""The seed-scan probe sequence (af_scan_read, the template k_seed_scan runs) executed on the
+host for every read length class, against the numpy emulation of the filter: no false negatives,
+and exactly the filter's positives."""
+import ctypes
+
+import numpy as np
+import pytest
+
+
+def _scan_pairs_host(af, index, batch):
+    from anchored_fusion_b200._lib import check, lib
+    lay = af.layout(batch.max_read_len, batch.n_pairs)
+    W, Q = lay.words_per_read, lay.quads_per_pair
+    L = batch.uniform_len if batch.uniform_len > 0 else batch.max_read_len
+    packed = batch.packed.reshape(-1)
+    out = np.zeros(2 * batch.n_pairs, bool)
+    f1, f2 = ctypes.c_int32(), ctypes.c_int32()
+    for p in range(batch.n_pairs):
+        tile, lane = p >> 5, p & 31
+        words = np.concatenate([packed[((tile * Q + q) * 32 + lane) * 4: ((tile * Q + q) * 32 + lane) * 4 + 4] for q in range(Q)])[: 2 * W]
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        check(lib().af_debug_scan_pair(index._h, words.ctypes.data, W, L, ctypes.byref(f1), ctypes.byref(f2)))
+        out[2 * p], out[2 * p + 1] = bool(f1.value), bool(f2.value)
+    return out
+
+
+@pytest.mark.parametrize("read_len", [36, 76, 101, 125, 150, 151, 250])
+@pytest.mark.parametrize("kp", [12, 13])
+def test_host_twin_equals_emulation_and_has_no_false_negatives(read_len, kp):
+    import anchored_fusion_b200 as af
+    from filter_emulator import expected_flags
+    from oracle import oracle
+    spec = af.synth_spec(seed=read_len * 7 + kp, ref_len=60_000, anchor_start=20_000, anchor_len=8000, read_len=read_len,
+                         frag_mean=max(2 * read_len, 200), sub_ppm=20_000, fusion_ppm=100_000)
+    anchor = af.synth_anchor(spec)
+    index = af.AnchorIndex(anchor, kp=kp)
+    n = 1500
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    batch = af.pack_pairs([lut[r].tobytes() for r in m1], [lut[r].tobytes() for r in m2], pad_byte=index.pad_byte)
+    got = _scan_pairs_host(af, index, batch)
+    codes = np.empty((2 * n, read_len), dtype=np.uint8)
+    codes[0::2], codes[1::2] = m1, m2
+    want = expected_flags(index, codes)
+    assert np.array_equal(got, want)
+    hits = oracle.anchor_reads(oracle.encode(anchor), codes, threads=4)
+    assert len(hits) > 50 and got[hits["read_id"]].all()
