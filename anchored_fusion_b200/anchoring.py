@@ -246,7 +246,7 @@ class Anchorer:
     def anchor_host(self, batch, slot_pairs=1 << 20, n_slots=3, hits_out=None):
         """Anchor a HOST batch (numpy / pinned arrays): H2D copies, kernels and the D2H of the
         hit list all happen inside this call.  Returns (hits ndarray, stats)."""
-        pipe = self.pipeline(batch.max_read_len, min(slot_pairs, max(32, (batch.n_pairs + 31) // 32 * 32)), n_slots)
+        pipe = self.pipeline(batch.max_read_len, slot_pairs, n_slots)
         cap = 2 * max(batch.n_pairs, 1) if hits_out is None else len(hits_out)
         out = hits_out if hits_out is not None else np.zeros(cap, dtype=HIT_DTYPE)
         nh, nf = ctypes.c_int64(0), ctypes.c_int64(0)

@@ -15,7 +15,7 @@ import sys
 import time
 
 from .functions import combine_split_reads, split_records
-from .stage import anchor_stage
+from .stage import GeneAnchorer, anchor_stage
 
 
 def _common_flags(p):
@@ -98,14 +98,14 @@ def write_split_points(stats, gene, path):
     return groups
 
 
-def run_gene_sample(file_anchored_seq, gene, fastq1, fastq2, out_dir_name, args):
+def run_gene_sample(file_anchored_seq, gene, fastq1, fastq2, out_dir_name, args, gene_anchorer=None):
     done = out_dir_name + '_anchored_reads.bam'
     if os.path.exists(done) and os.path.exists(out_dir_name + '_realign_reads.bam'):
         print('[anchoring] %s: outputs exist, skipping (same existence guard as the reference)' % out_dir_name)
         return None
     t0 = time.time()
     stats = anchor_stage(file_anchored_seq, fastq1, fastq2, out_dir_name, thread=args.thread,
-                         gpu_number=args.gpu_number, gene_name=gene)
+                         gpu_number=args.gpu_number, gene_name=gene, gene_anchorer=gene_anchorer)
     groups = write_split_points(stats, gene, out_dir_name + '_split_points.txt')
     dt = time.time() - t0
     print('[anchoring] %s: %d pairs, %d anchored reads, %d half-anchored pairs, %d split-point groups, %.2f s (%.0f pairs/s)'
@@ -169,10 +169,11 @@ def main_singlecell(argv=None):
 
     fastas = split_anchor_fasta(args.file_anchored_cds, gene_names, lambda g: gene_prefix(g) + '_anchored_gene_sequence.fa')
     for gene, fa in zip(gene_names, fastas):
+        ga = GeneAnchorer(fa, args.gpu_number, gene)      # one index upload + staging per gene, not per cell
         for cell, f1, f2 in cells:
             cell_dir = args.out_folder + '/' + gene + '/work_dir/' + cell
             _mkdir(cell_dir)
-            run_gene_sample(fa, gene, args.fastq_dir + '/' + f1, args.fastq_dir + '/' + f2, cell_dir + '/' + gene + '_fusion', args)
+            run_gene_sample(fa, gene, args.fastq_dir + '/' + f1, args.fastq_dir + '/' + f2, cell_dir + '/' + gene + '_fusion', args, ga)
     return 0
 
 

@@ -10,9 +10,16 @@
 #include "af_common.h"
 
 struct SeqRef { const char *p; int32_t len; };
-int af_pack_core(const SeqRef *r1, const SeqRef *r2, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte,
-                 void *packed_out, uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
-                 int64_t *n_nreads_out, int32_t *uniform_len_out);
+struct PackSide {
+    std::vector<uint32_t> nids, nmask;
+    int32_t ulen = -1;
+    int rc = AF_OK;
+    std::string err;
+};
+void af_pack_side(const SeqRef *r, int m, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
+                  uint16_t *lens_out, PackSide &st);
+int af_pack_finish(PackSide &a, PackSide &b, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
+                   int64_t *n_nreads_out, int32_t *uniform_len_out);
 
 namespace {
 
@@ -123,8 +130,18 @@ extern "C" int af_fastq_next(af_fastq_t *fq, int64_t max_pairs, int32_t max_read
                              uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
                              int64_t *n_nreads_out, int32_t *uniform_len_out, int64_t *n_pairs_out) {
     if (!fq || !n_pairs_out || max_pairs <= 0) { af_set_error("af_fastq_next: bad argument"); return AF_ERR_ARG; }
-    std::thread t1([&] { fq->side[1].read_batch(max_pairs); });
-    fq->side[0].read_batch(max_pairs);
+    // each side: inflate + parse its file, then pack its mate's words (the mates own disjoint words)
+    PackSide ps[2];
+    auto work = [&](int m) {
+        Side &sd = fq->side[m];
+        sd.read_batch(max_pairs);
+        if (!sd.err.empty() || !packed_out) return;
+        std::vector<SeqRef> refs(sd.recs.size());
+        for (size_t i = 0; i < sd.recs.size(); i++) refs[i] = {sd.text.data() + sd.recs[i].seq_off, sd.recs[i].len};
+        af_pack_side(refs.data(), m, (int64_t)refs.size(), max_read_len, pad_byte, packed_out, lens_out, ps[m]);
+    };
+    std::thread t1(work, 1);
+    work(0);
     t1.join();
     for (int i = 0; i < 2; i++)
         if (!fq->side[i].err.empty()) { af_set_error("af_fastq_next: file %d: %s", i + 1, fq->side[i].err.c_str()); return AF_ERR_IO; }
@@ -136,13 +153,8 @@ extern "C" int af_fastq_next(af_fastq_t *fq, int64_t max_pairs, int32_t max_read
     fq->n_cur = n;
     *n_pairs_out = n;
     if (n == 0) { if (n_nreads_out) *n_nreads_out = 0; if (uniform_len_out) *uniform_len_out = 0; return AF_OK; }
-    std::vector<SeqRef> r[2];
-    for (int s = 0; s < 2; s++) {
-        r[s].resize((size_t)n);
-        for (int64_t i = 0; i < n; i++) r[s][(size_t)i] = {fq->side[s].text.data() + fq->side[s].recs[(size_t)i].seq_off, fq->side[s].recs[(size_t)i].len};
-    }
-    return af_pack_core(r[0].data(), r[1].data(), n, max_read_len, pad_byte, packed_out, lens_out, nread_ids_out,
-                        nmask_out, ncap, n_nreads_out, uniform_len_out);
+    if (!packed_out) { af_set_error("af_fastq_next: packed_out is null"); return AF_ERR_ARG; }
+    return af_pack_finish(ps[0], ps[1], nread_ids_out, nmask_out, ncap, n_nreads_out, uniform_len_out);
 }
 
 extern "C" int af_fastq_record(const af_fastq_t *fq, int64_t read_id, const char **name, int32_t *name_len,

@@ -179,56 +179,105 @@ extern "C" int af_layout(int32_t max_read_len, int64_t n_pairs, af_layout_t *out
 
 struct SeqRef { const char *p; int32_t len; };
 
+// One mate's words of every pair of a batch (mate 0 also writes the zero words that pad a pair to
+// whole quads).  The two mates touch disjoint 32-bit words, so the two sides of a FASTQ pair can
+// be packed by two threads at once.  N positions and the tail past a read keep the pad pattern.
+struct PackSide {
+    std::vector<uint32_t> nids, nmask;   // read ids (2p+m) holding an N, and their 256-bit masks
+    int32_t ulen = -1;                   // common length, -2 once lengths differ
+    int rc = AF_OK;
+    std::string err;
+};
+
+static const uint8_t *code_lut() {
+    static uint8_t lut[256];
+    static bool init = false;
+    if (!init) { for (int c = 0; c < 256; c++) lut[c] = af_code_of((char)c); init = true; }
+    return lut;
+}
+
+void af_pack_side(const SeqRef *r, int m, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
+                  uint16_t *lens_out, PackSide &st) {
+    af_layout_t lay;
+    st.rc = af_layout(max_read_len, n_pairs, &lay);
+    if (st.rc) return;
+    const int W = lay.words_per_read, Q = lay.quads_per_pair;
+    const uint8_t *lut = code_lut();
+    uint32_t *out = (uint32_t *)packed_out;
+    uint32_t padw = 0;  // 16 bases of the period-4 pad pattern
+    for (int i = 0; i < 16; i++) padw |= (uint32_t)((pad_byte >> (2 * (i & 3))) & 3) << (2 * i);
+    for (int64_t p = 0; p < lay.n_tiles * AF_TILE_PAIRS; p++) {
+        const int64_t tile = p >> 5, lane = p & 31;
+        uint32_t *pair_base = out + (tile * Q * 32 + lane) * 4;       // word wi of the pair at pair_base[(wi>>2)*128 + (wi&3)]
+        if (m == 0) for (int wi = 2 * W; wi < 4 * Q; wi++) pair_base[(wi >> 2) * 128 + (wi & 3)] = 0u;
+        int32_t len = 0;
+        const char *seq = nullptr;
+        if (p < n_pairs) {
+            len = r[p].len; seq = r[p].p;
+            if (len > max_read_len || len < 0) {
+                char buf[160];
+                snprintf(buf, sizeof(buf), "af_pack: read %lld/%d has %d bases, max_read_len is %d", (long long)p, m + 1, len, max_read_len);
+                st.err = buf; st.rc = AF_ERR_ARG;
+                return;
+            }
+            if (st.ulen == -1) st.ulen = len; else if (st.ulen != len) st.ulen = -2;
+            if (lens_out) lens_out[2 * p + m] = (uint16_t)len;
+        }
+        uint32_t nm[AF_NMASK_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool hasn = false;
+        for (int t = 0; t < W; t++) {
+            uint32_t word = padw;
+            const int i0 = 16 * t, cnt = len - i0 < 16 ? (len - i0 > 0 ? len - i0 : 0) : 16;
+            for (int i = 0; i < cnt; i++) {
+                const uint8_t c = lut[(uint8_t)seq[i0 + i]];
+                if (c == 4) { hasn = true; nm[(i0 + i) >> 5] |= 1u << ((i0 + i) & 31); continue; }   // keeps the pad base
+                word = (word & ~(3u << (2 * i))) | ((uint32_t)c << (2 * i));
+            }
+            const int wi = m * W + t;
+            pair_base[(wi >> 2) * 128 + (wi & 3)] = word;
+        }
+        if (hasn) {
+            st.nids.push_back((uint32_t)(2 * p + m));
+            st.nmask.insert(st.nmask.end(), nm, nm + AF_NMASK_WORDS);
+        }
+    }
+}
+
+// merge the two sides' N lists (each sorted by read id) into the caller's arrays
+int af_pack_finish(PackSide &a, PackSide &b, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
+                   int64_t *n_nreads_out, int32_t *uniform_len_out) {
+    for (PackSide *s : {&a, &b}) if (s->rc) { af_set_error("%s", s->err.empty() ? "af_pack: bad layout" : s->err.c_str()); return s->rc; }
+    const int64_t nn = (int64_t)(a.nids.size() + b.nids.size());
+    if (nn > 0) {
+        if (nn > ncap || !nread_ids_out || !nmask_out) { af_set_error("af_pack: N-read list capacity %lld exceeded", (long long)ncap); return AF_ERR_CAPACITY; }
+        size_t ia = 0, ib = 0;
+        int64_t k = 0;
+        while (ia < a.nids.size() || ib < b.nids.size()) {
+            const bool take_a = ib >= b.nids.size() || (ia < a.nids.size() && a.nids[ia] < b.nids[ib]);
+            PackSide &s = take_a ? a : b;
+            size_t &i = take_a ? ia : ib;
+            nread_ids_out[k] = s.nids[i];
+            memcpy(nmask_out + k * AF_NMASK_WORDS, s.nmask.data() + i * AF_NMASK_WORDS, AF_NMASK_WORDS * 4);
+            i++; k++;
+        }
+    }
+    if (n_nreads_out) *n_nreads_out = nn;
+    if (uniform_len_out) {
+        int32_t u = 0;
+        if (a.ulen >= 0 && b.ulen >= 0 && a.ulen == b.ulen) u = a.ulen;
+        *uniform_len_out = u > 0 ? u : 0;
+    }
+    return AF_OK;
+}
+
 // shared by af_pack_pairs and the FASTQ reader (af_fastq.cpp)
 int af_pack_core(const SeqRef *r1, const SeqRef *r2, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte,
                  void *packed_out, uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
                  int64_t *n_nreads_out, int32_t *uniform_len_out) {
-    af_layout_t lay;
-    int rc = af_layout(max_read_len, n_pairs, &lay);
-    if (rc) return rc;
-    const int W = lay.words_per_read, Q = lay.quads_per_pair;
-    uint32_t *out = (uint32_t *)packed_out;
-    uint32_t padw = 0;  // 16 bases of the period-4 pad pattern
-    for (int i = 0; i < 16; i++) padw |= (uint32_t)((pad_byte >> (2 * (i & 3))) & 3) << (2 * i);
-    int64_t nn = 0;
-    int32_t ulen = -1;
-    bool uniform = true;
-    uint32_t words[2 * 16 + 4];
-    for (int64_t p = 0; p < lay.n_tiles * AF_TILE_PAIRS; p++) {
-        for (int i = 0; i < 4 * Q; i++) words[i] = i < 2 * W ? padw : 0u;
-        if (p < n_pairs) {
-            for (int m = 0; m < 2; m++) {
-                const SeqRef &s = m == 0 ? r1[p] : r2[p];
-                if (s.len > max_read_len || s.len < 0) {
-                    af_set_error("af_pack: read %lld/%d has %d bases, max_read_len is %d", (long long)p, m + 1, s.len, max_read_len);
-                    return AF_ERR_ARG;
-                }
-                if (ulen < 0) ulen = s.len; else if (ulen != s.len) uniform = false;
-                if (lens_out) lens_out[2 * p + m] = (uint16_t)s.len;
-                uint32_t *w = words + m * W;
-                uint32_t nm[AF_NMASK_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
-                bool hasn = false;
-                for (int32_t i = 0; i < s.len; i++) {
-                    uint8_t c = af_code_of(s.p[i]);
-                    if (c == 4) { hasn = true; nm[i >> 5] |= 1u << (i & 31); continue; }  // keeps the pad base
-                    int sh = 2 * (i & 15);
-                    w[i >> 4] = (w[i >> 4] & ~(3u << sh)) | ((uint32_t)c << sh);
-                }
-                if (hasn) {
-                    if (nn >= ncap || !nread_ids_out || !nmask_out) { af_set_error("af_pack: N-read list capacity %lld exceeded", (long long)ncap); return AF_ERR_CAPACITY; }
-                    nread_ids_out[nn] = (uint32_t)(2 * p + m);
-                    memcpy(nmask_out + nn * AF_NMASK_WORDS, nm, sizeof(nm));
-                    nn++;
-                }
-            }
-        }
-        int64_t tile = p >> 5, lane = p & 31;
-        for (int q = 0; q < Q; q++)
-            memcpy(out + ((tile * Q + q) * 32 + lane) * 4, words + 4 * q, 16);
-    }
-    if (n_nreads_out) *n_nreads_out = nn;
-    if (uniform_len_out) *uniform_len_out = (uniform && ulen > 0) ? ulen : 0;
-    return AF_OK;
+    PackSide a, b;
+    af_pack_side(r1, 0, n_pairs, max_read_len, pad_byte, packed_out, lens_out, a);
+    af_pack_side(r2, 1, n_pairs, max_read_len, pad_byte, packed_out, lens_out, b);
+    return af_pack_finish(a, b, nread_ids_out, nmask_out, ncap, n_nreads_out, uniform_len_out);
 }
 
 extern "C" int af_pack_pairs(const char *seq1, const int64_t *off1, const char *seq2, const int64_t *off2,

@@ -144,7 +144,7 @@ def scan_fastq_pair(index, fastq1, fastq2, device=0, batch_pairs=1 << 21, max_re
                 if batch is None:
                     break
                 if batch_filter is None or batch_filter(i):
-                    hits, st = eng.anchor_host(batch, slot_pairs=min(batch_pairs, 1 << 20))
+                    hits, st = eng.anchor_host(batch, slot_pairs=1 << 18, n_slots=3)
                     have = set(int(r) for r in hits["read_id"])
                     for h in hits:
                         rid = int(h["read_id"])
@@ -240,16 +240,26 @@ def hits_array(anchored):
     return sort_hits(hits)
 
 
+class GeneAnchorer:
+    """Index + GPU engine of one anchored gene, reusable over many FASTQ pairs (single-cell runs
+    call the stage once per cell: the index upload and the pinned / device staging buffers are
+    paid once per gene, not once per cell)."""
+
+    def __init__(self, file_anchored_seq, gpu_number="-1", gene_name=None, kp=0):
+        name, self.seq = read_single_fasta(file_anchored_seq)
+        self.gene = gene_name or name.split()[0]
+        self.index = AnchorIndex(self.seq, kp=kp)
+        self.engine = Anchorer(self.index, resolve_device(gpu_number))
+
+
 def anchor_stage(file_anchored_seq, fastq1, fastq2, out_prefix, thread="1", gpu_number="-1", gene_name=None,
-                 batch_pairs=1 << 21, kp=0):
+                 batch_pairs=1 << 20, kp=0, gene_anchorer=None):
     """Drop-in for the anchoring stage.  file_anchored_seq is <work>_anchored_gene_sequence.fa;
     `thread` is accepted for signature compatibility (the two zlib decode threads and the GPU do
     the work).  Returns a stats dict; see write_stage_outputs for the files."""
-    name, seq = read_single_fasta(file_anchored_seq)
-    gene = gene_name or name.split()[0]
-    index = AnchorIndex(seq, kp=kp)
-    anchored, mates, stats = scan_fastq_pair(index, fastq1, fastq2, device=resolve_device(gpu_number),
-                                             batch_pairs=batch_pairs)
+    ga = gene_anchorer or GeneAnchorer(file_anchored_seq, gpu_number, gene_name, kp)
+    gene, seq, index = ga.gene, ga.seq, ga.index
+    anchored, mates, stats = scan_fastq_pair(index, fastq1, fastq2, batch_pairs=batch_pairs, engine=ga.engine)
     stats.update(write_stage_outputs(out_prefix, gene, len(seq), anchored, mates))
     stats["half_anchored_pairs"] = len(mates)
     stats["hits"] = hits_array(anchored)
