@@ -42,21 +42,14 @@ def read_single_fasta(path):
 class FastqPairReader:
     """Paired FASTQ / FASTQ.gz -> packed host batches (C++: af_fastq_open / af_fastq_next)."""
 
-    def __init__(self, path1, path2, max_read_len, pad_byte, batch_pairs):
+    def __init__(self, path1, path2, max_read_len, pad_byte, batch_pairs, buffers=None):
         self.max_read_len, self.pad_byte, self.batch_pairs = max_read_len, pad_byte, batch_pairs
         h = ctypes.c_void_p()
         check(lib().af_fastq_open(path1.encode(), path2.encode(), ctypes.byref(h)))
         self._h = h
-        lay = layout(max_read_len, batch_pairs)
-        self._pinned = lib().af_host_alloc(lay.packed_bytes)     # pinned staging; pageable if that fails
-        if self._pinned:
-            self.packed = np.ctypeslib.as_array(ctypes.cast(self._pinned, ctypes.POINTER(ctypes.c_uint32)),
-                                                (lay.packed_bytes // 4,))
-        else:
-            self.packed = np.zeros(lay.packed_bytes // 4, dtype=np.uint32)
-        self.lens = np.zeros(2 * batch_pairs, dtype=np.uint16)
-        self.nids = np.zeros(2 * batch_pairs, dtype=np.uint32)
-        self.nmask = np.zeros((2 * batch_pairs, _lib.NMASK_WORDS), dtype=np.uint32)
+        self._bufs = buffers if buffers is not None else HostBuffers(max_read_len, batch_pairs)
+        self._own = buffers is None
+        self.packed, self.lens, self.nids, self.nmask = self._bufs.packed, self._bufs.lens, self._bufs.nids, self._bufs.nmask
 
     def next_batch(self):
         """PackedBatch (host) or None at EOF; record text stays valid until the next call."""
@@ -83,14 +76,42 @@ class FastqPairReader:
         if self._h:
             lib().af_fastq_close(self._h)
             self._h = None
-        if self._pinned:
-            lib().af_host_free(self._pinned)
-            self._pinned = None
+        if self._own and self._bufs is not None:
+            self._bufs.free()
+        self._bufs = None
 
     def __del__(self):
         try:
             if _lib._lib is not None:
                 self.close()
+        except Exception:
+            pass
+
+
+class HostBuffers:
+    """Pinned staging for one packed batch (+ lens and the N side list); reusable across files."""
+
+    def __init__(self, max_read_len, batch_pairs):
+        self.key = (max_read_len, batch_pairs)
+        lay = layout(max_read_len, batch_pairs)
+        self._pinned = lib().af_host_alloc(lay.packed_bytes)     # pageable if pinning fails
+        if self._pinned:
+            self.packed = np.ctypeslib.as_array(ctypes.cast(self._pinned, ctypes.POINTER(ctypes.c_uint32)),
+                                                (lay.packed_bytes // 4,))
+        else:
+            self.packed = np.zeros(lay.packed_bytes // 4, dtype=np.uint32)
+        self.lens = np.zeros(2 * batch_pairs, dtype=np.uint16)
+        self.nids = np.zeros(2 * batch_pairs, dtype=np.uint32)
+        self.nmask = np.zeros((2 * batch_pairs, _lib.NMASK_WORDS), dtype=np.uint32)
+
+    def free(self):
+        if self._pinned and _lib._lib is not None:
+            lib().af_host_free(self._pinned)
+        self._pinned = None
+
+    def __del__(self):
+        try:
+            self.free()
         except Exception:
             pass
 
@@ -135,7 +156,12 @@ def scan_fastq_pair(index, fastq1, fastq2, device=0, batch_pairs=1 << 21, max_re
     eng = engine or Anchorer(index, device)
     mrl = max_read_len or max(peek_max_read_len(fastq1), peek_max_read_len(fastq2))
     while True:
-        reader = FastqPairReader(fastq1, fastq2, mrl, index.pad_byte, batch_pairs)
+        bufs = getattr(eng, "_host_buffers", None)
+        if bufs is None or bufs.key != (mrl, batch_pairs):
+            if bufs is not None:
+                bufs.free()
+            bufs = eng._host_buffers = HostBuffers(mrl, batch_pairs)      # lives with the engine: reused across files
+        reader = FastqPairReader(fastq1, fastq2, mrl, index.pad_byte, batch_pairs, buffers=bufs)
         anchored, mates, base, stats = [], {}, 0, {"pairs": 0, "flagged": 0, "anchored": 0}
         try:
             i = 0
