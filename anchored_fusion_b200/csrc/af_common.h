@@ -22,7 +22,7 @@ static const uint32_t AF_F_HIGH = 0xA0080200u;   // high bit of each field
 static const uint32_t AF_F_REP = 0x00100401u;    // replicates a fingerprint into 3 fields
 static const uint32_t AF_F_EMPTY = 0x40000000u;  // empty, normal bucket
 static const int AF_F_SLOTS = 3;
-static const uint32_t AF_MAX_BUCKETS = 53248;    // 208 KB of the 227 KB shared memory per CTA
+static const uint32_t AF_MAX_BUCKETS = 50176;    // 196 KB of the 227 KB shared memory per CTA; the rest holds the fused kernel's queues
 static const uint32_t AF_MIN_BUCKETS = 2048;
 
 AF_HD uint32_t af_umulhi(uint32_t a, uint32_t b) {
@@ -186,6 +186,8 @@ struct af_index {
     uint32_t tmask;
     std::vector<uint32_t> table;    // (tmask+1) x {key, value}; value = strand<<31 | anchor pos
     std::vector<uint32_t> member;   // 4^kp-bit bitmap: bit key set iff key is an anchor k'-mer
+    std::vector<uint32_t> apk[2];   // anchor, 2 bit/base: [0] forward, [1] reverse complement (N packed as A)
+    int32_t anchor_has_n;
     int32_t n_keys, n_entries, n_overflow, pad_byte;
 };
 

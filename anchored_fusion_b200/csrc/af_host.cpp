@@ -64,6 +64,18 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     idx->codes.resize((size_t)len);
     for (int64_t i = 0; i < len; i++) idx->codes[(size_t)i] = af_code_of(anchor[i]);
 
+    // 2-bit packed anchor, both orientations, for word-parallel run checks
+    idx->anchor_has_n = 0;
+    for (int o = 0; o < 2; o++) {
+        idx->apk[o].assign((size_t)(idx->G + 15) / 16 + 4, 0u);
+        for (int32_t i = 0; i < idx->G; i++) {
+            uint8_t c = o == 0 ? idx->codes[(size_t)i] : idx->codes[(size_t)(idx->G - 1 - i)];
+            if (c >= 4) { idx->anchor_has_n = 1; continue; }
+            if (o) c = (uint8_t)(3 - c);
+            idx->apk[o][(size_t)i >> 4] |= (uint32_t)c << (2 * (i & 15));
+        }
+    }
+
     struct Ent { uint32_t key, val; };
     std::vector<Ent> ents;
     int run = 0;

@@ -89,6 +89,8 @@ struct af_dev_index {
     uint2 *d_table;      // tmask+1 entries {key, value}
     uint32_t *d_member;  // 4^kp-bit exact membership bitmap (L2 resident)
     uint8_t *d_anchor;   // G base codes
+    uint32_t *d_apk[2];  // 2-bit packed anchor: forward / reverse complement
+    int anchor_has_n;
     int pad_byte;
     int num_sms;
 };
@@ -104,6 +106,20 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+}
+
+// Stage the anchor filter into shared memory: 128-bit loads, several in flight per thread (a
+// one-word-per-iteration loop spends ~20 us of pure L2 latency here; ncu, round 1).
+__device__ __forceinline__ void stage_filter(uint32_t *filt, const uint32_t *__restrict__ g_filter, uint32_t nb) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(g_filter);
+    uint4 *dst = reinterpret_cast<uint4 *>(filt);
+    const uint32_t n4 = nb >> 2, step = blockDim.x;              // nb is a multiple of 32
+    uint32_t i = threadIdx.x;
+    for (; i + 3 * step < n4; i += 4 * step) {
+        const uint4 a = src[i], b = src[i + step], c = src[i + 2 * step], d = src[i + 3 * step];
+        dst[i] = a; dst[i + step] = b; dst[i + 2 * step] = c; dst[i + 3 * step] = d;
+    }
+    for (; i < n4; i += step) dst[i] = src[i];
 }
 
 template <int Q>
@@ -170,7 +186,7 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     if constexpr (PF) {
         uint32_t wa[4 * Q], wb[4 * Q];
         if (tile < t_end) load_tile<Q>(wa, packed, tile, lane);   // in flight while the filter is staged
-        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) filt[i] = g_filter[i];
+        stage_filter(filt, g_filter, nb);
         __syncthreads();
         while (tile < t_end) {
             const long long t2 = tile + stride;
@@ -183,7 +199,7 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
             tile = t3;
         }
     } else {
-        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) filt[i] = g_filter[i];
+        stage_filter(filt, g_filter, nb);
         __syncthreads();
         for (; tile < t_end; tile += stride) {
             uint32_t w[4 * Q];
@@ -197,11 +213,14 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     }
 }
 
-static int g_scan_threads = 768, g_scan_mode = 3;
+static int g_scan_threads = 768, g_scan_mode = 3, g_fused = 0;
 // tuning knob: mode 0/3 = register double buffer under an 85-register cap (threads <= 768, the
 // default: 24 warps per SM), 1 = register double buffer with 128 registers (threads <= 512),
 // 2 = no prefetch (threads <= 1024)
 extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
+    // modes 4 / 5 switch af_anchor_batch between the fused, warp-specialised scan+verify kernel (4)
+    // and the separate seed-scan / verify kernels (5, default); the stand-alone scan variant is untouched
+    if (mode == 4 || mode == 5) { g_fused = mode == 4; return AF_OK; }
     if (mode == 0) mode = 3;
     if (mode < 1 || mode > 3) { af_set_error("af_seed_scan_config: mode must be 0..3"); return AF_ERR_ARG; }
     const int maxt = mode == 1 ? 512 : (mode == 2 ? 1024 : 768);
@@ -321,13 +340,13 @@ __device__ __forceinline__ uint32_t sum_before(const uint32_t *chunk_counts, uin
 // flag words -> candidate read_ids; total -> counts[AF_CNT_FLAGGED]
 __global__ void __launch_bounds__(CB_THREADS)
 k_flag_scatter(const uint2 *__restrict__ flags, long long n_tiles, const uint32_t *__restrict__ chunk_counts,
-               uint32_t n_chunks, uint32_t *__restrict__ cand, uint32_t cand_cap, uint32_t *counts) {
+               uint32_t n_chunks, uint32_t *__restrict__ cand, uint32_t cand_cap, uint32_t *counts, int count_idx) {
     __shared__ uint32_t sm[9];
     for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const uint32_t mine = chunk_counts[chunk];
         if (mine == 0) continue;                       // uniform across the block
         const uint32_t base = sum_before(chunk_counts, chunk, sm);
-        if (threadIdx.x == 0) atomicAdd(&counts[AF_CNT_FLAGGED], mine);
+        if (threadIdx.x == 0) atomicAdd(&counts[count_idx], mine);
         uint2 f[CB_ITEMS];
         uint32_t c = 0;
         const long long t0 = (long long)chunk * CB_PER_BLOCK + threadIdx.x * CB_ITEMS;
@@ -514,6 +533,250 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
         const uint32_t bal = __ballot_sync(FULL, seeded);
         if (lane == 0 && bal) atomicAdd(&chunk_counts[c0 / CB_PER_BLOCK], __popc(bal));
     }
+}
+
+// 32 bases (64 bits) of a 2-bit packed sequence starting at base `pos` (pos >= 0)
+__device__ __forceinline__ unsigned long long packed_window(const uint32_t *__restrict__ a, int pos) {
+    const int wi = pos >> 4, sh = 2 * (pos & 15);
+    const uint32_t w0 = a[wi], w1 = a[wi + 1], w2 = a[wi + 2];
+    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused seed scan + verify: warp-specialised persistent kernel
+//
+// 24 warps per CTA: 20 SCAN warps run exactly the probe sequence of k_seed_scan; a flagged lane
+// pushes (read_id, its packed words -- already in registers) into its warp's single-producer
+// queue in shared memory.  4 VERIFY warps, each serving five of those queues, pop up to 32
+// candidates at a time, re-probe their samples in the shared-memory filter to learn which
+// samples hit (all 32 lanes busy), walk the exact table for those and check the >= k run
+// word-parallel against the 2-bit packed anchor.  Scan warps keep the LSU busy while verify
+// warps wait on L2: the latency-bound stage hides under the bandwidth-bound one, the flagged
+// reads never go back to HBM, and two compaction passes disappear.  Output: seeded flag words in
+// the same (tile, mate) ballot layout the scan uses, plus per-chunk counts -> k_flag_scatter.
+// ------------------------------------------------------------------------------------------
+#ifndef AF_FZ_SCAN_WARPS
+#define AF_FZ_SCAN_WARPS 20
+#endif
+#ifndef AF_FZ_VERIFY_WARPS
+#define AF_FZ_VERIFY_WARPS 4
+#endif
+#ifndef AF_FZ_QCAP
+#define AF_FZ_QCAP 16
+#endif
+static const int FZ_SCAN_WARPS = AF_FZ_SCAN_WARPS, FZ_VERIFY_WARPS = AF_FZ_VERIFY_WARPS, FZ_QPC = FZ_SCAN_WARPS / FZ_VERIFY_WARPS,
+                 FZ_QCAP = AF_FZ_QCAP, FZ_THREADS = 32 * (FZ_SCAN_WARPS + FZ_VERIFY_WARPS);
+static_assert(FZ_SCAN_WARPS % FZ_VERIFY_WARPS == 0 && FZ_QPC <= 8, "each verify warp serves FZ_QPC <= 8 scan warps");
+
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+// push the flagged lanes' reads (registers w[OFF..OFF+W)) into this scan warp's queue
+template <int W, int OFF, int NW>
+__device__ __forceinline__ void fz_push(uint32_t mrem, const uint32_t (&w)[NW], uint32_t rid, int lane, uint32_t *qdata,
+                                        uint32_t *qhead, uint32_t *qtail, uint32_t &tail) {
+    constexpr int ES = W + 1;
+    while (mrem) {                                           // warp-uniform
+        const int room = FZ_QCAP - (int)(tail - ld_vol(qhead));
+        if (room <= 0) { __nanosleep(40); continue; }
+        const bool mine = (mrem >> lane) & 1u;
+        const int rank = __popc(mrem & ((1u << lane) - 1u));
+        const bool go = mine && rank < room;
+        if (go) {
+            uint32_t *e = qdata + ((tail + rank) % FZ_QCAP) * ES;
+            e[0] = rid;
+#pragma unroll
+            for (int t = 0; t < W; t++) e[1 + t] = w[OFF + t];
+        }
+        const uint32_t taken = __ballot_sync(FULL, go);
+        mrem &= ~taken;
+        __threadfence_block();
+        __syncwarp();
+        tail += __popc(taken);
+        if (lane == 0) st_vol(qtail, tail);
+    }
+}
+
+template <int W, int KP>
+__global__ void __launch_bounds__(FZ_THREADS, 1)
+k_scan_verify(const uint4 *__restrict__ packed, long long n_tiles, long long n_pairs, int nprobe, int uniform_len,
+              const uint16_t *__restrict__ lens, const uint32_t *__restrict__ nread_ids,
+              const uint32_t *__restrict__ nmask, int n_nreads, const uint32_t *__restrict__ g_filter, uint32_t fmul,
+              uint32_t nb, const uint2 *__restrict__ table, uint32_t tmask, const uint8_t *__restrict__ anchor,
+              const uint32_t *__restrict__ apk0, const uint32_t *__restrict__ apk1, int anchor_has_n, int G, int K,
+              uint32_t *__restrict__ seeded_flags, uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ counts) {
+    extern __shared__ uint32_t fsm[];
+    constexpr int Q = (2 * W + 3) / 4, ES = W + 1, SWW = W + 3, S = 20 - KP;
+    constexpr uint32_t kpmask = (1u << (2 * KP)) - 1u;
+    uint32_t *filt = fsm;
+    uint32_t *qdata = filt + nb;                                         // [FZ_SCAN_WARPS][FZ_QCAP][ES]
+    uint32_t *qhead = qdata + FZ_SCAN_WARPS * FZ_QCAP * ES;              // [FZ_SCAN_WARPS]
+    uint32_t *qtail = qhead + FZ_SCAN_WARPS, *qdone = qtail + FZ_SCAN_WARPS;
+    uint32_t *scratch = qdone + FZ_SCAN_WARPS;                           // [FZ_VERIFY_WARPS][SWW][32]
+    uint32_t *nflag = scratch + FZ_VERIFY_WARPS * SWW * 32;              // [1]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long t_begin = n_tiles * blockIdx.x / gridDim.x, t_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+    if (threadIdx.x < 3 * FZ_SCAN_WARPS) qhead[threadIdx.x] = 0;         // heads, tails, done flags
+    if (threadIdx.x == 0) *nflag = 0;
+    uint32_t wa[4 * Q], wb[4 * Q];
+    long long tile = t_begin + warp;
+    const bool scanner = warp < FZ_SCAN_WARPS;
+    if (scanner && tile < t_end) load_tile<Q>(wa, packed, tile, lane);   // in flight while the filter is staged
+    stage_filter(filt, g_filter, nb);
+    __syncthreads();
+    if (scanner) {
+        uint32_t tail = 0, flagged = 0;
+        uint32_t *qd = qdata + warp * FZ_QCAP * ES;
+        auto scan_and_push = [&](const uint32_t (&w)[4 * Q], long long tl) {
+            const uint32_t a1 = af_scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
+            const uint32_t a2 = af_scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
+            const uint32_t vm = tile_valid_mask(tl, n_pairs);
+            const uint32_t b1 = __ballot_sync(FULL, a1 != 0) & vm, b2 = __ballot_sync(FULL, a2 != 0) & vm;
+            const uint32_t rid = (uint32_t)(tl * 32 + lane) * 2u;
+            if (b1) fz_push<W, 0, 4 * Q>(b1, w, rid, lane, qd, qhead + warp, qtail + warp, tail);
+            if (b2) fz_push<W, W, 4 * Q>(b2, w, rid + 1u, lane, qd, qhead + warp, qtail + warp, tail);
+            flagged += __popc(b1) + __popc(b2);
+        };
+        while (tile < t_end) {
+            const long long t2 = tile + FZ_SCAN_WARPS;
+            if (t2 < t_end) load_tile<Q>(wb, packed, t2, lane);
+            scan_and_push(wa, tile);
+            if (t2 >= t_end) break;
+            const long long t3 = t2 + FZ_SCAN_WARPS;
+            if (t3 < t_end) load_tile<Q>(wa, packed, t3, lane);
+            scan_and_push(wb, t2);
+            tile = t3;
+        }
+        __threadfence_block();
+        if (lane == 0) { st_vol(qdone + warp, 1u); if (flagged) atomicAdd(nflag, flagged); }
+    } else {
+        const int c = warp - FZ_SCAN_WARPS, q0 = c * FZ_QPC;
+        uint32_t *sw = scratch + c * SWW * 32 + lane;                    // word k of this lane's candidate at sw[k*32]
+        uint32_t hq = 0;                                                 // lanes < FZ_QPC: head of queue q0+lane
+        for (;;) {
+            uint32_t avail = 0;
+            if (lane < FZ_QPC) avail = ld_vol(qtail + q0 + lane) - hq;
+            uint32_t pre = avail;                                        // inclusive prefix over the five queues
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { uint32_t t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
+            const uint32_t total = __shfl_sync(FULL, pre, FZ_QPC - 1);
+            // A round is latency bound (dependent L2 loads), so it pays to run it with all 32 lanes:
+            // wait for a full warp's worth of candidates unless a queue is about to fill up (its scan
+            // warp would stall) or the scan warps are done.
+            if (total < 32u) {
+                const uint32_t dn = lane < FZ_QPC ? ld_vol(qdone + q0 + lane) : 1u;
+                const bool all_done = __all_sync(FULL, dn != 0);
+                const bool pressure = __any_sync(FULL, avail >= (uint32_t)(FZ_QCAP - 4));
+                if (!all_done && !pressure) { __nanosleep(200); continue; }
+                if (total == 0) {
+                    const uint32_t again = lane < FZ_QPC ? ld_vol(qtail + q0 + lane) - hq : 0u;   // a push may precede the done flag
+                    if (!__any_sync(FULL, again != 0)) break;
+                    continue;
+                }
+            }
+            const uint32_t ntake = min(total, 32u);
+            __threadfence_block();                                       // entries were written before the tails we just read
+            // lane i < ntake takes the i-th available entry, queues in order
+            uint32_t rid = 0;
+            bool have = false;
+#pragma unroll
+            for (int q = 0; q < FZ_QPC; q++) {
+                const uint32_t incl = __shfl_sync(FULL, pre, q), av = __shfl_sync(FULL, avail, q), h = __shfl_sync(FULL, hq, q);
+                const uint32_t start = incl - av;
+                if ((uint32_t)lane < ntake && (uint32_t)lane >= start && (uint32_t)lane < incl) {
+                    const uint32_t *e = qdata + ((q0 + q) * FZ_QCAP + (h + (lane - start)) % FZ_QCAP) * ES;
+                    rid = e[0];
+#pragma unroll
+                    for (int t = 0; t < W; t++) sw[t * 32] = e[1 + t];
+                    have = true;
+                }
+            }
+            if (have) { sw[W * 32] = 0; sw[(W + 1) * 32] = 0; sw[(W + 2) * 32] = 0; }
+            __threadfence_block();
+            __syncwarp();
+            if (lane < FZ_QPC) {                                         // release what was copied out
+                const uint32_t start = pre - avail;
+                const uint32_t took = ntake > start ? min(avail, ntake - start) : 0u;
+                hq += took;
+                if (took) st_vol(qhead + q0 + lane, hq);
+            }
+            // ---- verify this lane's candidate --------------------------------------------
+            bool seeded = false;
+            if (have) {
+                const uint32_t pair = rid >> 1;
+                ReadRef r;                                              // global view, used only by the slow (N) path
+                r.packed = reinterpret_cast<const uint32_t *>(packed);
+                r.base = ((size_t)(pair >> 5) * Q * 32 + (pair & 31)) * 4;
+                r.wofs = (int)(rid & 1u) * W;
+                r.L = uniform_len > 0 ? uniform_len : (int)lens[rid];
+                r.nm = nullptr;
+                if (n_nreads > 0) {
+                    int lo = 0, hi = n_nreads;
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
+                    if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
+                }
+                const int np = r.L >= KP ? (r.L - KP) / S + 1 : 0;
+                unsigned long long hit = 0;
+                for (int j = 0; j < np; j++) {                           // which samples pass the filter
+                    const int o = 2 * j * S, wi = o >> 5;
+                    const uint32_t key = __funnelshift_r(sw[wi * 32], sw[(wi + 1) * 32], o & 31) & kpmask;
+                    uint32_t b, fp3;
+                    af_filter_hash(key, fmul, nb, b, fp3);
+                    if (af_filter_test(filt[b], fp3)) hit |= 1ull << j;
+                }
+                const bool fast = !r.nm && !anchor_has_n;
+                while (hit && !seeded) {
+                    const int j = __ffsll((long long)hit) - 1;
+                    hit &= hit - 1;
+                    const int p = j * S, o = 2 * p;
+                    const uint32_t key = __funnelshift_r(sw[(o >> 5) * 32], sw[((o >> 5) + 1) * 32], o & 31) & kpmask;
+                    if (r.nm) {   // a k'-mer that overlaps an N is no seed material
+                        bool n = false;
+                        for (int t = 0; t < KP; t++) n |= r.is_n(p + t);
+                        if (n) continue;
+                    }
+                    for (uint32_t slot = af_table_hash(key, tmask);; slot = (slot + 1) & tmask) {
+                        const uint2 e = table[slot];
+                        if (e.x == AF_T_EMPTY) break;
+                        if (e.x != key) continue;
+                        const int s = e.y >> 31, jpos = (int)(e.y & 0x7FFFFFFFu);
+                        int run = KP;
+                        if (fast) {
+                            // read-forward frame: the sample at p sits at js on the forward (s=0) or
+                            // reverse-complemented (s=1) anchor; compare 2-bit windows word-parallel
+                            constexpr int FL = 7;
+                            const int js = s ? G - jpos - KP : jpos, dd = js - p;
+                            const int i0 = max(max(p - FL, 0), -dd), i1 = min(min(p + KP + FL, r.L), G - dd), n = i1 - i0;
+                            const int wi = i0 >> 4, sh = 2 * (i0 & 15);
+                            const uint32_t r0 = sw[wi * 32], r1 = sw[(wi + 1) * 32], r2 = sw[(wi + 2) * 32];
+                            const unsigned long long rb = (unsigned long long)__funnelshift_r(r0, r1, sh) |
+                                                          ((unsigned long long)__funnelshift_r(r1, r2, sh) << 32);
+                            const unsigned long long x = rb ^ packed_window(s ? apk1 : apk0, i0 + dd);
+                            unsigned long long ne = (x | (x >> 1)) & 0x5555555555555555ull;   // 1 = bases differ
+                            ne |= 0x5555555555555555ull << (2 * n);                             // past the overlap
+                            const int a = p - i0;
+                            const unsigned long long lm = ne & ((1ull << (2 * a)) - 1ull), rm = ne >> (2 * (a + KP));
+                            run += lm ? a - 1 - ((63 - __clzll((long long)lm)) >> 1) : a;
+                            run += (__ffsll((long long)rm) - 1) >> 1;                           // rm != 0: n < 32
+                        } else {
+                            const int qp = s ? r.L - p - KP : p, d = jpos - qp;
+                            for (int i = qp - 1; run < K && diag_match(r, s, i, d, anchor, G); i--) run++;
+                            for (int i = qp + KP; run < K && diag_match(r, s, i, d, anchor, G); i++) run++;
+                        }
+                        if (run >= K) { seeded = true; break; }
+                    }
+                }
+                if (seeded) {
+                    const uint32_t tl = pair >> 5;
+                    atomicOr(&seeded_flags[tl * 2 + (rid & 1u)], 1u << (pair & 31));
+                    atomicAdd(&chunk_counts[tl / CB_PER_BLOCK], 1u);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && *nflag) atomicAdd(&counts[AF_CNT_FLAGGED], *nflag);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -727,6 +990,46 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
     }
 }
 
+template <int W, int KP>
+static int launch_fused(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
+                        uint32_t *cc, uint32_t *counts, cudaStream_t st) {
+    const size_t smem = ((size_t)d->nb + FZ_SCAN_WARPS * FZ_QCAP * (W + 1) + 3 * FZ_SCAN_WARPS + FZ_VERIFY_WARPS * (W + 3) * 32 + 1) * 4;
+    if (smem > 227 * 1024) { af_set_error("fused kernel: %zu bytes of shared memory needed", smem); return AF_ERR_ARG; }
+    static bool attr_set[64] = {false};  // per device
+    if (!attr_set[d->device & 63]) {
+        AF_CUDA(cudaFuncSetAttribute(k_scan_verify<W, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[d->device & 63] = true;
+    }
+    long long want = (n_tiles + FZ_SCAN_WARPS - 1) / FZ_SCAN_WARPS;
+    int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
+    k_scan_verify<W, KP><<<grid, FZ_THREADS, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe, b->uniform_len, b->lens,
+                                                  b->nread_ids, b->nmask, (int)b->n_nreads, d->d_filter, d->fmul, d->nb,
+                                                  d->d_table, d->tmask, d->d_anchor, d->d_apk[0], d->d_apk[1], d->anchor_has_n,
+                                                  d->G, d->P.k, flags, cc, counts);
+    g_launches++;
+    AF_CUDA(cudaGetLastError());
+    return AF_OK;
+}
+
+#define AF_FUSED_CASE(WW)                                                                               \
+    case WW:                                                                                            \
+        return d->kp == 12 ? launch_fused<WW, 12>(d, b, lay.n_tiles, nprobe, flags, cc, counts, st)      \
+                           : launch_fused<WW, 13>(d, b, lay.n_tiles, nprobe, flags, cc, counts, st);
+
+static int fused_impl(const af_dev_index *d, const af_batch_t *b, const af_layout_t &lay, uint32_t *flags, uint32_t *cc,
+                      uint32_t *counts, cudaStream_t st) {
+    if (d->P.k != 19 || (d->kp != 12 && d->kp != 13)) { af_set_error("seed scan is built for k=19, k' in {12,13}"); return AF_ERR_ARG; }
+    const int L = b->uniform_len > 0 ? b->uniform_len : b->max_read_len;
+    const int nprobe = L >= d->kp ? (L - d->kp) / d->stride + 1 : 0;
+    switch (lay.words_per_read) {
+        AF_FUSED_CASE(1) AF_FUSED_CASE(2) AF_FUSED_CASE(3) AF_FUSED_CASE(4) AF_FUSED_CASE(5) AF_FUSED_CASE(6)
+        AF_FUSED_CASE(7) AF_FUSED_CASE(8) AF_FUSED_CASE(9) AF_FUSED_CASE(10) AF_FUSED_CASE(11) AF_FUSED_CASE(12)
+        AF_FUSED_CASE(13) AF_FUSED_CASE(14) AF_FUSED_CASE(15) AF_FUSED_CASE(16)
+    }
+    af_set_error("unsupported words_per_read %d", lay.words_per_read);
+    return AF_ERR_ARG;
+}
+
 // ------------------------------------------------------------------------------------------
 // the hot path on one GPU
 // ------------------------------------------------------------------------------------------
@@ -779,14 +1082,28 @@ extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, voi
     if (lay.n_tiles == 0) return AF_OK;
     AF_CUDA(cudaMemsetAsync(cc1, 0, w.cc_bytes, st));
     const int scatter_grid = d->num_sms * 4;
+    const int sg2 = (int)(w.nch2 < (uint32_t)scatter_grid ? w.nch2 : scatter_grid);
     cudaEvent_t ev;
     prof_mark(&ev, st);
+    if (g_fused) {
+        // fused: seed scan + verify in one warp-specialised kernel -> seeded flag words
+        AF_CUDA(cudaMemsetAsync(flags, 0, (size_t)lay.n_tiles * 8, st));
+        rc = fused_impl(d, b, lay, flags, cc1, d_counts, st);
+        if (rc) return rc;
+        prof_span(ev, st, ST_SCAN);
+        prof_mark(&ev, st);
+        k_flag_scatter<<<(int)(w.nch1 < (uint32_t)scatter_grid ? w.nch1 : scatter_grid), CB_THREADS, 0, st>>>(
+            (const uint2 *)flags, lay.n_tiles, cc1, w.nch1, cand2, (uint32_t)cand_cap, d_counts, AF_CNT_SEEDED);
+        prof_span(ev, st, ST_COMPACT1);
+        prof_mark(&ev, st);
+        g_launches -= 2;                                    // this path has 4 kernels, the code below counts 5 more
+    } else {
     rc = seed_scan_impl(d, b, flags, cc1, st);
     if (rc) return rc;
     prof_span(ev, st, ST_SCAN);
     prof_mark(&ev, st);
     k_flag_scatter<<<(int)(w.nch1 < (uint32_t)scatter_grid ? w.nch1 : scatter_grid), CB_THREADS, 0, st>>>(
-        (const uint2 *)flags, lay.n_tiles, cc1, w.nch1, cand, (uint32_t)cand_cap, d_counts);
+        (const uint2 *)flags, lay.n_tiles, cc1, w.nch1, cand, (uint32_t)cand_cap, d_counts, AF_CNT_FLAGGED);
     prof_span(ev, st, ST_COMPACT1);
     prof_mark(&ev, st);
     long long vthreads = cand_cap < (long long)d->num_sms * 2048 ? cand_cap : (long long)d->num_sms * 2048;
@@ -796,8 +1113,8 @@ extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, voi
         d->tmask, d->d_anchor, d->G, d->P.k, keep, cc2
     if (d->kp == 12) k_verify<12><<<vgrid, 256, 0, st>>>(AF_VERIFY_ARGS);
     else k_verify<13><<<vgrid, 256, 0, st>>>(AF_VERIFY_ARGS);
-    const int sg2 = (int)(w.nch2 < (uint32_t)scatter_grid ? w.nch2 : scatter_grid);
     k_sel_scatter<<<sg2, CB_THREADS, 0, st>>>(cand, keep, (uint32_t)cand_cap, cc2, cand2, d_counts);
+    }
     prof_span(ev, st, ST_VERIFY);
     prof_mark(&ev, st);
     ExtParams P = {d->P.k, d->P.A, d->P.B, d->P.clip5, d->P.clip3, d->P.T, d->P.X};
@@ -833,7 +1150,13 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     d->fmul = idx->fmul; d->nb = idx->nb; d->tmask = idx->tmask; d->pad_byte = idx->pad_byte;
     d->num_sms = prop.multiProcessorCount;
     d->d_filter = nullptr; d->d_table = nullptr; d->d_anchor = nullptr; d->d_member = nullptr;
+    d->d_apk[0] = d->d_apk[1] = nullptr;
+    d->anchor_has_n = idx->anchor_has_n;
     cudaError_t e = cudaMalloc(&d->d_filter, idx->filter.size() * 4);
+    for (int o = 0; o < 2; o++) {
+        if (e == cudaSuccess) e = cudaMalloc(&d->d_apk[o], idx->apk[o].size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(d->d_apk[o], idx->apk[o].data(), idx->apk[o].size() * 4, cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&d->d_member, idx->member.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(d->d_member, idx->member.data(), idx->member.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_table, idx->table.size() * 4);
@@ -843,7 +1166,7 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     if (e == cudaSuccess) e = cudaMemcpy(d->d_anchor, idx->codes.data(), idx->codes.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         af_set_error("af_index_upload: %s", cudaGetErrorString(e));
-        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member);
+        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]);
         delete d;
         return AF_ERR_CUDA;
     }
@@ -856,7 +1179,7 @@ extern "C" int af_dev_index_device(const af_dev_index_t *d) { return d ? d->devi
 extern "C" void af_dev_index_free(af_dev_index_t *d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member);
+    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]);
     delete d;
 }
 

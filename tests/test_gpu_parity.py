@@ -162,6 +162,32 @@ def test_pipeline_equals_resident_path_and_counts_launches(af):
     assert lib().af_kernel_launches() - before == 6 * ((n + 65_535) // 65_536)
 
 
+def test_fused_scan_verify_kernel_gives_the_same_records(af, bundled):
+    """af_seed_scan_config(0, 4): the warp-specialised fused scan+verify kernel (20 scan warps feed
+    4 verify warps through shared-memory queues) instead of the separate kernels."""
+    from oracle import oracle
+    from anchored_fusion_b200._lib import check, lib
+    check(lib().af_seed_scan_config(0, 4))
+    try:
+        index = af.AnchorIndex(bundled["anchor"])
+        eng = af.Anchorer(index, 0)
+        host = af.pack_pairs(bundled["seqs1"], bundled["seqs2"], pad_byte=index.pad_byte)
+        hits, st = eng.anchor(host.to_device(0))
+        assert hits_equal(hits, bundled["oracle_hits"]) and st["flagged"] >= len(hits)
+        for L, kp in ((150, 12), (250, 13), (36, 12)):
+            spec = af.synth_spec(seed=L, ref_len=300_000, anchor_start=100_000, anchor_len=9000, read_len=L,
+                                 frag_mean=max(2 * L, 300), sub_ppm=15_000, fusion_ppm=30_000, )
+            anchor = af.synth_anchor(spec)
+            idx = af.AnchorIndex(anchor, kp=kp)
+            e2 = af.Anchorer(idx, 0)
+            n = 60_000
+            h, _ = e2.anchor(af.synth_pairs_device(spec, 0, n, idx.pad_byte, 0))
+            m1, m2 = af.synth_pairs_host(spec, 0, n)
+            assert hits_equal(h, oracle.anchor_reads(oracle.encode(anchor), _interleave(m1, m2), threads=8))
+    finally:
+        check(lib().af_seed_scan_config(0, 5))
+
+
 def test_capacity_overflow_is_reported_not_dropped(af):
     spec = af.synth_spec(seed=4, ref_len=20_000, anchor_start=1_000, anchor_len=15_000, read_len=150)
     index = af.AnchorIndex(af.synth_anchor(spec))
