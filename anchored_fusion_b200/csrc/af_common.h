@@ -59,32 +59,70 @@ AF_HD uint32_t af_funnel_r(uint32_t lo, uint32_t hi, int sh) {   // bits [sh, sh
 }
 
 // ---- the seed-scan probe sequence of one read (shared by k_seed_scan and its host twin) ------
-// All sample positions of one read held in registers w[OFF..OFF+W).  Fully unrolled: every
-// shift and word index is a compile-time constant, and there is no branch: the first NPMIN
-// samples exist for every read length this W can hold, the last few are masked by a
-// warp-uniform select, so all probes of a read are independent instructions in one block.
-template <int W, int KP, int OFF, int NW>
+// k'-mer starting at base P (compile-time) of the read in registers w[OFF..OFF+W)
+template <int W, int KP, int OFF, int P, int NW>
+AF_HD uint32_t af_kmer_at(const uint32_t (&w)[NW]) {
+    constexpr uint32_t KMASK = (1u << (2 * KP)) - 1u;
+    constexpr int o = 2 * P, wi = o >> 5, sh = o & 31;
+    if (sh + 2 * KP <= 32) return (w[OFF + wi] >> sh) & KMASK;
+    return af_funnel_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh) & KMASK;
+}
+
+AF_HD uint32_t af_filter_probe(uint32_t key, const uint32_t *filt, uint32_t fmul, uint32_t nb) {
+    uint32_t b, fp3;
+    af_filter_hash(key, fmul, nb, b, fp3);
+    const uint32_t v = filt[b] ^ fp3;
+    return (v - AF_F_ONES) & ~v;                                             // & AF_F_HIGH != 0  <=>  hit
+}
+
+// The rarely taken second look at a sample that passed the filter (compile-time position P):
+// a true >= k match [q, q+k) around the sample also holds the k'-mer at P-H or the one at P+H,
+// H = ceil((k-k')/2) -- left slack a = P-q and right slack b add up to k-k', so a >= H or b >= H.
+// Chance k'-mer hits, which are ~96 % of what the plain filter flags, pass with probability ~0.3 %.
+template <int W, int KP, int OFF, int P, int NW>
+AF_HD bool af_neighbour_ok(const uint32_t (&w)[NW], const uint32_t *filt, uint32_t fmul, uint32_t nb) {
+    constexpr int H = (19 - KP + 1) / 2;
+    bool ok = false;
+    if (P - H >= 0) ok = (af_filter_probe(af_kmer_at<W, KP, OFF, (P - H >= 0 ? P - H : 0)>(w), filt, fmul, nb) & AF_F_HIGH) != 0;
+    if (P + H + KP <= 16 * W) {
+        if (!ok) ok = (af_filter_probe(af_kmer_at<W, KP, OFF, (P + H + KP <= 16 * W ? P + H : 0)>(w), filt, fmul, nb) & AF_F_HIGH) != 0;
+    }
+    return ok;
+}
+
+template <int W, int KP, int OFF, int J, int NP, int NPMIN, bool REFINE, int NW>
+AF_HD void af_scan_sample(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
+                          uint32_t &acc) {
+    if constexpr (J < NP) {
+        constexpr int S = 20 - KP;
+        uint32_t t = af_filter_probe(af_kmer_at<W, KP, OFF, J * S>(w), filt, fmul, nb);
+        if (J >= NPMIN) t = J < nprobe ? t : 0u;
+        if constexpr (REFINE) {
+            if (t & AF_F_HIGH) {                                             // rare: ~0.14 % of the samples
+                if (!af_neighbour_ok<W, KP, OFF, J * S>(w, filt, fmul, nb)) t = 0u;
+            }
+        }
+        acc |= t;
+        af_scan_sample<W, KP, OFF, J + 1, NP, NPMIN, REFINE>(w, nprobe, filt, fmul, nb, acc);
+    }
+}
+
+// All sample positions of one read held in registers w[OFF..OFF+W).  Fully unrolled (compile-time
+// recursion): every shift and word index is a constant, the first NPMIN samples exist for every
+// read length this W can hold, the last few are masked by a warp-uniform select.  With REFINE a
+// sample only counts if its neighbour test passes too (af_neighbour_ok): that removes nearly all
+// chance hits (362 k -> 16 k flagged reads per 10 M pairs) but the rarely taken branch per sample
+// splits the probe sequence into 36 basic blocks and the kernel runs 2x slower (measured), so the
+// production scan uses REFINE = false and leaves the false positives to k_verify.
+template <int W, int KP, int OFF, int NW, bool REFINE = false>
 AF_HD uint32_t af_scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul,
                               uint32_t nb) {
     constexpr int S = 20 - KP;  // k = 19
-    constexpr uint32_t KMASK = (1u << (2 * KP)) - 1u;
     constexpr int NP = (16 * W - KP) / S + 1;                                // samples when L == 16 W
     constexpr int LMIN = 16 * (W - 1) + 1;                                   // shortest L with this W
     constexpr int NPMIN = LMIN >= KP ? (LMIN - KP) / S + 1 : 0;
     uint32_t acc = 0;
-#pragma unroll
-    for (int j = 0; j < NP; j++) {
-        const int o = 2 * j * S, wi = o >> 5, sh = o & 31;
-        uint32_t x;
-        if (sh + 2 * KP <= 32) x = (w[OFF + wi] >> sh) & KMASK;
-        else x = af_funnel_r(w[OFF + wi], w[OFF + (wi + 1 < W ? wi + 1 : wi)], sh) & KMASK;
-        uint32_t b, fp3;
-        af_filter_hash(x, fmul, nb, b, fp3);
-        const uint32_t v = filt[b] ^ fp3;
-        uint32_t t = (v - AF_F_ONES) & ~v;                                   // AF_F_HIGH applied once, below
-        if (j >= NPMIN) t = j < nprobe ? t : 0u;
-        acc |= t;
-    }
+    af_scan_sample<W, KP, OFF, 0, NP, NPMIN, REFINE>(w, nprobe, filt, fmul, nb, acc);
     return acc & AF_F_HIGH;
 }
 

@@ -363,19 +363,25 @@ extern "C" int af_synth_pairs_host(const af_synth_t *s, int64_t first_pair, int6
 // suite check the kernel's probe logic for every W without a GPU; no product path calls it.
 // ------------------------------------------------------------------------------------------
 template <int W, int KP>
-static void scan_pair_host(const af_index *idx, const uint32_t *words, int nprobe, int *f1, int *f2) {
+static void scan_pair_host(const af_index *idx, const uint32_t *words, int nprobe, bool refine, int *f1, int *f2) {
     uint32_t w[2 * W];
     for (int i = 0; i < 2 * W; i++) w[i] = words[i];
     const uint32_t fm = idx->fmul;
-    *f1 = af_scan_read<W, KP, 0, 2 * W>(w, nprobe, idx->filter.data(), fm, idx->nb) != 0;
-    *f2 = af_scan_read<W, KP, W, 2 * W>(w, nprobe, idx->filter.data(), fm, idx->nb) != 0;
+    if (refine) {
+        *f1 = af_scan_read<W, KP, 0, 2 * W, true>(w, nprobe, idx->filter.data(), fm, idx->nb) != 0;
+        *f2 = af_scan_read<W, KP, W, 2 * W, true>(w, nprobe, idx->filter.data(), fm, idx->nb) != 0;
+    } else {
+        *f1 = af_scan_read<W, KP, 0, 2 * W, false>(w, nprobe, idx->filter.data(), fm, idx->nb) != 0;
+        *f2 = af_scan_read<W, KP, W, 2 * W, false>(w, nprobe, idx->filter.data(), fm, idx->nb) != 0;
+    }
 }
 
 #define AF_HOST_SCAN_CASE(WW) \
-    case WW: if (idx->kp == 12) scan_pair_host<WW, 12>(idx, words, nprobe, flag1, flag2); else scan_pair_host<WW, 13>(idx, words, nprobe, flag1, flag2); return AF_OK;
+    case WW: if (idx->kp == 12) scan_pair_host<WW, 12>(idx, words, nprobe, refine, flag1, flag2); else scan_pair_host<WW, 13>(idx, words, nprobe, refine, flag1, flag2); return AF_OK;
 
 extern "C" int af_debug_scan_pair(const af_index_t *idx, const uint32_t *words, int32_t words_per_read, int32_t read_len,
-                                  int32_t *flag1, int32_t *flag2) {
+                                  int32_t with_neighbour_test, int32_t *flag1, int32_t *flag2) {
+    const bool refine = with_neighbour_test != 0;
     if (!idx || !words || !flag1 || !flag2 || (idx->kp != 12 && idx->kp != 13) || idx->P.k != 19) { af_set_error("af_debug_scan_pair: bad argument"); return AF_ERR_ARG; }
     const int nprobe = read_len >= idx->kp ? (read_len - idx->kp) / idx->stride + 1 : 0;
     switch (words_per_read) {

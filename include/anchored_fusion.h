@@ -171,7 +171,7 @@ int af_seed_scan(const af_dev_index_t *d, const af_batch_t *batch, uint32_t *d_f
 /* host twin of the kernel's probe sequence for one pair (2*words_per_read packed words, mate 1 then
  * mate 2): test hook, runs the same template code the kernel runs; not on any product path */
 int af_debug_scan_pair(const af_index_t *idx, const uint32_t *words, int32_t words_per_read, int32_t read_len,
-                       int32_t *flag1, int32_t *flag2);
+                       int32_t with_neighbour_test, int32_t *flag1, int32_t *flag2);
 int af_seed_scan_config(int32_t threads_per_block, int32_t blocks_per_sm); /* tuning knob; 0 = default */
 int64_t af_kernel_launches(void); /* kernels this library has launched since it was loaded */
 /* per-stage device time of af_anchor_batch, CUDA events on the launching stream: begin, run,

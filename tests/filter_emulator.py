@@ -12,9 +12,10 @@ def filter_hash(key, fmul, kp, nb):
     return b, fp3
 
 
-def expected_flags(index, codes, lens=None):
+def expected_flags(index, codes, lens=None, refine=False):
     """codes: (n_reads, stride) base codes with N/pad positions already replaced by the pad
-    pattern (i.e. what the packed words hold).  Returns bool[n_reads]."""
+    pattern (i.e. what the packed words hold).  Returns bool[n_reads].  refine=True models the
+    optional neighbour test (af_neighbour_ok): a sample counts only if the k'-mer at p-H or p+H passes too."""
     info = index.info
     KP, S, nb, fm = info.kp, info.stride, info.n_buckets, info.filter_mul
     filt = index.filter_words().astype(np.uint64)
@@ -30,11 +31,24 @@ def expected_flags(index, codes, lens=None):
     if lens is not None:
         for i in range(stride):
             full[lens <= i, i] = pad[i & 3]
-    for p in range(0, Lmax - KP + 1, S):          # the kernel samples up to the batch's longest read
+    H = (19 - KP + 1) // 2
+
+    def probe(p):
         key = np.zeros(n, np.uint64)
         for t in range(KP):
             key |= full[:, p + t] << np.uint64(2 * t)
         b, fp3 = filter_hash(key, fm, KP, nb)
         v = filt[b] ^ fp3
-        flag |= (((v - np.uint64(0x40100401)) & ~v & np.uint64(0xA0080200)) & np.uint64(0xFFFFFFFF)) != 0
+        return (((v - np.uint64(0x40100401)) & ~v & np.uint64(0xA0080200)) & np.uint64(0xFFFFFFFF)) != 0
+
+    for p in range(0, Lmax - KP + 1, S):          # the kernel samples up to the batch's longest read
+        hit = probe(p)
+        if refine and hit.any():                  # neighbour test (af_neighbour_ok)
+            ok = np.zeros(n, bool)
+            if p - H >= 0:
+                ok |= probe(p - H)
+            if p + H + KP <= 16 * W:
+                ok |= probe(p + H)
+            hit &= ok
+        flag |= hit
     return flag

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 
-def _scan_pairs_host(af, index, batch):
+def _scan_pairs_host(af, index, batch, refine=False):
     from anchored_fusion_b200._lib import check, lib
     lay = af.layout(batch.max_read_len, batch.n_pairs)
     W, Q = lay.words_per_read, lay.quads_per_pair
@@ -19,7 +19,7 @@ def _scan_pairs_host(af, index, batch):
         tile, lane = p >> 5, p & 31
         words = np.concatenate([packed[((tile * Q + q) * 32 + lane) * 4: ((tile * Q + q) * 32 + lane) * 4 + 4] for q in range(Q)])[: 2 * W]
         words = np.ascontiguousarray(words, dtype=np.uint32)
-        check(lib().af_debug_scan_pair(index._h, words.ctypes.data, W, L, ctypes.byref(f1), ctypes.byref(f2)))
+        check(lib().af_debug_scan_pair(index._h, words.ctypes.data, W, L, int(refine), ctypes.byref(f1), ctypes.byref(f2)))
         out[2 * p], out[2 * p + 1] = bool(f1.value), bool(f2.value)
     return out
 
@@ -45,3 +45,8 @@ def test_host_twin_equals_emulation_and_has_no_false_negatives(read_len, kp):
     assert np.array_equal(got, want)
     hits = oracle.anchor_reads(oracle.encode(anchor), codes, threads=4)
     assert len(hits) > 50 and got[hits["read_id"]].all()
+    # the optional neighbour test (a sample counts only if the k'-mer at p-H or p+H passes too) loses
+    # no anchored read either and removes most chance hits
+    ref = _scan_pairs_host(af, index, batch, refine=True)
+    assert np.array_equal(ref, expected_flags(index, codes, refine=True))
+    assert ref[hits["read_id"]].all() and not (ref & ~got).any() and ref.sum() <= got.sum()
