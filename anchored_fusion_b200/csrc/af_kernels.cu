@@ -214,21 +214,20 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
 }
 
 static int g_scan_threads = 768, g_scan_mode = 3, g_fused = 0, g_middle = 7;
-// tuning knob: mode 0/3 = register double buffer under an 85-register cap (threads <= 768, the
-// default: 24 warps per SM), 1 = register double buffer with 128 registers (threads <= 512),
-// 2 = no prefetch (threads <= 1024)
+// tuning knobs.  Scan variant (mode 0/3): register double buffer under an 85-register cap, up to 768
+// threads = 24 warps per SM (a 512-thread / 128-register variant and a 1024-thread variant without
+// prefetch measured the same and were dropped to keep the build short).
 extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     // modes 4 / 5 switch af_anchor_batch between the fused, warp-specialised scan+verify kernel (4)
     // and the separate seed-scan / verify kernels (5, default); the stand-alone scan variant is untouched
     if (mode == 4 || mode == 5) { g_fused = mode == 4; return AF_OK; }
-    // modes 7 / 6 / 8: what stands between the scan and k_extend -- 7 = k_verify (default: exact seeded
-    // test against the table and the anchor), 6 = k_refine (neighbour test in shared memory, no gathers
-    // beyond the read itself; measured slower than k_verify), 8 = nothing (every flagged read gets a warp
-    // of k_extend; only sensible with a scan built with REFINE)
-    if (mode == 6 || mode == 7 || mode == 8) { g_middle = mode == 8 ? 0 : mode; return AF_OK; }
-    if (mode == 0) mode = 3;
-    if (mode < 1 || mode > 3) { af_set_error("af_seed_scan_config: mode must be 0..3"); return AF_ERR_ARG; }
-    const int maxt = mode == 1 ? 512 : (mode == 2 ? 1024 : 768);
+    // modes 7 / 8: what stands between the scan and k_extend -- 7 = k_verify (default: exact seeded test
+    // against the table and the anchor), 8 = nothing (every flagged read gets a warp of k_extend; for
+    // experiments with a scan built with the neighbour test, af_scan_read<..., REFINE = true>)
+    if (mode == 7 || mode == 8) { g_middle = mode == 8 ? 0 : 7; return AF_OK; }
+    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off) or 7/8"); return AF_ERR_ARG; }
+    mode = 3;
+    const int maxt = 768;
     if (threads_per_block == 0) threads_per_block = maxt;
     if (threads_per_block < 64 || threads_per_block > maxt || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..%d, multiple of 32", maxt); return AF_ERR_ARG; }
     g_scan_threads = threads_per_block;
@@ -258,9 +257,7 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
 template <int W, int KP>
 static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
                             uint32_t *cc, cudaStream_t st) {
-    if (g_scan_mode == 2) return launch_scan<W, KP, 1024, false>(d, b, n_tiles, nprobe, flags, cc, st);
-    if (g_scan_mode == 3) return launch_scan<W, KP, 768, true>(d, b, n_tiles, nprobe, flags, cc, st);
-    return launch_scan<W, KP, 512, true>(d, b, n_tiles, nprobe, flags, cc, st);
+    return launch_scan<W, KP, 768, true>(d, b, n_tiles, nprobe, flags, cc, st);
 }
 
 #define AF_SCAN_CASE(WW)                                                                       \
@@ -786,108 +783,6 @@ k_scan_verify(const uint4 *__restrict__ packed, long long n_tiles, long long n_p
 }
 
 // ------------------------------------------------------------------------------------------
-// refine: the cheap replacement of k_verify in front of k_extend.
-//
-// k_verify is bound by L1TEX gathers (~30 distinct lines per flagged read).  This kernel asks a
-// question that needs NO gather beyond the read itself: a true >= k match [q, q+k) that contains the
-// sample k'-mer at p also contains the k'-mer at p-h or the one at p+h, h = ceil((k-k')/2) -- so a
-// flagged read is kept iff some sample passes the shared-memory filter AND so does its neighbour
-// at p-h or p+h.  No false negatives; a chance k'-mer hit (96 % of the flagged reads) survives
-// with probability ~0.3 %.  Survivors that are not seeded after all cost k_extend one warp each and
-// produce no record.  Persistent, one CTA per SM, filter staged once, reads in registers.
-// ------------------------------------------------------------------------------------------
-template <int W, int KP>
-__global__ void __launch_bounds__(1024, 1)
-k_refine(const uint4 *__restrict__ packed, int uniform_len, const uint16_t *__restrict__ lens,
-         const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts, uint32_t cand_cap,
-         const uint32_t *__restrict__ g_filter, uint32_t fmul, uint32_t nb, uint8_t *__restrict__ keep,
-         uint32_t *__restrict__ chunk_counts) {
-    extern __shared__ uint32_t filt[];
-    constexpr int Q = (2 * W + 3) / 4, S = 20 - KP, H = (19 - KP + 1) / 2;
-    constexpr uint32_t KMASK = (1u << (2 * KP)) - 1u;
-    constexpr int NP = (16 * W - KP) / S + 1;
-    const uint32_t ncand = min(counts[AF_CNT_FLAGGED], cand_cap);
-    const int lane = threadIdx.x & 31;
-    if ((uint32_t)blockIdx.x * blockDim.x >= ncand) return;
-    stage_filter(filt, g_filter, nb);
-    __syncthreads();
-    auto kmer_at = [&](const uint32_t (&w)[W + 1], int p) -> uint32_t {     // p is a compile-time constant after unrolling
-        const int o = 2 * p, wi = o >> 5, sh = o & 31;
-        return (sh + 2 * KP <= 32 ? (w[wi] >> sh) : af_funnel_r(w[wi], w[wi + 1], sh)) & KMASK;
-    };
-    auto passes = [&](uint32_t key) -> bool {
-        uint32_t b, fp3;
-        af_filter_hash(key, fmul, nb, b, fp3);
-        return af_filter_test(filt[b], fp3) != 0;
-    };
-    for (uint32_t c0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; c0 < ncand; c0 += gridDim.x * blockDim.x) {
-        const uint32_t c = c0 + lane;
-        bool kept = false;
-        if (c < ncand) {
-            const uint32_t rid = cand[c], pair = rid >> 1, mate = rid & 1u;
-            const int L = uniform_len > 0 ? uniform_len : (int)lens[rid];
-            const uint4 *src = packed + (size_t)(pair >> 5) * (Q * 32) + (pair & 31);
-            uint32_t qw[4 * Q];
-#pragma unroll
-            for (int q = 0; q < Q; q++) {
-                const uint4 v = src[q * 32];
-                qw[4 * q] = v.x; qw[4 * q + 1] = v.y; qw[4 * q + 2] = v.z; qw[4 * q + 3] = v.w;
-            }
-            uint32_t w[W + 1];
-#pragma unroll
-            for (int t = 0; t < W; t++) w[t] = mate ? qw[W + t] : qw[t];
-            w[W] = 0;
-#pragma unroll
-            for (int j = 0; j < NP; j++) {
-                const int p = j * S;
-                if (p + KP > L) continue;
-                if (!passes(kmer_at(w, p))) continue;
-                bool nb_ok = false;
-                if (p - H >= 0) nb_ok = passes(kmer_at(w, p - H >= 0 ? p - H : 0));
-                if (!nb_ok && p + H + KP <= 16 * W && p + H + KP <= L) nb_ok = passes(kmer_at(w, p + H + KP <= 16 * W ? p + H : 0));
-                kept |= nb_ok;
-            }
-            keep[c] = kept ? 1 : 0;
-        }
-        const uint32_t bal = __ballot_sync(FULL, kept);
-        if (lane == 0 && bal) atomicAdd(&chunk_counts[c0 / CB_PER_BLOCK], __popc(bal));
-    }
-}
-
-template <int W, int KP>
-static int launch_refine(const af_dev_index *d, const af_batch_t *b, const uint32_t *cand, uint32_t cand_cap,
-                         uint32_t *counts, uint8_t *keep, uint32_t *cc, cudaStream_t st) {
-    const size_t smem = (size_t)d->nb * 4;
-    static bool attr_set[64] = {false};  // per device
-    if (!attr_set[d->device & 63]) {
-        AF_CUDA(cudaFuncSetAttribute(k_refine<W, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[d->device & 63] = true;
-    }
-    long long blocks = ((long long)cand_cap + 1023) / 1024;
-    k_refine<W, KP><<<(int)(blocks < d->num_sms ? blocks : d->num_sms), 1024, smem, st>>>(
-        (const uint4 *)b->packed, b->uniform_len, b->lens, cand, counts, cand_cap, d->d_filter, d->fmul, d->nb, keep, cc);
-    g_launches++;
-    AF_CUDA(cudaGetLastError());
-    return AF_OK;
-}
-
-#define AF_REFINE_CASE(WW)                                                                          \
-    case WW:                                                                                        \
-        return d->kp == 12 ? launch_refine<WW, 12>(d, b, cand, cand_cap, counts, keep, cc, st)       \
-                           : launch_refine<WW, 13>(d, b, cand, cand_cap, counts, keep, cc, st);
-
-static int refine_impl(const af_dev_index *d, const af_batch_t *b, int W, const uint32_t *cand, uint32_t cand_cap,
-                       uint32_t *counts, uint8_t *keep, uint32_t *cc, cudaStream_t st) {
-    switch (W) {
-        AF_REFINE_CASE(1) AF_REFINE_CASE(2) AF_REFINE_CASE(3) AF_REFINE_CASE(4) AF_REFINE_CASE(5) AF_REFINE_CASE(6)
-        AF_REFINE_CASE(7) AF_REFINE_CASE(8) AF_REFINE_CASE(9) AF_REFINE_CASE(10) AF_REFINE_CASE(11) AF_REFINE_CASE(12)
-        AF_REFINE_CASE(13) AF_REFINE_CASE(14) AF_REFINE_CASE(15) AF_REFINE_CASE(16)
-    }
-    af_set_error("unsupported words_per_read %d", W);
-    return AF_ERR_ARG;
-}
-
-// ------------------------------------------------------------------------------------------
 // extend: one warp per seeded read
 // ------------------------------------------------------------------------------------------
 struct ExtParams {
@@ -1222,11 +1117,7 @@ extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, voi
         (const uint2 *)flags, lay.n_tiles, cc1, w.nch1, cand, (uint32_t)cand_cap, d_counts, AF_CNT_FLAGGED, -1);
     prof_span(ev, st, ST_COMPACT1);
     prof_mark(&ev, st);
-    if (g_middle == 6) {
-        rc = refine_impl(d, b, lay.words_per_read, cand, (uint32_t)cand_cap, d_counts, keep, cc2, st);
-        if (rc) return rc;
-        g_launches--;                                       // counted again below
-    } else {
+    {
     long long vthreads = cand_cap < (long long)d->num_sms * 2048 ? cand_cap : (long long)d->num_sms * 2048;
     const unsigned vgrid = (unsigned)((vthreads + 255) / 256);
 #define AF_VERIFY_ARGS (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, \

@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=10_000_000)
 ap.add_argument("--read-len", type=int, default=150)
 ap.add_argument("--iters", type=int, default=10)
-ap.add_argument("--configs", default="12:1:512,12:1:448,12:2:1024,12:3:768,12:3:640,12:3:576,13:1:512,13:3:768")
+ap.add_argument("--configs", default="12:3:768,12:3:640,12:3:512,13:3:768")
 args = ap.parse_args()
 peak = 6554.2
 spec = af.synth_spec(seed=1, ref_len=10_000_000, anchor_start=2_000_000, anchor_len=6783, read_len=args.read_len,
