@@ -15,7 +15,7 @@ import sys
 import time
 
 from .functions import combine_split_reads, split_records
-from .stage import GeneAnchorer, anchor_stage
+from .stage import GeneAnchorer, anchor_stage, anchor_stage_multi
 
 
 def _common_flags(p):
@@ -130,8 +130,24 @@ def main_bulk(argv=None):
         return folder + '/work_dir/' + gene + '_fusion'
 
     fastas = split_anchor_fasta(args.file_anchored_cds, gene_names, lambda g: work_prefix(g) + '_anchored_gene_sequence.fa')
-    for gene, fa in zip(gene_names, fastas):
-        run_gene_sample(fa, gene, args.fastq1, args.fastq2, work_prefix(gene), args)
+    todo = [(g, fa) for g, fa in zip(gene_names, fastas)
+            if not (os.path.exists(work_prefix(g) + '_anchored_reads.bam') and os.path.exists(work_prefix(g) + '_realign_reads.bam'))]
+    for g in gene_names:
+        if g not in [t[0] for t in todo]:
+            print('[anchoring] %s: outputs exist, skipping (same existence guard as the reference)' % work_prefix(g))
+    if len(todo) == 1:
+        run_gene_sample(todo[0][1], todo[0][0], args.fastq1, args.fastq2, work_prefix(todo[0][0]), args)
+    elif todo:
+        # several anchored genes: decode and pack the FASTQ pair once, scan it for every gene
+        # (the reference re-reads both files once per gene, Anchored_Fusion.py:126,182)
+        t0 = time.time()
+        gas = [GeneAnchorer(fa, args.gpu_number, g) for g, fa in todo]
+        all_stats = anchor_stage_multi(gas, args.fastq1, args.fastq2, [work_prefix(g) for g, _ in todo])
+        for (g, _), stats in zip(todo, all_stats):
+            groups = write_split_points(stats, g, work_prefix(g) + '_split_points.txt')
+            print('[anchoring] %s: %d pairs, %d anchored reads, %d half-anchored pairs, %d split-point groups'
+                  % (g, stats['pairs'], stats['anchored'], stats['half_anchored_pairs'], len(groups)))
+        print('[anchoring] %d genes in one pass over the reads, %.2f s' % (len(todo), time.time() - t0))
     return 0
 
 

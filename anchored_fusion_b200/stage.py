@@ -147,50 +147,62 @@ class AnchoredRead:
         self.hit, self.gid, self.name, self.seq, self.qual = hit, gid, name, seq, qual
 
 
-def scan_fastq_pair(index, fastq1, fastq2, device=0, batch_pairs=1 << 21, max_read_len=None, engine=None,
-                    batch_filter=None):
-    """Stream a FASTQ pair through the GPU.  Returns (anchored, mates, stats): anchored is a list of
-    AnchoredRead (global read ids), mates maps the global read id of every UNanchored mate of a
-    half-anchored pair to its (name, seq, qual).  batch_filter(i) -> bool lets a rank of a
-    multi-GPU job take only its share of the batches (all ranks still decode the stream)."""
-    eng = engine or Anchorer(index, device)
+def scan_fastq_pair_multi(gene_engines, fastq1, fastq2, batch_pairs=1 << 20, max_read_len=None, batch_filter=None):
+    """Stream a FASTQ pair ONCE through the GPU for several anchored genes (the
+    reference re-reads both FASTQs once per gene, Anchored_Fusion.py:126,182).  gene_engines is a list
+    of (AnchorIndex, Anchorer); every decoded / packed batch is handed to each engine in turn.
+    Returns one (anchored, mates, stats) per gene: anchored is a list of AnchoredRead (global read
+    ids), mates maps the global read id of every UNanchored mate of a half-anchored pair to its
+    (name, seq, qual).  batch_filter(i) -> bool lets a rank of a multi-GPU job take only its share
+    of the batches (all ranks still decode the stream).  The pad pattern of the first gene's index
+    is used for all of them (the pad only influences false positives of the filter, never results)."""
+    index0, eng0 = gene_engines[0]
     mrl = max_read_len or max(peek_max_read_len(fastq1), peek_max_read_len(fastq2))
     while True:
-        bufs = getattr(eng, "_host_buffers", None)
+        bufs = getattr(eng0, "_host_buffers", None)
         if bufs is None or bufs.key != (mrl, batch_pairs):
             if bufs is not None:
                 bufs.free()
-            bufs = eng._host_buffers = HostBuffers(mrl, batch_pairs)      # lives with the engine: reused across files
-        reader = FastqPairReader(fastq1, fastq2, mrl, index.pad_byte, batch_pairs, buffers=bufs)
-        anchored, mates, base, stats = [], {}, 0, {"pairs": 0, "flagged": 0, "anchored": 0}
+            bufs = eng0._host_buffers = HostBuffers(mrl, batch_pairs)     # lives with the engine: reused across files
+        reader = FastqPairReader(fastq1, fastq2, mrl, index0.pad_byte, batch_pairs, buffers=bufs)
+        out = [([], {}, {"pairs": 0, "flagged": 0, "anchored": 0}) for _ in gene_engines]
+        base = 0
         try:
             i = 0
             while True:
                 batch = reader.next_batch()
                 if batch is None:
                     break
-                if batch_filter is None or batch_filter(i):
-                    hits, st = eng.anchor_host(batch, slot_pairs=1 << 18, n_slots=3)
-                    have = set(int(r) for r in hits["read_id"])
-                    for h in hits:
-                        rid = int(h["read_id"])
-                        name, seq, qual = reader.record(rid)
-                        anchored.append(AnchoredRead(h.copy(), 2 * base + rid, name, seq, qual))
-                        if (rid ^ 1) not in have:
-                            mates[2 * base + (rid ^ 1)] = reader.record(rid ^ 1)
-                    stats["flagged"] += st["flagged"]
-                    stats["anchored"] += len(hits)
+                for (index, eng), (anchored, mates, stats) in zip(gene_engines, out):
+                    if batch_filter is None or batch_filter(i):
+                        hits, st = eng.anchor_host(batch, slot_pairs=1 << 18, n_slots=3)
+                        have = set(int(r) for r in hits["read_id"])
+                        for h in hits:
+                            rid = int(h["read_id"])
+                            name, seq, qual = reader.record(rid)
+                            anchored.append(AnchoredRead(h.copy(), 2 * base + rid, name, seq, qual))
+                            if (rid ^ 1) not in have:
+                                mates[2 * base + (rid ^ 1)] = reader.record(rid ^ 1)
+                        stats["flagged"] += st["flagged"]
+                        stats["anchored"] += len(hits)
+                    stats["pairs"] += batch.n_pairs
                 base += batch.n_pairs
-                stats["pairs"] += batch.n_pairs
                 i += 1
             reader.close()
-            return anchored, mates, stats
+            return out
         except AnchoredFusionError as e:
             reader.close()
             if "max_read_len" in str(e) and mrl < _lib.MAX_READ_LEN:
                 mrl = _lib.MAX_READ_LEN      # a later read was longer than the peeked ones: start over
                 continue
             raise
+
+
+def scan_fastq_pair(index, fastq1, fastq2, device=0, batch_pairs=1 << 20, max_read_len=None, engine=None,
+                    batch_filter=None):
+    """One gene: see scan_fastq_pair_multi.  Returns (anchored, mates, stats)."""
+    eng = engine or Anchorer(index, device)
+    return scan_fastq_pair_multi([(index, eng)], fastq1, fastq2, batch_pairs, max_read_len, batch_filter)[0]
 
 
 def _sorted_anchored(anchored):
@@ -278,15 +290,26 @@ class GeneAnchorer:
         self.engine = Anchorer(self.index, resolve_device(gpu_number))
 
 
+def finish_stage(ga, out_prefix, anchored, mates, stats):
+    """Write one gene's stage files from a scan result; returns the stats dict of anchor_stage."""
+    stats = dict(stats)
+    stats.update(write_stage_outputs(out_prefix, ga.gene, len(ga.seq), anchored, mates))
+    stats["half_anchored_pairs"] = len(mates)
+    stats["hits"] = hits_array(anchored)
+    return stats
+
+
+def anchor_stage_multi(gene_anchorers, fastq1, fastq2, out_prefixes, batch_pairs=1 << 20):
+    """The anchoring stage for several genes with ONE pass over the FASTQ pair."""
+    results = scan_fastq_pair_multi([(ga.index, ga.engine) for ga in gene_anchorers], fastq1, fastq2, batch_pairs)
+    return [finish_stage(ga, prefix, *res) for ga, prefix, res in zip(gene_anchorers, out_prefixes, results)]
+
+
 def anchor_stage(file_anchored_seq, fastq1, fastq2, out_prefix, thread="1", gpu_number="-1", gene_name=None,
                  batch_pairs=1 << 20, kp=0, gene_anchorer=None):
     """Drop-in for the anchoring stage.  file_anchored_seq is <work>_anchored_gene_sequence.fa;
     `thread` is accepted for signature compatibility (the two zlib decode threads and the GPU do
     the work).  Returns a stats dict; see write_stage_outputs for the files."""
     ga = gene_anchorer or GeneAnchorer(file_anchored_seq, gpu_number, gene_name, kp)
-    gene, seq, index = ga.gene, ga.seq, ga.index
-    anchored, mates, stats = scan_fastq_pair(index, fastq1, fastq2, batch_pairs=batch_pairs, engine=ga.engine)
-    stats.update(write_stage_outputs(out_prefix, gene, len(seq), anchored, mates))
-    stats["half_anchored_pairs"] = len(mates)
-    stats["hits"] = hits_array(anchored)
-    return stats
+    anchored, mates, stats = scan_fastq_pair(ga.index, fastq1, fastq2, batch_pairs=batch_pairs, engine=ga.engine)
+    return finish_stage(ga, out_prefix, anchored, mates, stats)

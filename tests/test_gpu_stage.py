@@ -114,3 +114,32 @@ def test_singlecell_cli_matches_bulk_union(bundled, tmp_path):
         _, _, recs = read_bam(os.path.join(out, "BCR", "work_dir", c, "BCR_fusion_anchored_reads.bam"))
         got += [(r["qname"], 1 if r["flag"] & 0x80 else 0, r["pos"]) for r in recs]
     assert sorted(got) == want
+
+
+def test_two_genes_one_pass_equals_two_separate_runs(bundled, tmp_path):
+    """A two-record CDS file: the bulk driver decodes the FASTQ pair once and scans it for both
+    anchors; each gene's files equal those of a run with that gene alone."""
+    from anchored_fusion_b200.bam import read_bam, sam_line
+    from anchored_fusion_b200.cli import main_bulk
+    d = str(tmp_path)
+    a = bundled["anchor"]
+    second = a[2500:6000][::-1].translate(str.maketrans("ACGT", "TGCA"))     # reverse complement of a BCR slice
+    fa2 = os.path.join(d, "two.fa")
+    open(fa2, "w").write(bundled["header"] + "\n" + a + "\n>NM_000000.1 RCBCR [organism=Homo sapiens]\n" + second + "\n")
+    p1, p2 = _write_bundled_fastqs(bundled, d)
+    out2 = os.path.join(d, "out2")
+    assert main_bulk(["--file_anchored_cds", fa2, "--fastq1", p1, "--fastq2", p2, "--out_folder", out2]) == 0
+    singles = {}
+    for gene, seq in (("BCR", a), ("RCBCR", second)):
+        fa1 = os.path.join(d, gene + ".fa")
+        open(fa1, "w").write(">NM_1.1 " + gene + "\n" + seq + "\n")
+        out1 = os.path.join(d, "out_" + gene)
+        assert main_bulk(["--file_anchored_cds", fa1, "--fastq1", p1, "--fastq2", p2, "--out_folder", out1]) == 0
+        singles[gene] = out1
+    for gene in ("BCR", "RCBCR"):
+        w2 = os.path.join(out2, gene + "_fusion", "work_dir", gene + "_fusion")
+        w1 = os.path.join(singles[gene], gene + "_fusion", "work_dir", gene + "_fusion")
+        r2, r1 = read_bam(w2 + "_anchored_reads.bam")[2], read_bam(w1 + "_anchored_reads.bam")[2]
+        assert len(r2) > 300 and [sam_line(r) for r in r2] == [sam_line(r) for r in r1]
+        for suffix in ("_tmp_1.fastq", "_tmp_2.fastq", "_split_points.txt"):
+            assert open(w2 + suffix).read() == open(w1 + suffix).read()
