@@ -221,6 +221,8 @@ struct af_index {
     std::vector<uint8_t> codes;     // anchor base codes 0..4
     uint32_t fmul, nb;
     std::vector<uint32_t> filter;   // nb bucket words
+    uint32_t fmul2, nb2;
+    std::vector<uint32_t> filter2;  // half-size copy (own multiplier) for k_verify, which shares the SM with read staging
     uint32_t tmask;
     std::vector<uint32_t> table;    // (tmask+1) x {key, value}; value = strand<<31 | anchor pos
     std::vector<uint32_t> member;   // 4^kp-bit bitmap: bit key set iff key is an anchor k'-mer

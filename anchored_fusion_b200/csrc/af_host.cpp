@@ -126,20 +126,25 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du,
                                     0xFD7046C5u, 0xB55A4F09u, 0x8DA6B343u, 0xD8163841u, 0xCB1AB31Fu, 0x9C06FAF5u,
                                     0x2545F491u, 0x6C8E9CF5u, 0xE7037ED1u, 0xA3B19535u};
-    long best = -1;
     std::vector<uint32_t> cand;
-    for (uint32_t m : muls) {
-        int ov = build_filter(keys, m, nb, cand);
-        long fp = 0;
-        uint32_t x = 0x12345678u;
-        for (int t = 0; t < (1 << 18); t++) {
-            x = af_mix32(x + 0x9E3779B9u);
-            uint32_t b, fp3;
-            af_filter_hash(x & kmask, m, nb, b, fp3);
-            fp += af_filter_test(cand[b], fp3) != 0;
+    auto pick = [&](uint32_t nbk, uint32_t &mul_out, std::vector<uint32_t> &filt_out, int32_t *ov_out) {
+        long best = -1;
+        for (uint32_t m : muls) {
+            int ov = build_filter(keys, m, nbk, cand);
+            long fp = 0;
+            uint32_t x = 0x12345678u;
+            for (int t = 0; t < (1 << 18); t++) {
+                x = af_mix32(x + 0x9E3779B9u);
+                uint32_t b, fp3;
+                af_filter_hash(x & kmask, m, nbk, b, fp3);
+                fp += af_filter_test(cand[b], fp3) != 0;
+            }
+            if (best < 0 || fp < best) { best = fp; mul_out = m; filt_out = cand; if (ov_out) *ov_out = ov; }
         }
-        if (best < 0 || fp < best) { best = fp; idx->fmul = m; idx->filter = cand; idx->n_overflow = ov; }
-    }
+    };
+    pick(nb, idx->fmul, idx->filter, &idx->n_overflow);
+    idx->nb2 = ((nb / 2) + 31u) & ~31u;
+    pick(idx->nb2, idx->fmul2, idx->filter2, nullptr);
 
     // 4-base pad pattern whose k'-mers (all 4 phases) are absent from the anchor, so padded
     // tails and N positions of a read never light the filter up by themselves.

@@ -86,6 +86,8 @@ struct af_dev_index {
     int32_t kp, stride, G;
     uint32_t fmul, nb, tmask;
     uint32_t *d_filter;  // nb words
+    uint32_t fmul2, nb2;
+    uint32_t *d_filter2; // nb2 words: the half-size filter k_verify stages
     uint2 *d_table;      // tmask+1 entries {key, value}
     uint32_t *d_member;  // 4^kp-bit exact membership bitmap (L2 resident)
     uint8_t *d_anchor;   // G base codes
@@ -213,7 +215,7 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     }
 }
 
-static int g_scan_threads = 768, g_scan_mode = 3, g_fused = 0, g_middle = 7;
+static int g_scan_threads = 768, g_scan_mode = 3, g_fused = 0, g_middle = 7, g_verify_smem = 1;
 // tuning knobs.  Scan variant (mode 0/3): register double buffer under an 85-register cap, up to 768
 // threads = 24 warps per SM (a 512-thread / 128-register variant and a 1024-thread variant without
 // prefetch measured the same and were dropped to keep the build short).
@@ -225,7 +227,10 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     // against the table and the anchor), 8 = nothing (every flagged read gets a warp of k_extend; for
     // experiments with a scan built with the neighbour test, af_scan_read<..., REFINE = true>)
     if (mode == 7 || mode == 8) { g_middle = mode == 8 ? 0 : 7; return AF_OK; }
-    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off) or 7/8"); return AF_ERR_ARG; }
+    // modes 9 / 10: k_verify_smem (9, default: membership from a half-size filter in shared memory) or
+    // k_verify (10: membership from the L2-resident bitmap)
+    if (mode == 9 || mode == 10) { g_verify_smem = mode == 9; return AF_OK; }
+    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off), 7/8 or 9/10"); return AF_ERR_ARG; }
     mode = 3;
     const int maxt = 768;
     if (threads_per_block == 0) threads_per_block = maxt;
@@ -538,11 +543,126 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
     }
 }
 
+
 // 32 bases (64 bits) of a 2-bit packed sequence starting at base `pos` (pos >= 0)
 __device__ __forceinline__ unsigned long long packed_window(const uint32_t *__restrict__ a, int pos) {
     const int wi = pos >> 4, sh = 2 * (pos & 15);
     const uint32_t w0 = a[wi], w1 = a[wi + 1], w2 = a[wi + 2];
     return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// verify, shared-memory variant (default).  k_verify above spends its time in L1TEX: ~36 sector
+// requests per flagged read (ncu: 13 M sectors, 0.8 per cycle per SM), half of them the
+// membership gathers.  Here one persistent 1024-thread CTA per SM stages a HALF-SIZE copy of the
+// anchor filter next to the candidates' words, so "which samples are anchor k'-mers" costs no
+// global traffic at all; only those samples (1.3 per flagged read) go to the exact table, and the
+// >= k run is checked word-parallel against the 2-bit packed anchor: ~11 sector requests per read.
+// Same exact SEEDED predicate as k_verify.
+// ------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(1024, 1)
+k_verify_smem(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, const uint16_t *__restrict__ lens,
+              const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
+              const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts, uint32_t cand_cap,
+              const uint32_t *__restrict__ g_filter, uint32_t fmul, uint32_t nb, const uint2 *__restrict__ table,
+              uint32_t tmask, const uint8_t *__restrict__ anchor, const uint32_t *__restrict__ apk0,
+              const uint32_t *__restrict__ apk1, int anchor_has_n, int G, int K, uint8_t *__restrict__ keep,
+              uint32_t *__restrict__ chunk_counts) {
+    constexpr int S = 20 - KP, FL = 7;                      // flank bases needed on a side: k - k' <= 7
+    constexpr uint32_t kpmask = (1u << (2 * KP)) - 1u;
+    extern __shared__ uint32_t vsm[];
+    uint32_t *filt = vsm, *swb = vsm + nb;                  // word k of this thread's read at swb[k*VT + tid]
+    const int VT = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    const uint32_t ncand = min(counts[AF_CNT_FLAGGED], cand_cap);
+    if ((uint32_t)blockIdx.x * VT >= ncand) return;         // whole CTA idle: skip the staging too
+    stage_filter(filt, g_filter, nb);
+    __syncthreads();
+    uint32_t *sw = swb + tid;
+    // warp-uniform trip count so the ballot below is well defined
+    for (uint32_t c0 = (blockIdx.x * VT + tid) & ~31u; c0 < ncand; c0 += gridDim.x * VT) {
+        const uint32_t c = c0 + lane;
+        bool seeded = false;
+        if (c < ncand) {
+            const uint32_t rid = cand[c], pair = rid >> 1;
+            ReadRef r;
+            r.packed = packed;
+            r.base = ((size_t)(pair >> 5) * Q * 32 + (pair & 31)) * 4;
+            r.wofs = (int)(rid & 1u) * W;
+            r.L = uniform_len > 0 ? uniform_len : (int)lens[rid];
+            r.nm = nullptr;
+            if (n_nreads > 0) {
+                int lo = 0, hi = n_nreads;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
+                if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
+            }
+            const int np = r.L >= KP ? (r.L - KP) / S + 1 : 0;
+            // the read's words: whole quads (128-bit loads), then the W words it owns into shared memory
+            const int q0 = r.wofs >> 2, q1 = (r.wofs + W - 1) >> 2;
+            for (int q = q0; q <= q1; q++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(packed + r.base + (size_t)q * 128);
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int t = 4 * q + e - r.wofs;
+                    if (t >= 0 && t < W) sw[t * VT] = vv[e];
+                }
+            }
+            sw[W * VT] = 0; sw[(W + 1) * VT] = 0; sw[(W + 2) * VT] = 0;
+            unsigned long long hit = 0;
+            for (int j = 0; j < np; j++) {                   // which samples pass the shared-memory filter
+                const int o = 2 * j * S, wi = o >> 5;
+                const uint32_t key = __funnelshift_r(sw[wi * VT], sw[(wi + 1) * VT], o & 31) & kpmask;
+                uint32_t b, fp3;
+                af_filter_hash(key, fmul, nb, b, fp3);
+                if (af_filter_test(filt[b], fp3)) hit |= 1ull << j;
+            }
+            const bool fast = !r.nm && !anchor_has_n;
+            while (hit && !seeded) {
+                const int j = __ffsll((long long)hit) - 1;
+                hit &= hit - 1;
+                const int p = j * S, o = 2 * p;
+                const uint32_t key = __funnelshift_r(sw[(o >> 5) * VT], sw[((o >> 5) + 1) * VT], o & 31) & kpmask;
+                if (r.nm) {   // a k'-mer that overlaps an N is no seed material
+                    bool n = false;
+                    for (int t = 0; t < KP; t++) n |= r.is_n(p + t);
+                    if (n) continue;
+                }
+                for (uint32_t slot = af_table_hash(key, tmask);; slot = (slot + 1) & tmask) {
+                    const uint2 e = table[slot];
+                    if (e.x == AF_T_EMPTY) break;
+                    if (e.x != key) continue;
+                    const int s = e.y >> 31, jpos = (int)(e.y & 0x7FFFFFFFu);
+                    int run = KP;
+                    if (fast) {
+                        // read-forward frame: the sample at p sits at js on the forward (s=0) or
+                        // reverse-complemented (s=1) anchor; compare 2-bit windows word-parallel
+                        const int js = s ? G - jpos - KP : jpos, dd = js - p;
+                        const int i0 = max(max(p - FL, 0), -dd), i1 = min(min(p + KP + FL, r.L), G - dd), n = i1 - i0;
+                        const int wi = i0 >> 4, sh = 2 * (i0 & 15);
+                        const uint32_t r0 = sw[wi * VT], r1 = sw[(wi + 1) * VT], r2 = sw[(wi + 2) * VT];
+                        const unsigned long long rb = (unsigned long long)__funnelshift_r(r0, r1, sh) |
+                                                      ((unsigned long long)__funnelshift_r(r1, r2, sh) << 32);
+                        const unsigned long long x = rb ^ packed_window(s ? apk1 : apk0, i0 + dd);
+                        unsigned long long ne = (x | (x >> 1)) & 0x5555555555555555ull;   // 1 = bases differ
+                        ne |= 0x5555555555555555ull << (2 * n);                             // past the overlap
+                        const int a = p - i0;
+                        const unsigned long long lm = ne & ((1ull << (2 * a)) - 1ull), rm = ne >> (2 * (a + KP));
+                        run += lm ? a - 1 - ((63 - __clzll((long long)lm)) >> 1) : a;
+                        run += (__ffsll((long long)rm) - 1) >> 1;                           // rm != 0: n < 32
+                    } else {
+                        const int qp = s ? r.L - p - KP : p, d = jpos - qp;
+                        for (int i = qp - 1; run < K && diag_match(r, s, i, d, anchor, G); i--) run++;
+                        for (int i = qp + KP; run < K && diag_match(r, s, i, d, anchor, G); i++) run++;
+                    }
+                    if (run >= K) { seeded = true; break; }
+                }
+            }
+            keep[c] = seeded ? 1 : 0;
+        }
+        const uint32_t bal = __ballot_sync(FULL, seeded);
+        if (lane == 0 && bal) atomicAdd(&chunk_counts[c0 / CB_PER_BLOCK], __popc(bal));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1118,6 +1238,22 @@ extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, voi
     prof_span(ev, st, ST_COMPACT1);
     prof_mark(&ev, st);
     {
+    if (g_verify_smem) {
+        const size_t vsmem = ((size_t)d->nb2 + (size_t)(lay.words_per_read + 3) * 1024) * 4;
+        static bool vattr[64][2] = {{false}};
+        if (!vattr[d->device & 63][d->kp == 12 ? 0 : 1]) {
+            if (d->kp == 12) AF_CUDA(cudaFuncSetAttribute(k_verify_smem<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            else AF_CUDA(cudaFuncSetAttribute(k_verify_smem<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            vattr[d->device & 63][d->kp == 12 ? 0 : 1] = true;
+        }
+        long long vb = (cand_cap + 1023) / 1024;
+        const unsigned vg = (unsigned)(vb < d->num_sms ? vb : d->num_sms);
+#define AF_VERIFY_SMEM_ARGS (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, \
+        b->nread_ids, b->nmask, (int)b->n_nreads, cand, d_counts, (uint32_t)cand_cap, d->d_filter2, d->fmul2, d->nb2,       \
+        d->d_table, d->tmask, d->d_anchor, d->d_apk[0], d->d_apk[1], d->anchor_has_n, d->G, d->P.k, keep, cc2
+        if (d->kp == 12) k_verify_smem<12><<<vg, 1024, vsmem, st>>>(AF_VERIFY_SMEM_ARGS);
+        else k_verify_smem<13><<<vg, 1024, vsmem, st>>>(AF_VERIFY_SMEM_ARGS);
+    } else {
     long long vthreads = cand_cap < (long long)d->num_sms * 2048 ? cand_cap : (long long)d->num_sms * 2048;
     const unsigned vgrid = (unsigned)((vthreads + 255) / 256);
 #define AF_VERIFY_ARGS (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, \
@@ -1125,6 +1261,7 @@ extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, voi
         d->tmask, d->d_anchor, d->G, d->P.k, keep, cc2
     if (d->kp == 12) k_verify<12><<<vgrid, 256, 0, st>>>(AF_VERIFY_ARGS);
     else k_verify<13><<<vgrid, 256, 0, st>>>(AF_VERIFY_ARGS);
+    }
     }
     k_sel_scatter<<<sg2, CB_THREADS, 0, st>>>(cand, keep, (uint32_t)cand_cap, cc2, cand2, d_counts);
     }
@@ -1166,7 +1303,10 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     d->d_filter = nullptr; d->d_table = nullptr; d->d_anchor = nullptr; d->d_member = nullptr;
     d->d_apk[0] = d->d_apk[1] = nullptr;
     d->anchor_has_n = idx->anchor_has_n;
+    d->fmul2 = idx->fmul2; d->nb2 = idx->nb2; d->d_filter2 = nullptr;
     cudaError_t e = cudaMalloc(&d->d_filter, idx->filter.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_filter2, idx->filter2.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_filter2, idx->filter2.data(), idx->filter2.size() * 4, cudaMemcpyHostToDevice);
     for (int o = 0; o < 2; o++) {
         if (e == cudaSuccess) e = cudaMalloc(&d->d_apk[o], idx->apk[o].size() * 4);
         if (e == cudaSuccess) e = cudaMemcpy(d->d_apk[o], idx->apk[o].data(), idx->apk[o].size() * 4, cudaMemcpyHostToDevice);
@@ -1180,7 +1320,7 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     if (e == cudaSuccess) e = cudaMemcpy(d->d_anchor, idx->codes.data(), idx->codes.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         af_set_error("af_index_upload: %s", cudaGetErrorString(e));
-        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]);
+        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]); cudaFree(d->d_filter2);
         delete d;
         return AF_ERR_CUDA;
     }
@@ -1193,7 +1333,7 @@ extern "C" int af_dev_index_device(const af_dev_index_t *d) { return d ? d->devi
 extern "C" void af_dev_index_free(af_dev_index_t *d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]);
+    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]); cudaFree(d->d_filter2);
     delete d;
 }
 
