@@ -25,6 +25,9 @@
 #include "af_common.h"
 
 #define FULL 0xFFFFFFFFu
+#ifndef AF_SCAN_BOUND
+#define AF_SCAN_BOUND 768   // __launch_bounds__ of the seed scan (register cap 65536 / bound); launched with <= 768 threads
+#endif
 
 static std::atomic<long long> g_launches{0};
 extern "C" int64_t af_kernel_launches(void) { return (int64_t)g_launches.load(); }
@@ -262,7 +265,7 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
 template <int W, int KP>
 static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
                             uint32_t *cc, cudaStream_t st) {
-    return launch_scan<W, KP, 768, true>(d, b, n_tiles, nprobe, flags, cc, st);
+    return launch_scan<W, KP, AF_SCAN_BOUND, true>(d, b, n_tiles, nprobe, flags, cc, st);
 }
 
 #define AF_SCAN_CASE(WW)                                                                       \
