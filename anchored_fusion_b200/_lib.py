@@ -81,6 +81,13 @@ SIGNATURES = {
     "af_pipeline_free": (None, [c_vp]),
     "af_pipeline_run": (ctypes.c_int, [c_vp, P(Batch), c_vp, c_i64, P(c_i64), P(c_i64)]),
     "af_pipeline_launches": (c_i64, [c_vp]),
+    "af_exchange_create": (ctypes.c_int, [ctypes.c_int, c_i32, c_i32, c_i32, c_i64, P(c_vp)]),
+    "af_exchange_free": (None, [c_vp]),
+    "af_exchange_handle": (ctypes.c_int, [c_vp, c_vp]),
+    "af_exchange_connect": (ctypes.c_int, [c_vp, c_vp]),
+    "af_exchange_reset": (ctypes.c_int, [c_vp, c_vp]),
+    "af_anchor_batch_exchange": (ctypes.c_int, [c_vp, P(Batch), c_vp, ctypes.c_size_t, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i64, c_vp]),
+    "af_exchange_read": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i64, P(c_i64), P(ctypes.c_uint32), P(ctypes.c_uint32)]),
     "af_host_alloc": (c_vp, [ctypes.c_size_t]),
     "af_host_free": (None, [c_vp]),
     "af_synth_anchor": (ctypes.c_int, [P(Synth), c_vp]),

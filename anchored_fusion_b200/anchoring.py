@@ -192,10 +192,12 @@ class Anchorer:
         """The side stream of workspace slot `slot` (> 0), created on first use."""
         return self._ws[slot][4]
 
-    def enqueue(self, batch, cand_cap=None, hits_cap=None, stream=None, slot=0):
+    def enqueue(self, batch, cand_cap=None, hits_cap=None, stream=None, slot=0, exchange=None, pair_base=0):
         """Launch the whole path on the current (or given) stream; no host sync.
         `slot` selects an independent workspace so that consecutive batches can be in flight on
         different streams (slot > 0 owns a side stream, used when `stream` is None).
+        exchange: a dist.HitExchange -- the batch's records are also appended (by the hit-compaction
+        kernel itself, NVLink peer stores) to this rank's log `slot` on every rank, tagged `pair_base`.
         Returns (hits tensor [cap,4] int32 raw records, counts tensor)."""
         torch = self.torch
         n = batch.n_pairs
@@ -204,8 +206,13 @@ class Anchorer:
         ws, hits, counts, side = self._workspace(n, cand_cap, hits_cap, slot)
         st = stream if stream is not None else (side if side is not None else torch.cuda.current_stream(self.dev))
         cb = batch.c_struct()
-        check(lib().af_anchor_batch(self.dindex._h, ctypes.byref(cb), ws.data_ptr(), ws.numel(), cand_cap,
-                                    hits.data_ptr(), hits_cap, counts.data_ptr(), ctypes.c_void_p(st.cuda_stream)))
+        if exchange is not None:
+            check(lib().af_anchor_batch_exchange(self.dindex._h, ctypes.byref(cb), ws.data_ptr(), ws.numel(), cand_cap,
+                                                 hits.data_ptr(), hits_cap, counts.data_ptr(), exchange._h, slot,
+                                                 int(pair_base), ctypes.c_void_p(st.cuda_stream)))
+        else:
+            check(lib().af_anchor_batch(self.dindex._h, ctypes.byref(cb), ws.data_ptr(), ws.numel(), cand_cap,
+                                        hits.data_ptr(), hits_cap, counts.data_ptr(), ctypes.c_void_p(st.cuda_stream)))
         return hits, counts
 
     def anchor(self, batch, cand_cap=None, hits_cap=None):

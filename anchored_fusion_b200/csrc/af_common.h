@@ -240,3 +240,27 @@ static inline uint8_t af_code_of(char c) {
         default: return 4;
     }
 }
+
+// ---- multi-GPU hit exchange (af_exchange.cu; the appending kernel is k_hit_scatter) --------
+static const int AF_LOG_HEADER_BYTES = 128;
+struct af_log_header { unsigned long long tail; uint32_t status, n_batches; };
+// what k_hit_scatter needs to append one batch to log (rank, slot) on every rank; by value
+struct af_sink {
+    int32_t world;
+    uint32_t log_cap;                // records per region, markers included
+    unsigned long long *state;       // writer side, local: [0] tail, [1] n_batches<<32 | status
+    uint32_t *ticket;                // local: blocks finished so far
+    unsigned long long pair_base;
+    char *region[AF_MAX_PEERS];      // region (rank, slot) inside each rank's buffer (own rank: local pointer)
+};
+struct af_exchange {
+    int device, rank, world, n_slots;
+    int64_t log_cap;
+    size_t region_bytes, total_bytes;
+    char *local;                     // world x n_slots regions
+    char *peer[AF_MAX_PEERS];        // peer[r] = rank r's buffer mapped here (peer[rank] = local)
+    unsigned long long *state;       // n_slots x 2
+    uint32_t *tickets;               // n_slots
+    bool connected;
+};
+int af_exchange_sink(af_exchange *ex, int slot, int64_t pair_base, af_sink *out);

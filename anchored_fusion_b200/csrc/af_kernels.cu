@@ -411,11 +411,17 @@ k_sel_scatter(const uint32_t *__restrict__ items, const uint8_t *__restrict__ ke
 }
 
 // result slots of k_extend with m_len != 0 -> hit list; total -> counts[AF_CNT_HITS]
+template <bool SINK>
 __global__ void __launch_bounds__(CB_THREADS)
 k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cap, const uint32_t *__restrict__ chunk_counts,
-              uint4 *__restrict__ hits, uint32_t hits_cap, uint32_t *counts) {
+              uint4 *__restrict__ hits, uint32_t hits_cap, uint32_t *counts, const af_sink sink) {
     __shared__ uint32_t sm[9];
     const uint32_t n = min(counts[AF_CNT_SEEDED], cap), n_chunks = (n + CB_PER_BLOCK - 1) / CB_PER_BLOCK;
+    // SINK: this batch's records also go to log (rank, slot) on every rank, after one marker record at
+    // the log's tail.  The tail only moves when the last block of this launch retires (below), and
+    // launches on one slot are stream-ordered, so every block reads the same value here.
+    const unsigned long long tail0 = SINK ? *(volatile unsigned long long *)sink.state : 0ull;
+    bool over = false, over_log = false;
     for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const uint32_t mine = chunk_counts[chunk];
         if (mine == 0) continue;
@@ -430,11 +436,54 @@ k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cap, const uint32_t *__r
             c += (v[i].z >> 16) != 0;   // m_len
         }
         uint32_t off = base + block_excl_scan(c, sm);
-        bool over = false;
 #pragma unroll
         for (int i = 0; i < CB_ITEMS; i++)
-            if ((v[i].z >> 16) != 0) { if (off < hits_cap) hits[off] = v[i]; else over = true; off++; }
-        if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
+            if ((v[i].z >> 16) != 0) {
+                if (off < hits_cap) hits[off] = v[i]; else over = true;
+                if (SINK) {
+                    const unsigned long long at = tail0 + 1 + off;
+                    if (at < sink.log_cap) {
+                        for (int r = 0; r < sink.world; r++)    // 16-byte stores, local HBM and NVLink peers alike
+                            ((uint4 *)(sink.region[r] + AF_LOG_HEADER_BYTES))[at] = v[i];
+                    } else over_log = true;
+                }
+                off++;
+            }
+    }
+    if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
+    if (SINK) {
+        if (over_log) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_LOG_OVERFLOW);
+        // last block to retire: marker, new tail, headers on every rank.  No waiting on anything.
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t t = atomicAdd(sink.ticket, 1u);
+            if (t == gridDim.x - 1) {
+                __threadfence();
+                const uint32_t total = *(volatile uint32_t *)&counts[AF_CNT_HITS];
+                uint32_t status = (uint32_t)(sink.state[1] & 0xFFFFFFFFull) | (*(volatile uint32_t *)&counts[AF_CNT_STATUS] & AF_STATUS_LOG_OVERFLOW);
+                const uint32_t batches = (uint32_t)(sink.state[1] >> 32) + 1;
+                unsigned long long tail = tail0;
+                if (tail0 < sink.log_cap) {
+                    const uint4 marker = make_uint4(AF_LOG_MARKER, (uint32_t)sink.pair_base, (uint32_t)(sink.pair_base >> 32), total);
+                    for (int r = 0; r < sink.world; r++) ((uint4 *)(sink.region[r] + AF_LOG_HEADER_BYTES))[tail0] = marker;
+                    tail = tail0 + 1 + total;
+                    if (tail > sink.log_cap) tail = sink.log_cap;
+                } else {
+                    status |= AF_STATUS_LOG_OVERFLOW;
+                    atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_LOG_OVERFLOW);
+                }
+                __threadfence_system();
+                for (int r = 0; r < sink.world; r++) {
+                    af_log_header *h = (af_log_header *)sink.region[r];
+                    h->status = status; h->n_batches = batches; h->tail = tail;
+                }
+                sink.state[0] = tail;
+                sink.state[1] = ((unsigned long long)batches << 32) | status;
+                *sink.ticket = 0;
+                __threadfence_system();
+            }
+        }
     }
 }
 
@@ -1186,8 +1235,9 @@ extern "C" size_t af_workspace_bytes(int64_t n_pairs, int64_t cand_cap) {
     return ws_layout(n_pairs, cand_cap).total + 256;
 }
 
-extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, void *workspace, size_t workspace_bytes,
-                               int64_t cand_cap, af_hit_t *d_hits, int64_t hits_cap, uint32_t *d_counts, void *stream) {
+static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void *workspace, size_t workspace_bytes,
+                             int64_t cand_cap, af_hit_t *d_hits, int64_t hits_cap, uint32_t *d_counts, const af_sink *sink,
+                             void *stream) {
     af_layout_t lay;
     int rc = batch_check(d, b, &lay);
     if (rc) return rc;
@@ -1280,11 +1330,29 @@ extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, voi
                                          d->stride, P, slots, cc3);
     prof_span(ev, st, ST_EXTEND);
     prof_mark(&ev, st);
-    k_hit_scatter<<<sg2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, cc3, (uint4 *)d_hits, (uint32_t)hits_cap, d_counts);
+    if (sink) k_hit_scatter<true><<<sg2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, cc3, (uint4 *)d_hits, (uint32_t)hits_cap, d_counts, *sink);
+    else k_hit_scatter<false><<<sg2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, cc3, (uint4 *)d_hits, (uint32_t)hits_cap, d_counts, af_sink());
     prof_span(ev, st, ST_COMPACT2);
     g_launches += 5;
     AF_CUDA(cudaGetLastError());
     return AF_OK;
+}
+
+extern "C" int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *b, void *workspace, size_t workspace_bytes,
+                               int64_t cand_cap, af_hit_t *d_hits, int64_t hits_cap, uint32_t *d_counts, void *stream) {
+    return anchor_batch_impl(d, b, workspace, workspace_bytes, cand_cap, d_hits, hits_cap, d_counts, nullptr, stream);
+}
+
+// The same path with the hit exchange fused into its last kernel: k_hit_scatter<true> stores each record
+// into this rank's log on every GPU of the job (NVLink peer stores), see af_exchange.cu.
+extern "C" int af_anchor_batch_exchange(const af_dev_index_t *d, const af_batch_t *b, void *workspace, size_t workspace_bytes,
+                                        int64_t cand_cap, af_hit_t *d_hits, int64_t hits_cap, uint32_t *d_counts,
+                                        af_exchange_t *ex, int32_t slot, int64_t pair_base, void *stream) {
+    af_sink sink;
+    int rc = af_exchange_sink(ex, slot, pair_base, &sink);
+    if (rc) return rc;
+    if (d && ex->device != d->device) { af_set_error("af_anchor_batch_exchange: exchange lives on device %d, index on %d", ex->device, d->device); return AF_ERR_ARG; }
+    return anchor_batch_impl(d, b, workspace, workspace_bytes, cand_cap, d_hits, hits_cap, d_counts, &sink, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -7,8 +7,10 @@
 A step = one pass of the hot path (seed scan -> compaction -> verify/extend -> compaction)
 over one batch of synthetic 2x150 bp pairs resident in HBM (BASELINE.json configs[1]:
 10M pairs against a 6 783 bp anchored CDS cut from a random 10 Mbp reference).  Under torchrun
-every rank owns its own 10M-pair shard (weak scaling) and the ranks' hit lists are gathered
-with one NCCL all-gather per step.  See DESIGN.md "Measurement".
+every rank owns its own 10M-pair shard (weak scaling) and every rank receives all ranks' hit
+lists: by default the hit-compaction kernel stores them into a log on every GPU over NVLink
+peer memory (--exchange p2p), alternatively one NCCL all-gather per step (--exchange nccl).
+See DESIGN.md "Measurement".
 """
 import argparse
 import ctypes
@@ -43,7 +45,7 @@ def config_dict(args, n_gpus):
                         "reference (seeded generator, %d ppm substitutions, %d ppm fusion fragments)"
                         % (args.pairs, args.read_len, args.anchor_len, args.sub_ppm, args.fusion_ppm),
             "pairs_per_gpu": args.pairs, "read_len": args.read_len, "anchor_len": args.anchor_len,
-            "sharding": "reads x%d, hit lists all-gathered" % n_gpus,
+            "sharding": "reads x%d, hit lists delivered to every rank" % n_gpus,
             "l2_policy": "input per step (%.0f MB) exceeds the 126 MB L2; no flush needed" % (args.pairs * 80 / 1e6)}
 
 
@@ -147,6 +149,9 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=250_000, help="pairs per step of the reference arm")
     ap.add_argument("--gather-cap", type=int, default=0, help="hit records per rank in the per-step all-gather "
                     "(0: sized from a probe pass, 1.25 x the largest per-rank hit count, rounded up to 4096)")
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="N > 1: how the ranks' hit lists reach every rank -- p2p: the hit-compaction kernel stores them "
+                         "into every GPU's log over NVLink peer memory; nccl: one all-gather per step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -193,6 +198,11 @@ def main():
     profiling = [False]
     n_slots = max(1, args.slots)
     cand_cap = args.cand_cap or 2 * n
+    exchange = None
+    if world > 1 and args.exchange == "p2p" and not args.graphs:
+        # a log region takes the batches of one slot of one rank for a whole timed region
+        exchange = afdist.HitExchange(rank, world, n_slots, (max(args.warmup, args.steps) + 1) * (gather_cap + 1), dev)
+    step_base = [0]
     streams = []
     for sl in range(n_slots):               # slot 0 runs on the current stream, the others own side streams
         eng.enqueue(batch, cand_cap=cand_cap, slot=sl)
@@ -220,6 +230,10 @@ def main():
             with torch.cuda.stream(streams[sl]):
                 graphs[sl].replay()
             hits, counts = eng.counts_and_hits(sl)[2:], eng.counts_and_hits(sl)[:2].view(-1)
+        elif exchange is not None:
+            # the records reach every rank from inside the last kernel of the path; nothing else to launch
+            return eng.enqueue(batch, cand_cap=cand_cap, slot=sl, exchange=exchange,
+                               pair_base=((step_base[0] + i) * world + rank) * n)
         else:
             hits, counts = eng.enqueue(batch, cand_cap=cand_cap, slot=sl)
         if world > 1:
@@ -248,6 +262,8 @@ def main():
 
     out = run_steps(args.warmup)
     barrier()
+    if exchange is not None:
+        exchange.reset()
     stats_counts = eng.counts_and_hits(0)[:2].reshape(-1).cpu().numpy().view(np.uint32)
     sampler = ClockSampler(local)
     sampler.start()
@@ -267,6 +283,30 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
+    exchange_info = None
+    if world > 1:
+        exchange_info = {"kind": "nccl all_gather_into_tensor per step", "records_cap_per_rank": gather_cap}
+    if exchange is not None:
+        # outside the clock: every rank checks that its logs hold the K timed batches of every rank and
+        # that each equals what one NCCL all-gather of the ranks' hit lists delivers
+        got = exchange.collect()
+        with torch.cuda.stream(streams[0]):
+            eng.enqueue(batch, cand_cap=cand_cap, slot=0)
+            ac, ah = afdist.gather_hits_tensor(eng.counts_and_hits(0), gather_cap)
+        torch.cuda.synchronize()
+        ac, ah = ac.cpu().numpy(), ah.cpu().numpy()
+        for r in range(world):
+            mine = [(b, h) for (src, b, h) in got if src == r]
+            want_bases = sorted((i * world + r) * n for i in range(args.steps))
+            assert sorted(b for b, _ in mine) == want_bases, "rank %d: log of rank %d holds batches %s" % (rank, r, [b for b, _ in mine][:4])
+            ref = np.ascontiguousarray(ah[r, : ac[r]]).view(np.uint8).reshape(-1).view(af.HIT_DTYPE)
+            for _, h in mine:
+                assert len(h) == len(ref) and (h.view(np.uint8) == ref.view(np.uint8)).all(), "rank %d: log of rank %d differs from the all-gather" % (rank, r)
+        exchange_info = {"kind": "p2p: k_hit_scatter stores each record into every rank's log (NVLink peer memory, CUDA IPC)",
+                         "validated": "each rank's logs hold the %d timed batches of all %d ranks, byte-equal to an NCCL all-gather" % (args.steps, world),
+                         "records_per_rank_per_step": int(ac[rank]), "log_records_per_region": exchange.log_cap}
+        step_base[0] = args.steps
+        exchange.reset()
 
     # Second timed region, the same K steps on ONE stream, with CUDA events recorded on that stream
     # around every stage (af_profile_*): clean per-kernel durations for the roofline.  (In the
@@ -354,11 +394,14 @@ def main():
         os.write(real_stdout, (json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": dict(config_dict(args, world), streams=n_slots, cuda_graphs=bool(args.graphs)), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                          "config": dict(config_dict(args, world), streams=n_slots, cuda_graphs=bool(args.graphs), exchange=exchange_info), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                           "gpu_launches": int(launches), "clocks": clocks,
                           "per_step": {"flagged_reads": int(stats_counts[0]), "seeded_reads": int(stats_counts[3]),
                                        "anchored_reads": nh,
                                        "kp": index.info.kp, "stride": index.info.stride}}) + "\n").encode())
+    if exchange is not None:
+        barrier()
+        exchange.close()
     if world > 1:
         dist.destroy_process_group()
 

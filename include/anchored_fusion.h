@@ -115,6 +115,7 @@ enum { AF_CNT_FLAGGED = 0, AF_CNT_HITS = 1, AF_CNT_STATUS = 2, AF_CNT_SEEDED = 3
 /* bits of counts[AF_CNT_STATUS] */
 #define AF_STATUS_CAND_OVERFLOW 1u
 #define AF_STATUS_HIT_OVERFLOW 2u
+#define AF_STATUS_LOG_OVERFLOW 4u /* a hit-exchange log region filled up (af_anchor_batch_exchange) */
 
 const char *af_last_error(void);
 int af_abi_version(void);
@@ -192,6 +193,43 @@ int af_pipeline_run(af_pipeline_t *p, const af_batch_t *host_batch, af_hit_t *h_
 int64_t af_pipeline_launches(const af_pipeline_t *p); /* kernels launched so far */
 void *af_host_alloc(size_t bytes);                    /* cudaHostAlloc (pinned) */
 void af_host_free(void *p);
+
+/* ---- multi-GPU hit exchange over NVLink peer memory ---------------------- *
+ * One process per GPU, reads sharded over the ranks; the only exchange on the path is the small
+ * list of hit records.  (The reference has no counterpart: it is one process, its "gather" is
+ * `samtools view` writing one BAM, Anchored_Fusion.py:194.)  Instead of a collective after the
+ * kernels, the last kernel of the path (hit compaction) stores every record straight into a
+ * log region on EVERY rank -- plain 16-byte stores through NVLink into buffers opened with CUDA
+ * IPC -- so there is no per-batch rendezvous between the ranks and nothing for NCCL to launch.
+ *
+ * Each rank's buffer holds world x n_slots regions; region (src, slot) is written only by rank
+ * `src` from its stream of workspace slot `slot`:
+ *     128-byte header { uint64 tail; uint32 status; uint32 n_batches; }
+ *     af_hit_t log[log_cap]: per batch one marker { read_id = 0xFFFFFFFF, pos / clip_l|m_len =
+ *     low / high 32 bits of pair_base, score_strand word = record count } then its records
+ *     (ordered by read_id, read_ids relative to the batch).
+ * A consumer reads after every rank has synchronised its streams and the ranks have met at a
+ * host barrier (no device-side waiting anywhere). */
+typedef struct af_exchange af_exchange_t;
+#define AF_IPC_HANDLE_BYTES 64
+#define AF_MAX_PEERS 16
+#define AF_LOG_MARKER 0xFFFFFFFFu
+int af_exchange_create(int device, int32_t rank, int32_t world, int32_t n_slots, int64_t log_cap, af_exchange_t **out);
+void af_exchange_free(af_exchange_t *ex);
+/* this rank's buffer as an IPC handle, to be passed to the other ranks by any host channel */
+int af_exchange_handle(const af_exchange_t *ex, void *handle_out /* AF_IPC_HANDLE_BYTES */);
+/* handles: world x AF_IPC_HANDLE_BYTES, entry `rank` is ignored; opens the peers' buffers */
+int af_exchange_connect(af_exchange_t *ex, const void *handles);
+/* empty this rank's logs on every rank (stream-ordered; call between host barriers) */
+int af_exchange_reset(af_exchange_t *ex, void *stream);
+/* af_anchor_batch + append of the batch's records to log (rank, slot) on every rank.  `stream`
+ * must be the same for all calls with one `slot`.  pair_base: job-wide index of the batch's first pair. */
+int af_anchor_batch_exchange(const af_dev_index_t *d, const af_batch_t *batch, void *workspace, size_t workspace_bytes,
+                             int64_t cand_cap, af_hit_t *d_hits, int64_t hits_cap, uint32_t *d_counts,
+                             af_exchange_t *ex, int32_t slot, int64_t pair_base, void *stream);
+/* synchronous copy of log (src_rank, slot) of THIS rank's buffer to the host: markers + records */
+int af_exchange_read(const af_exchange_t *ex, int32_t src_rank, int32_t slot, af_hit_t *h_out, int64_t cap,
+                     int64_t *n_out, uint32_t *status_out, uint32_t *n_batches_out);
 
 /* ---- seeded synthetic reads (measurement) --------------------------------- */
 typedef struct {
