@@ -248,8 +248,8 @@ struct af_log_header { unsigned long long tail; uint32_t status, n_batches; };
 struct af_sink {
     int32_t world;
     uint32_t log_cap;                // records per region, markers included
-    unsigned long long *state;       // writer side, local: [0] tail, [1] n_batches<<32 | status
-    uint32_t *ticket;                // local: blocks finished so far
+    unsigned long long *state;       // writer side, local: [0..1] tail by batch parity, [2..3] n_batches<<32 | status
+    uint32_t seq;                    // batches appended to this log since the last reset
     unsigned long long pair_base;
     char *region[AF_MAX_PEERS];      // region (rank, slot) inside each rank's buffer (own rank: local pointer)
 };
@@ -259,8 +259,8 @@ struct af_exchange {
     size_t region_bytes, total_bytes;
     char *local;                     // world x n_slots regions
     char *peer[AF_MAX_PEERS];        // peer[r] = rank r's buffer mapped here (peer[rank] = local)
-    unsigned long long *state;       // n_slots x 2
-    uint32_t *tickets;               // n_slots
+    unsigned long long *state;       // n_slots x 4
+    uint32_t seq[64];                // per slot: batches appended since the last reset (host side)
     bool connected;
 };
 int af_exchange_sink(af_exchange *ex, int slot, int64_t pair_base, af_sink *out);

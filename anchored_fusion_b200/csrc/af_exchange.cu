@@ -39,19 +39,18 @@ extern "C" int af_exchange_create(int device, int32_t rank, int32_t world, int32
     ex->device = device; ex->rank = rank; ex->world = world; ex->n_slots = n_slots; ex->log_cap = log_cap;
     ex->region_bytes = ((size_t)AF_LOG_HEADER_BYTES + (size_t)log_cap * sizeof(af_hit_t) + 255) & ~(size_t)255;
     ex->total_bytes = ex->region_bytes * (size_t)world * (size_t)n_slots;
-    ex->local = nullptr; ex->state = nullptr; ex->tickets = nullptr; ex->connected = world == 1;
+    ex->local = nullptr; ex->state = nullptr; ex->connected = world == 1;
+    memset(ex->seq, 0, sizeof ex->seq);
     for (int r = 0; r < AF_MAX_PEERS; r++) ex->peer[r] = nullptr;
     cudaError_t e = cudaMalloc((void **)&ex->local, ex->total_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&ex->state, (size_t)n_slots * 2 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&ex->tickets, (size_t)n_slots * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(ex->state, 0, (size_t)n_slots * 2 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(ex->tickets, 0, (size_t)n_slots * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ex->state, (size_t)n_slots * 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ex->state, 0, (size_t)n_slots * 4 * sizeof(unsigned long long));
     // only the headers need to start out zero
     for (int i = 0; e == cudaSuccess && i < world * n_slots; i++) e = cudaMemset(ex->local + (size_t)i * ex->region_bytes, 0, AF_LOG_HEADER_BYTES);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         af_set_error("af_exchange_create: %s", cudaGetErrorString(e));
-        cudaFree(ex->local); cudaFree(ex->state); cudaFree(ex->tickets);
+        cudaFree(ex->local); cudaFree(ex->state);
         delete ex;
         return AF_ERR_CUDA;
     }
@@ -66,7 +65,7 @@ extern "C" void af_exchange_free(af_exchange_t *ex) {
     cudaDeviceSynchronize();
     for (int r = 0; r < ex->world; r++)
         if (r != ex->rank && ex->peer[r]) cudaIpcCloseMemHandle(ex->peer[r]);
-    cudaFree(ex->local); cudaFree(ex->state); cudaFree(ex->tickets);
+    cudaFree(ex->local); cudaFree(ex->state);
     delete ex;
 }
 
@@ -103,8 +102,8 @@ int af_exchange_sink(af_exchange *ex, int slot, int64_t pair_base, af_sink *out)
     if (slot < 0 || slot >= ex->n_slots || pair_base < 0) { af_set_error("hit exchange: slot %d of %d", slot, ex->n_slots); return AF_ERR_ARG; }
     out->world = ex->world;
     out->log_cap = (uint32_t)ex->log_cap;
-    out->state = ex->state + 2 * slot;
-    out->ticket = ex->tickets + slot;
+    out->state = ex->state + 4 * slot;
+    out->seq = ex->seq[slot];
     out->pair_base = (unsigned long long)pair_base;
     for (int r = 0; r < AF_MAX_PEERS; r++) out->region[r] = r < ex->world ? region_of(ex, ex->peer[r], ex->rank, slot) : nullptr;
     return AF_OK;
@@ -118,8 +117,7 @@ __global__ void k_exchange_reset(af_sink s0, int n_slots, size_t region_bytes) {
         af_log_header *h = (af_log_header *)(s0.region[r] + (size_t)slot * region_bytes);
         h->tail = 0; h->status = 0; h->n_batches = 0;
     }
-    if (r == 0) { s0.state[2 * slot] = 0; s0.state[2 * slot + 1] = 0; s0.ticket[slot] = 0; }
-    __threadfence_system();
+    if (r < 4) s0.state[4 * slot + r] = 0;
 }
 
 extern "C" int af_exchange_reset(af_exchange_t *ex, void *stream) {
@@ -129,6 +127,7 @@ extern "C" int af_exchange_reset(af_exchange_t *ex, void *stream) {
     AF_CUDA(cudaSetDevice(ex->device));
     k_exchange_reset<<<ex->n_slots, 32, 0, (cudaStream_t)stream>>>(s0, ex->n_slots, ex->region_bytes);
     AF_CUDA(cudaGetLastError());
+    memset(ex->seq, 0, sizeof ex->seq);
     return AF_OK;
 }
 

@@ -418,10 +418,39 @@ k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cap, const uint32_t *__r
     __shared__ uint32_t sm[9];
     const uint32_t n = min(counts[AF_CNT_SEEDED], cap), n_chunks = (n + CB_PER_BLOCK - 1) / CB_PER_BLOCK;
     // SINK: this batch's records also go to log (rank, slot) on every rank, after one marker record at
-    // the log's tail.  The tail only moves when the last block of this launch retires (below), and
-    // launches on one slot are stream-ordered, so every block reads the same value here.
-    const unsigned long long tail0 = SINK ? *(volatile unsigned long long *)sink.state : 0ull;
-    bool over = false, over_log = false;
+    // the log's tail.  The writer-side tail is double-buffered by batch parity: launch `seq` reads
+    // state[seq & 1] and (block 0, below) writes state[~seq & 1] for the next launch on this slot's
+    // stream, so every block of a launch sees the same tail and nothing waits on anything.
+    const unsigned long long tail0 = SINK ? sink.state[sink.seq & 1u] : 0ull;
+    bool over = false;
+    if (SINK && blockIdx.x == 0) {
+        // marker, new tail and the region headers, up front: the batch's record count is the sum of
+        // the chunk counts k_extend left
+        const uint32_t total = sum_before(chunk_counts, n_chunks, sm);
+        if (threadIdx.x == 0) {
+            const unsigned long long meta = sink.state[2 + (sink.seq & 1u)];
+            uint32_t status = (uint32_t)meta;
+            const uint32_t batches = (uint32_t)(meta >> 32) + 1;
+            unsigned long long tail = tail0;
+            if (tail0 < sink.log_cap) {
+                const uint4 marker = make_uint4(AF_LOG_MARKER, (uint32_t)sink.pair_base, (uint32_t)(sink.pair_base >> 32), total);
+                for (int r = 0; r < sink.world; r++) ((uint4 *)(sink.region[r] + AF_LOG_HEADER_BYTES))[tail0] = marker;
+                tail = tail0 + 1 + total;
+            }
+            if (tail0 >= sink.log_cap || tail > sink.log_cap || total > hits_cap) {
+                if (tail > sink.log_cap) tail = sink.log_cap;
+                status |= AF_STATUS_LOG_OVERFLOW;
+                atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_LOG_OVERFLOW);
+            }
+            for (int r = 0; r < sink.world; r++) {
+                af_log_header *h = (af_log_header *)sink.region[r];
+                h->status = status; h->n_batches = batches; h->tail = tail;
+            }
+            sink.state[(sink.seq & 1u) ^ 1u] = tail;
+            sink.state[2 + ((sink.seq & 1u) ^ 1u)] = ((unsigned long long)batches << 32) | status;
+        }
+        __syncthreads();
+    }
     for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const uint32_t mine = chunk_counts[chunk];
         if (mine == 0) continue;
@@ -438,53 +467,22 @@ k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cap, const uint32_t *__r
         uint32_t off = base + block_excl_scan(c, sm);
 #pragma unroll
         for (int i = 0; i < CB_ITEMS; i++)
-            if ((v[i].z >> 16) != 0) {
-                if (off < hits_cap) hits[off] = v[i]; else over = true;
-                if (SINK) {
-                    const unsigned long long at = tail0 + 1 + off;
-                    if (at < sink.log_cap) {
-                        for (int r = 0; r < sink.world; r++)    // 16-byte stores, local HBM and NVLink peers alike
-                            ((uint4 *)(sink.region[r] + AF_LOG_HEADER_BYTES))[at] = v[i];
-                    } else over_log = true;
-                }
-                off++;
-            }
-    }
-    if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
-    if (SINK) {
-        if (over_log) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_LOG_OVERFLOW);
-        // last block to retire: marker, new tail, headers on every rank.  No waiting on anything.
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t t = atomicAdd(sink.ticket, 1u);
-            if (t == gridDim.x - 1) {
-                __threadfence();
-                const uint32_t total = *(volatile uint32_t *)&counts[AF_CNT_HITS];
-                uint32_t status = (uint32_t)(sink.state[1] & 0xFFFFFFFFull) | (*(volatile uint32_t *)&counts[AF_CNT_STATUS] & AF_STATUS_LOG_OVERFLOW);
-                const uint32_t batches = (uint32_t)(sink.state[1] >> 32) + 1;
-                unsigned long long tail = tail0;
-                if (tail0 < sink.log_cap) {
-                    const uint4 marker = make_uint4(AF_LOG_MARKER, (uint32_t)sink.pair_base, (uint32_t)(sink.pair_base >> 32), total);
-                    for (int r = 0; r < sink.world; r++) ((uint4 *)(sink.region[r] + AF_LOG_HEADER_BYTES))[tail0] = marker;
-                    tail = tail0 + 1 + total;
-                    if (tail > sink.log_cap) tail = sink.log_cap;
-                } else {
-                    status |= AF_STATUS_LOG_OVERFLOW;
-                    atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_LOG_OVERFLOW);
-                }
-                __threadfence_system();
-                for (int r = 0; r < sink.world; r++) {
-                    af_log_header *h = (af_log_header *)sink.region[r];
-                    h->status = status; h->n_batches = batches; h->tail = tail;
-                }
-                sink.state[0] = tail;
-                sink.state[1] = ((unsigned long long)batches << 32) | status;
-                *sink.ticket = 0;
-                __threadfence_system();
+            if ((v[i].z >> 16) != 0) { if (off < hits_cap) hits[off] = v[i]; else over = true; off++; }
+        if (SINK) {
+            // push this chunk's records (now contiguous in hits[base, base + mine)) to every rank's log:
+            // consecutive threads store consecutive records, so a warp's store is 512 contiguous bytes
+            // per destination -- full-size NVLink write packets instead of one packet per record
+            __syncthreads();
+            const uint32_t end = min(base + mine, hits_cap);
+            for (uint32_t j = base + threadIdx.x; j < end; j += CB_THREADS) {
+                const unsigned long long at = tail0 + 1 + j;
+                if (at >= sink.log_cap) break;                 // flagged by block 0
+                const uint4 rec = hits[j];
+                for (int r = 0; r < sink.world; r++) ((uint4 *)(sink.region[r] + AF_LOG_HEADER_BYTES))[at] = rec;
             }
         }
     }
+    if (over) atomicOr(&counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1352,7 +1350,10 @@ extern "C" int af_anchor_batch_exchange(const af_dev_index_t *d, const af_batch_
     int rc = af_exchange_sink(ex, slot, pair_base, &sink);
     if (rc) return rc;
     if (d && ex->device != d->device) { af_set_error("af_anchor_batch_exchange: exchange lives on device %d, index on %d", ex->device, d->device); return AF_ERR_ARG; }
-    return anchor_batch_impl(d, b, workspace, workspace_bytes, cand_cap, d_hits, hits_cap, d_counts, &sink, stream);
+    if (b && b->n_pairs == 0) return anchor_batch_impl(d, b, workspace, workspace_bytes, cand_cap, d_hits, hits_cap, d_counts, nullptr, stream);
+    rc = anchor_batch_impl(d, b, workspace, workspace_bytes, cand_cap, d_hits, hits_cap, d_counts, &sink, stream);
+    if (rc == AF_OK) ex->seq[slot]++;      // the batch parity k_hit_scatter double-buffers the log tail by
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------
