@@ -17,6 +17,25 @@ IPC_HANDLE_BYTES = 64
 STATUS_LOG_OVERFLOW = 4
 
 
+def bind_near_gpu(device_index):
+    """Pin this process to the CPUs NVML reports as local to the GPU (same socket / NUMA node), so that
+    the pinned staging buffers it allocates next are first-touched on that node and the H2D copies of
+    eight ranks do not all cross one socket's memory controller.  Returns the CPU set, or None when
+    NVML cannot tell (then nothing is changed)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%08X:%02X:%02X.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def shard_range(n_pairs, rank, world):
     """Contiguous, tile-aligned share of [0, n_pairs) for `rank`."""
     tiles = (n_pairs + 31) // 32

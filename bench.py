@@ -174,8 +174,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus = None
     if world > 1:
         import torch.distributed as dist
+        cpus = afdist.bind_near_gpu(local)      # host staging buffers on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=dev)
     L = lib()
     if args.scan_threads or args.scan_mode:
@@ -376,7 +378,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": world * n / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(lay.packed_bytes),
                "d2h_bytes_per_step": int(len(h) * 16 + 32 * ((n + (1 << 20) - 1) >> 20)), "ms_per_step": dt * 1e3,
-               "path": "af_pipeline_run: pinned host tiles -> cudaMemcpyAsync -> kernels -> hit list on host"}
+               "path": "af_pipeline_run: pinned host tiles -> cudaMemcpyAsync -> kernels -> hit list on host",
+               "host_cpus_rank0": ("%d CPUs local to the GPU (NVML affinity)" % len(cpus)) if cpus else "unbound"}
         eng.close_pipeline()
         L.af_host_free(hptr)
 

@@ -70,6 +70,136 @@ def run_contact_reads(ref, lines):
         os.remove(path)
 
 
+def run_find_fine_block(ref, lines):
+    """Reference Find_fine_block (functions.py:506) with blat stubbed: captures the FASTA its first
+    loop writes and the spanning_anchored objects it builds."""
+    made, captured = [], {}
+    real_cls, real_system = ref.spanning_anchored, ref.os.system
+
+    class Spy(real_cls):
+        def __init__(self, type_, left_length, right_length, read_name):
+            super().__init__(type_, left_length, right_length, read_name)
+            made.append([type_, int(left_length), int(right_length), read_name])
+
+    def fake_system(cmd):
+        assert cmd.startswith("blat "), cmd
+        parts = cmd.split()
+        captured["fasta"] = open(parts[-2]).read()
+        open(parts[-1], "w").close()
+        return 0
+
+    tmp = tempfile.mkdtemp()
+    f_read = os.path.join(tmp, "reads.sam")
+    with open(f_read, "w") as fh:
+        fh.writelines(lines)
+    ref.spanning_anchored, ref.os.system = Spy, fake_system
+    try:
+        ref.Find_fine_block(f_read, "genome.fa", os.path.join(tmp, "w"), None, [], {})
+    finally:
+        ref.spanning_anchored, ref.os.system = real_cls, real_system
+    return {"lines": lines, "candidates": made, "fasta": captured["fasta"]}
+
+
+def random_cigar(rng, total, kinds):
+    """A CIGAR over `total` query bases built from the op kinds given (M always present)."""
+    kind = rng.choice(kinds)
+    if kind == "M":
+        return "%dM" % total
+    if kind in ("SM", "HM"):
+        c = rng.randint(1, total - 20)
+        return "%d%s%dM" % (c, kind[0], total - c)
+    if kind in ("MS", "MH"):
+        c = rng.randint(1, total - 20)
+        return "%dM%d%s" % (total - c, c, kind[1])
+    if kind == "SMS":
+        a, b = rng.randint(1, 30), rng.randint(1, 30)
+        return "%dS%dM%dS" % (a, total - a - b, b)
+    if kind == "HMH":
+        a, b = rng.randint(1, 30), rng.randint(1, 30)
+        return "%dH%dM%dH" % (a, total - a - b, b)
+    if kind == "MDM":
+        a = rng.randint(10, total - 10)
+        return "%dM%dD%dM" % (a, rng.randint(1, 5), total - a)
+    if kind == "MIM":
+        a, i = rng.randint(10, total - 20), rng.randint(1, 4)
+        return "%dM%dI%dM" % (a, i, total - a - i)
+    if kind == "MNM":
+        a = rng.randint(10, total - 10)
+        return "%dM%dN%dM" % (a, rng.randint(50, 5000), total - a)
+    if kind == "SMDMS":
+        a, b, m = rng.randint(1, 20), rng.randint(1, 20), rng.randint(10, 30)
+        return "%dS%dM2D%dM%dS" % (a, m, total - a - b - m, b)
+    raise ValueError(kind)
+
+
+def run_del_too_many(ref, rng, case):
+    """Reference del_too_many_reads (functions.py:705) with `samtools view` replaced by prepared
+    anchored records and the genome `bwa mem` by a prepared SAM text: pins the 2-op selection
+    (the FASTA handed to bwa) and the contiguity decision (out_sam) for that text."""
+    L = 101
+    anchored = []
+    for k in range(60):
+        seq = "".join(rng.choice("ACGT") for _ in range(L))
+        cg = random_cigar(rng, L, ["SM", "MS", "SM", "MS", "M", "SMS", "HM", "MDM"])
+        flag = rng.choice([0, 16, 83, 99, 147, 163])
+        anchored.append("\t".join(["q%d_%d" % (case, k), str(flag), "BCR", str(rng.randint(1, 6000)), "60", cg, "=",
+                                   str(rng.randint(1, 6000)), "0", seq, "2" * L]))
+    captured = {}
+    genome = []
+    real_system, real_popen = ref.os.system, ref.os.popen
+
+    class FakePipe:
+        def __init__(self, text):
+            self.text = text
+
+        def read(self):
+            return self.text
+
+    def fake_popen(cmd):
+        assert cmd.startswith("samtools view "), cmd
+        return FakePipe("\n".join(anchored) + "\n")
+
+    def fake_system(cmd):
+        assert cmd.startswith("bwa mem "), cmd
+        left, tmp_sam = cmd.split(" > ")
+        tmp_fa = left.split()[-1]
+        captured["fasta"] = open(tmp_fa).read()
+        fa = captured["fasta"].split("\n")
+        if case != 5:
+            genome.append("@SQ\tSN:chr9\tLN:141213431\n")
+            genome.append("@PG\tID:bwa\tPN:bwa\n")
+        for tag, seq in zip(fa[0::2], fa[1::2]):
+            tag = tag[1:]
+            n_lines = rng.choice([1, 1, 2, 3])
+            for j in range(n_lines):
+                flag = rng.choice([0, 16, 0, 16, 2048, 2064, 256, 272])
+                if j == 0 and rng.random() < 0.15:
+                    genome.append("\t".join([tag, "4", "*", "0", "0", "*", "*", "0", "0", seq, "*"]) + "\n")
+                    break
+                cg = random_cigar(rng, len(seq), ["M", "SM", "MS", "SM", "MS", "HM", "MH", "SMS", "HMH", "MDM", "MIM", "MNM", "SMDMS"])
+                s = revcomp(seq) if flag & 16 else seq
+                if "H" in cg:      # hard clips are not part of SEQ
+                    ops = [(int(n), o) for n, o in __import__("re").findall(r"(\d+)([A-Z])", cg)]
+                    lead = ops[0][0] if ops[0][1] == "H" else 0
+                    tail = ops[-1][0] if ops[-1][1] == "H" else 0
+                    s = s[lead: len(s) - tail]
+                genome.append("\t".join([tag, str(flag), "chr9", str(rng.randint(1, 10 ** 8)), str(rng.choice([0, 60])), cg,
+                                         "*", "0", "0", s, "*"]) + "\n")
+        if case == 4:
+            genome.append("@CO\ta trailing header line: the last read is then never flushed\n")
+        open(tmp_sam, "w").writelines(genome)
+        return 0
+
+    tmp = tempfile.mkdtemp()
+    out_sam = os.path.join(tmp, "out.sam")
+    ref.os.system, ref.os.popen = fake_system, fake_popen
+    try:
+        ref.del_too_many_reads("anchored.bam", out_sam, os.path.join(tmp, "w"), "genome.fa", "1")
+    finally:
+        ref.os.system, ref.os.popen = real_system, real_popen
+    return {"anchored": anchored, "fasta": captured["fasta"], "genome_sam": genome, "out_sam": open(out_sam).read()}
+
+
 def main():
     ref = load_reference_functions()
     # ---- bundled sample -------------------------------------------------------------------
@@ -149,6 +279,11 @@ def main():
             k += 1
     lines = [l for _, l in sorted(lines, key=lambda t: t[0])]
     out["contact_reads"].append({"name": "synthetic_junctions", "lines": lines, "out": run_contact_reads(ref, lines)})
+
+    # ---- rows 8(f)-2 / 8(f)-3: the loops right behind the path, run in the REFERENCE with its two
+    #      shell-outs replaced (blat -> empty .psl, genome bwa mem -> a prepared SAM text) -------------
+    out["find_fine_block_first_loop"] = run_find_fine_block(ref, out["contact_reads"][2]["lines"] + hand)
+    out["del_too_many_reads"] = [run_del_too_many(ref, rng, case) for case in range(6)]
 
     with open(os.path.join(HERE, "ref_functions.json"), "w") as fh:
         json.dump(out, fh, indent=0)

@@ -79,3 +79,47 @@ def test_two_op_records(golden):
     heads = [h for h, _ in two_op_records(case["lines"])]
     assert "r1$BCR$100$40S61M" in heads and "r3$BCR$100$10S91M" in heads
     assert not any(h.startswith("r8$") for h in heads)      # 101M has one op
+
+
+def test_fine_block_first_loop_matches_reference(golden, tmp_path):
+    """the spanning_anchored objects and the FASTA that Find_fine_block's first loop
+    (functions.py:513-529) makes of the pseudo-SAM records -- reference run with blat stubbed."""
+    from anchored_fusion_b200.functions import fine_block_candidates, fine_block_candidates_from_file
+    case = golden["find_fine_block_first_loop"]
+    rows = [l.split("\t") for l in case["lines"]]
+    cands, fasta = fine_block_candidates((a[0], a[2], a[3], a[5], a[9]) for a in rows)
+    assert [[c.type_, c.left_length, c.right_length, c.read_name] for c in cands] == case["candidates"]
+    assert fasta == case["fasta"]
+    p = tmp_path / "split.sam"
+    p.write_text("".join(case["lines"]))
+    again = fine_block_candidates_from_file(str(p), str(tmp_path / "w"))
+    assert len(again) == len(cands) and (tmp_path / "w_prb_spanning.fa").read_text() == case["fasta"]
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_del_too_many_reads_matches_reference(golden, tmp_path, case):
+    """SURVEY 8(a8) + 8(f)-3: the 2-op selection handed to the genome aligner and the contiguity
+    decision on a prepared genome SAM text (flags 0/16/256/2048, H/S clips, D/I/N, unmapped, header
+    lines first and last) -- reference run with samtools / bwa replaced by the same texts."""
+    from anchored_fusion_b200.functions import contiguity_filter, del_too_many_reads, two_op_records
+    g = golden["del_too_many_reads"][case]
+    fasta = "".join(">%s\n%s\n" % (tag, seq) for tag, seq in two_op_records(g["anchored"]))
+    assert fasta == g["fasta"]
+    assert "".join(contiguity_filter(g["genome_sam"])) == g["out_sam"]
+    # the whole function, same signature, files and clean-up
+    f_read = tmp_path / "anchored.sam"
+    f_read.write_text("@HD\tVN:1.6\n" + "\n".join(g["anchored"]) + "\n")
+    out_sam = tmp_path / "out.sam"
+    del_too_many_reads(str(f_read), str(out_sam), str(tmp_path / "w"), "genome.fa", "1", genome_sam=g["genome_sam"])
+    assert out_sam.read_text() == g["out_sam"]
+    assert not (tmp_path / "w_del_tmp.fa").exists() and not (tmp_path / "w_del_tmp.sam").exists()
+
+
+def test_del_too_many_reads_needs_an_aligner(tmp_path, monkeypatch):
+    from anchored_fusion_b200.functions import del_too_many_reads
+    monkeypatch.setenv("PATH", str(tmp_path))
+    f_read = tmp_path / "anchored.sam"
+    f_read.write_text("r\t0\tBCR\t10\t60\t40S61M\t=\t1\t0\t" + "A" * 101 + "\t*\n")
+    with pytest.raises(RuntimeError):
+        del_too_many_reads(str(f_read), str(tmp_path / "o.sam"), str(tmp_path / "w"), "genome.fa", "1")
+    assert not (tmp_path / "w_del_tmp.fa").exists()
