@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--fusion-ppm", type=int, default=0)
     ap.add_argument("--kp", type=int, default=0)
     ap.add_argument("--scan-threads", type=int, default=0)
-    ap.add_argument("--scan-mode", type=int, default=0)
+    ap.add_argument("--scan-mode", type=str, default="0", help="af_seed_scan_config mode(s), comma separated")
     ap.add_argument("--slots", type=int, default=2, help="workspace slots / streams consecutive steps alternate between")
     ap.add_argument("--graphs", type=int, default=0, help="1: replay one CUDA graph per slot in the throughput region")
     ap.add_argument("--cand-cap", type=int, default=0, help="candidate capacity per batch (default 2 x pairs: every read)")
@@ -180,9 +180,12 @@ def main():
         cpus = afdist.bind_near_gpu(local)      # host staging buffers on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=dev)
     L = lib()
-    if args.scan_threads or args.scan_mode:
+    modes = [int(m) for m in str(args.scan_mode).split(",") if m and int(m)]
+    if args.scan_threads or modes:
         from anchored_fusion_b200._lib import check
-        check(L.af_seed_scan_config(args.scan_threads, args.scan_mode))
+        check(L.af_seed_scan_config(args.scan_threads, 0))
+        for m in modes:
+            check(L.af_seed_scan_config(0, m))
 
     spec = workload(args)
     index = af.AnchorIndex(af.synth_anchor(spec), kp=args.kp)
