@@ -1084,12 +1084,18 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
          const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
          const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts, uint32_t cand_cap,
          const uint2 *__restrict__ table, uint32_t tmask, const uint8_t *__restrict__ anchor, int G, int KP, int S,
-         ExtParams P, uint4 *__restrict__ slots, uint32_t *__restrict__ chunk_counts) {
+         ExtParams P, uint4 *__restrict__ slots, uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ next_read) {
     const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t ncand = min(counts[AF_CNT_SEEDED], cand_cap);
     const uint32_t kpmask = (1u << (2 * KP)) - 1u;
-    for (uint32_t c = gw; c < ncand; c += nw_total) {
+    // reads differ a lot in cost (number of diagonals, extension length): warps take the next read from a
+    // counter instead of a fixed stride, so no SM is left with the long tail (ncu: active cycles 44k avg /
+    // 62k max per SM with the static assignment)
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(next_read, 1u);
+        c = __shfl_sync(FULL, c, 0);
+        if (c >= ncand) break;
         const uint32_t rid = cand[c];
         const uint32_t pair = rid >> 1, mate = rid & 1u;
         const int L = uniform_len > 0 ? uniform_len : (int)lens[rid];
@@ -1109,7 +1115,7 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
         }
         int best_sc = -1, best_qb = 0, best_qe = 0;
         uint32_t best_key = 0xFFFFFFFFu;
-        const int nprobe = L >= KP ? (L - KP) / S + 1 : 0;
+        const int nprobe = L >= KP ? (KP == 12 ? (L - 12) >> 3 : (L - KP) / S) + 1 : 0;      // S == 20 - KP
         for (int p0 = 0; p0 < nprobe; p0 += 32) {
             const int pi = p0 + lane, p = pi * S;
             bool active = pi < nprobe;
@@ -1335,7 +1341,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     k_extend<<<ext_blocks, 256, 0, st>>>((const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair,
                                          b->uniform_len, b->lens, b->nread_ids, b->nmask, (int)b->n_nreads, cand2,
                                          d_counts, (uint32_t)cand_cap, d->d_table, d->tmask, d->d_anchor, d->G, d->kp,
-                                         d->stride, P, slots, cc3);
+                                         d->stride, P, slots, cc3, d_counts + AF_CNT_SCRATCH);
     prof_span(ev, st, ST_EXTEND);
     prof_mark(&ev, st);
     if (sink) k_hit_scatter<true><<<sg2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, cc3, (uint4 *)d_hits, (uint32_t)hits_cap, d_counts, *sink);

@@ -111,7 +111,7 @@ typedef struct {
 } af_batch_t;
 
 /* counts written by af_anchor_batch (device memory, AF_N_COUNTS x uint32) */
-enum { AF_CNT_FLAGGED = 0, AF_CNT_HITS = 1, AF_CNT_STATUS = 2, AF_CNT_SEEDED = 3, AF_N_COUNTS = 8 };
+enum { AF_CNT_FLAGGED = 0, AF_CNT_HITS = 1, AF_CNT_STATUS = 2, AF_CNT_SEEDED = 3, AF_CNT_SCRATCH = 4 /* internal */, AF_N_COUNTS = 8 };
 /* bits of counts[AF_CNT_STATUS] */
 #define AF_STATUS_CAND_OVERFLOW 1u
 #define AF_STATUS_HIT_OVERFLOW 2u
