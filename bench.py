@@ -130,8 +130,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step")
     ap.add_argument("--read-len", type=int, default=150)
@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--graphs", type=int, default=0, help="1: replay one CUDA graph per slot in the throughput region")
     ap.add_argument("--cand-cap", type=int, default=0, help="candidate capacity per batch (default 2 x pairs: every read)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-pairs", type=int, default=1_000_000, help="bounded sample for cpu_baseline")
+    ap.add_argument("--cpu-pairs", type=int, default=5_000_000, help="bounded sample for cpu_baseline")
     ap.add_argument("--ref-pairs", type=int, default=250_000, help="pairs per step of the reference arm")
     ap.add_argument("--gather-cap", type=int, default=0, help="hit records per rank in the per-step all-gather "
                     "(0: sized from a probe pass, 1.25 x the largest per-rank hit count, rounded up to 4096)")
