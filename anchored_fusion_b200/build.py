@@ -11,29 +11,50 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-cudart", "static"]
 
 
-def _stale():
-    if not os.path.exists(LIB):
+OBJDIR = os.path.join(HERE, "build")
+COMMON_DEPS = [os.path.join(CSRC, "af_common.h"), os.path.join(HERE, "..", "include", "anchored_fusion.h"), os.path.abspath(__file__)]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "anchored_fusion.h")]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False, extra=()):
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> anchored_fusion_b200/libafb200.so"""
-    if not force and not _stale():
-        return LIB
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> anchored_fusion_b200/libafb200.so
+    One object per source (rebuilt only when it or a header changed), then one link."""
     nvcc = os.environ.get("AF_NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-x", "cu"] + [os.path.join(CSRC, s) for s in SOURCES] + \
-          ["-o", LIB, "-lz", "-lpthread"]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
     env = dict(os.environ)
     env.pop("CC", None)   # the image exports CC=/opt/gcc/bin/gcc, which lacks some spec files
     env.pop("CXX", None)
-    subprocess.check_call(cmd, env=env)
+    os.makedirs(OBJDIR, exist_ok=True)
+    tag = os.path.join(OBJDIR, "flags.txt")
+    flags = " ".join(NVCC_FLAGS + list(extra))
+    if not os.path.exists(tag) or open(tag).read() != flags:
+        force = True
+    objs, rebuilt = [], False
+    for src in SOURCES:
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        path = os.path.join(CSRC, src)
+        if force or _newer(obj, [path] + COMMON_DEPS):
+            cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra) + ["-x", "cu", "-c", path, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.check_call(cmd, env=env)
+            rebuilt = True
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB, "-lz", "-lpthread"]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd, env=env)
+        with open(tag, "w") as fh:
+            fh.write(flags)
     return LIB
 
 
 if __name__ == "__main__":
-    build(force=True, verbose=True, extra=sys.argv[1:])
+    args = sys.argv[1:]
+    build(force="--force" in args, verbose=True, extra=[a for a in args if a != "--force"])

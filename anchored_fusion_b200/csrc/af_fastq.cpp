@@ -1,10 +1,16 @@
 // af_fastq.cpp -- paired FASTQ / FASTQ.gz reader feeding the 2-bit packer.
 // Replaces the kseq/zlib ingest that happens inside `bwa mem ... fastq1 fastq2`
-// (Anchored_Fusion.py:182).  One zlib decode thread per file; the text of the current batch
-// is kept so that names / bases / qualities of the (few) anchored reads can be written out.
+// (Anchored_Fusion.py:182).  Per file one inflate thread runs ahead of the consumer through a
+// bounded queue of decoded blocks, and one parse+pack thread per file works inside af_fastq_next,
+// so inflate (the wall for .gz input), record parsing and 2-bit packing overlap, and decoding goes
+// on while the caller is busy with the previous batch.  The text of the current batch is kept so
+// that names / bases / qualities of the (few) anchored reads can be written out.
 #include <zlib.h>
 
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 #include "af_common.h"
@@ -25,71 +31,143 @@ namespace {
 
 struct Rec { int64_t name_off, seq_off, qual_off; int32_t name_len, len; };
 
+static const size_t BLOCK_BYTES = 4u << 20;   // decoded text per queue entry
+static const size_t QUEUE_BLOCKS = 16;        // read-ahead bound per file (64 MB of text)
+
 struct Side {
     gzFile gz = nullptr;
-    std::vector<char> in;      // decode buffer
+    std::vector<char> in;      // parse buffer: decoded text not yet consumed
     size_t in_pos = 0, in_end = 0;
     bool eof = false;
     std::vector<char> text;    // records of the current batch (names, bases, quals)
     std::vector<Rec> recs;
     std::string err;
 
+    // inflate thread -> consumer
+    std::thread inflater;
+    std::mutex mu;
+    std::condition_variable cv_data, cv_room;
+    std::deque<std::vector<char>> ready;
+    std::vector<std::vector<char>> spare;   // recycled blocks
+    bool done = false, quit = false;
+    std::string inflate_err;
+
+    void inflate_loop() {
+        for (;;) {
+            std::vector<char> blk;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_room.wait(lk, [&] { return quit || ready.size() < QUEUE_BLOCKS; });
+                if (quit) return;
+                if (!spare.empty()) { blk.swap(spare.back()); spare.pop_back(); }
+            }
+            blk.resize(BLOCK_BYTES);
+            int n = gzread(gz, blk.data(), (unsigned)BLOCK_BYTES);
+            std::lock_guard<std::mutex> lk(mu);
+            if (n <= 0) {
+                if (n < 0) { int e; inflate_err = gzerror(gz, &e); }
+                done = true;
+                cv_data.notify_all();
+                return;
+            }
+            blk.resize((size_t)n);
+            ready.push_back(std::move(blk));
+            cv_data.notify_one();
+        }
+    }
+    void start() { inflater = std::thread([this] { inflate_loop(); }); }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv_room.notify_all();
+        if (inflater.joinable()) inflater.join();
+    }
+
     bool fill() {
         if (eof) return false;
-        if (in_pos > 0) { memmove(in.data(), in.data() + in_pos, in_end - in_pos); in_end -= in_pos; in_pos = 0; }
-        if (in_end == in.size()) in.resize(in.size() * 2);
-        int n = gzread(gz, in.data() + in_end, (unsigned)(in.size() - in_end));
-        if (n < 0) { int e; err = gzerror(gz, &e); eof = true; return false; }
-        if (n == 0) { eof = true; return false; }
-        in_end += (size_t)n;
-        return true;
-    }
-    // next line without its terminator; false at EOF with nothing left
-    bool line(const char *&p, size_t &len) {
-        for (;;) {
-            char *s = in.data() + in_pos;
-            char *nl = (char *)memchr(s, '\n', in_end - in_pos);
-            if (nl) {
-                len = (size_t)(nl - s);
-                in_pos += len + 1;
-                if (len && s[len - 1] == '\r') len--;
-                p = s;
-                return true;
-            }
-            if (!fill()) {
-                if (in_pos < in_end) { p = in.data() + in_pos; len = in_end - in_pos; in_pos = in_end; return true; }
+        std::vector<char> blk;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_data.wait(lk, [&] { return done || !ready.empty(); });
+            if (ready.empty()) {
+                if (!inflate_err.empty()) err = inflate_err;
+                eof = true;
                 return false;
             }
+            blk.swap(ready.front());
+            ready.pop_front();
+        }
+        cv_room.notify_one();
+        if (in_pos > 0) { memmove(in.data(), in.data() + in_pos, in_end - in_pos); in_end -= in_pos; in_pos = 0; }
+        if (in_end + blk.size() > in.size()) in.resize(std::max(in.size() * 2, in_end + blk.size()));
+        memcpy(in.data() + in_end, blk.data(), blk.size());
+        in_end += blk.size();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (spare.size() < QUEUE_BLOCKS) spare.push_back(std::move(blk));
+        }
+        return true;
+    }
+    // Finds the next record (4 lines, terminators stripped) in the parse buffer, pulling decoded blocks
+    // as needed; b[k] / e[k] delimit line k, `next` is where the following record starts.  Returns
+    // false at the end of the input (err is set when a record is cut short).
+    bool next_record(size_t b[4], size_t e[4], size_t &next) {
+        for (;;) {
+            size_t cur = in_pos;
+            int k = 0;
+            bool need_more = false;
+            while (k < 4) {
+                const char *nl = cur < in_end ? (const char *)memchr(in.data() + cur, '\n', in_end - cur) : nullptr;
+                size_t end;
+                if (nl) end = (size_t)(nl - in.data());
+                else if (eof && cur < in_end) end = in_end;           // last line without a terminator
+                else { need_more = true; break; }
+                const size_t le = (end > cur && in[end - 1] == '\r') ? end - 1 : end;
+                const size_t after = end < in_end ? end + 1 : in_end;
+                if (k == 0 && le == cur) { in_pos = cur = after; continue; }   // stray blank line between records
+                b[k] = cur; e[k] = le; k++;
+                cur = after;
+            }
+            if (!need_more) { next = cur; return true; }
+            if (eof) {
+                if (k > 0) err = "truncated FASTQ record";
+                return false;
+            }
+            fill();   // compacts the buffer (in_pos -> 0) and appends a block, or sets eof; rescan either way
         }
     }
     void read_batch(int64_t max_pairs) {
+        const size_t last = text.size();
         text.clear();
+        text.reserve(last);
         recs.clear();
-        const char *p;
-        size_t n;
-        while ((int64_t)recs.size() < max_pairs) {
-            if (!line(p, n)) break;
-            if (n == 0) continue;  // stray blank line between records
-            if (p[0] != '@') { err = "FASTQ record does not start with '@'"; return; }
-            Rec r;
+        // records are parsed in place in the parse buffer, then name, bases and qualities are copied
+        // back to back into `text`
+        size_t b[4], e[4], next;
+        while ((int64_t)recs.size() < max_pairs && next_record(b, e, next)) {
+            const char *p = in.data();
+            if (p[b[0]] != '@') { err = "FASTQ record does not start with '@'"; return; }
+            if (e[2] == b[2] || p[b[2]] != '+') { err = "FASTQ record lacks its '+' line"; return; }
+            const size_t slen = e[1] - b[1];
+            if (e[3] - b[3] != slen) { err = "FASTQ quality length differs from sequence length"; return; }
             // name: up to the first blank; a trailing /1 or /2 is dropped, as bwa does
-            size_t nl = 1;
-            while (nl < n && p[nl] != ' ' && p[nl] != '\t') nl++;
-            size_t name_len = nl - 1;
+            size_t nl = b[0] + 1;
+            while (nl < e[0] && p[nl] != ' ' && p[nl] != '\t') nl++;
+            size_t name_len = nl - (b[0] + 1);
             if (name_len >= 2 && p[nl - 2] == '/' && (p[nl - 1] == '1' || p[nl - 1] == '2')) name_len -= 2;
+            Rec r;
             r.name_off = (int64_t)text.size();
             r.name_len = (int32_t)name_len;
-            text.insert(text.end(), p + 1, p + 1 + name_len);
-            if (!line(p, n)) { err = "truncated FASTQ record"; return; }
-            r.seq_off = (int64_t)text.size();
-            r.len = (int32_t)n;
-            text.insert(text.end(), p, p + n);
-            if (!line(p, n) || n == 0 || p[0] != '+') { err = "FASTQ record lacks its '+' line"; return; }
-            if (!line(p, n)) { err = "truncated FASTQ record"; return; }
-            if ((int32_t)n != r.len) { err = "FASTQ quality length differs from sequence length"; return; }
-            r.qual_off = (int64_t)text.size();
-            text.insert(text.end(), p, p + n);
+            r.len = (int32_t)slen;
+            r.seq_off = r.name_off + (int64_t)name_len;
+            r.qual_off = r.seq_off + (int64_t)slen;
+            const size_t at = text.size();
+            text.resize(at + name_len + 2 * slen);
+            char *dst = text.data() + at;
+            memcpy(dst, p + b[0] + 1, name_len);
+            memcpy(dst + name_len, p + b[1], slen);
+            memcpy(dst + name_len + slen, p + b[3], slen);
             recs.push_back(r);
+            in_pos = next;
         }
     }
 };
@@ -114,14 +192,16 @@ extern "C" int af_fastq_open(const char *path1, const char *path2, af_fastq_t **
             return AF_ERR_IO;
         }
         gzbuffer(fq->side[i].gz, 1 << 20);
-        fq->side[i].in.resize(4 << 20);
+        fq->side[i].in.resize(2 * BLOCK_BYTES);
     }
+    for (int i = 0; i < 2; i++) fq->side[i].start();
     *out = fq;
     return AF_OK;
 }
 
 extern "C" void af_fastq_close(af_fastq_t *fq) {
     if (!fq) return;
+    for (int i = 0; i < 2; i++) fq->side[i].stop();
     for (int i = 0; i < 2; i++) if (fq->side[i].gz) gzclose(fq->side[i].gz);
     delete fq;
 }

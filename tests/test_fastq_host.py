@@ -70,6 +70,58 @@ def test_reader_errors(tmp_path):
         FastqPairReader(p1, p2, 16, 0xE4, 10).next_batch()
 
 
+def test_reader_line_endings_blank_lines_and_unterminated_tail(tmp_path):
+    """CRLF files, stray blank lines between records, a last line without '\\n', a record cut short."""
+    from anchored_fusion_b200.stage import FastqPairReader
+    import anchored_fusion_b200 as af
+    p1, p2 = str(tmp_path / "e_1.fastq"), str(tmp_path / "e_2.fastq")
+    open(p1, "wb").write(b"@r0/1 c\r\nACGTAC\r\n+\r\nIIIIII\r\n\r\n@r1\r\nGGGG\r\n+r1\r\n!!!!")      # CRLF, blank, no final newline
+    open(p2, "wb").write(b"\n@r0/2\nTTTTT\n+\n#####\n\n\n@r1\nCC\n+\nII\n")
+    rd = FastqPairReader(p1, p2, 16, 0xE4, 10)
+    b = rd.next_batch()
+    assert b.n_pairs == 2 and list(b.lens) == [6, 5, 4, 2]
+    assert rd.record(0) == ("r0", "ACGTAC", "IIIIII") and rd.record(1) == ("r0", "TTTTT", "#####")
+    assert rd.record(2) == ("r1", "GGGG", "!!!!") and rd.record(3) == ("r1", "CC", "II")
+    assert rd.next_batch() is None
+    rd.close()
+    open(p2, "w").write("@r0\nTTTTT\n+\n#####\n@r1\nCC\n+\n")
+    with pytest.raises(af.AnchoredFusionError, match="truncated"):
+        FastqPairReader(p1, p2, 16, 0xE4, 10).next_batch()
+
+
+@pytest.mark.parametrize("gz", [True, False])
+def test_reader_records_across_decode_blocks_and_early_close(tmp_path, gz):
+    """~30 MB of text per file: records straddle the 4 MB decode blocks, the inflate threads run ahead of
+    the consumer (bounded queue), and closing a reader mid-file joins them cleanly."""
+    from anchored_fusion_b200.stage import FastqPairReader
+    rng = np.random.default_rng(11)
+    n = 90_000
+    codes = rng.integers(0, 4, (2 * n, 150)).astype(np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = [lut[c].tobytes().decode() for c in codes]
+    ext = ".fastq.gz" if gz else ".fastq"
+    p1, p2 = str(tmp_path / ("b_1" + ext)), str(tmp_path / ("b_2" + ext))
+    opener = (lambda p: gzip.open(p, "wt", compresslevel=1)) if gz else (lambda p: open(p, "w"))
+    for path, mate in ((p1, 0), (p2, 1)):
+        with opener(path) as fh:
+            fh.write("".join("@read_number_%d/%d\n%s\n+\n%s\n" % (i, mate + 1, seqs[2 * i + mate], "F" * 150) for i in range(n)))
+    rd = FastqPairReader(p1, p2, 150, 0xE4, 25_000)
+    seen = 0
+    while True:
+        b = rd.next_batch()
+        if b is None:
+            break
+        for rid in (0, 2 * b.n_pairs - 1, b.n_pairs):
+            g = seen + rid // 2
+            assert rd.record(rid) == ("read_number_%d" % g, seqs[2 * g + (rid & 1)], "F" * 150)
+        seen += b.n_pairs
+    assert seen == n
+    rd.close()
+    rd = FastqPairReader(p1, p2, 150, 0xE4, 1000)      # read a little, then close with the queues full
+    assert rd.next_batch().n_pairs == 1000
+    rd.close()
+
+
 def test_bam_roundtrip(tmp_path):
     from anchored_fusion_b200.bam import BamWriter, read_bam, sam_line
     p = str(tmp_path / "t.bam")
