@@ -65,6 +65,7 @@ SIGNATURES = {
                                      P(c_i64), P(c_i32)]),
     "af_unpack_read": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i32, c_vp]),
     "af_fastq_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, P(c_vp)]),
+    "af_fastq_peek": (ctypes.c_int, [ctypes.c_char_p, c_i32, P(c_i32)]),
     "af_fastq_close": (None, [c_vp]),
     "af_fastq_next": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64), P(c_i32),
                                      P(c_i64)]),

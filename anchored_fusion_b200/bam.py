@@ -8,6 +8,8 @@ The reader exists for the tests (round trip) and for environments without samtoo
 import struct
 import zlib
 
+import numpy as np
+
 _EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 _CIGAR_OPS = "MIDNSHP=X"
 _SEQ_CODE = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
@@ -20,6 +22,10 @@ def _reg2bin(beg, end):
         if beg >> shift == end >> shift:
             return offset + (beg >> shift)
     return 0
+
+
+_SEQ_TABLE = bytes(_SEQ_CODE.get(chr(b).upper(), 15) for b in range(256))      # ASCII base -> 4-bit BAM code
+_QUAL_TABLE = bytes((b - 33) & 0xFF for b in range(256))                        # phred+33 -> phred
 
 
 class BamWriter:
@@ -52,11 +58,9 @@ class BamWriter:
         pos0 = pos - 1
         nxt = (next_pos - 1) if next_pos is not None else pos0
         ops = b"".join(struct.pack("<I", (n << 4) | _CIGAR_OPS.index(op)) for n, op in cigar)
-        codes = [_SEQ_CODE.get(c, 15) for c in seq.upper()]
-        if len(codes) & 1:
-            codes.append(0)
-        packed = bytes((codes[i] << 4) | codes[i + 1] for i in range(0, len(codes), 2))
-        q = bytes(ord(c) - 33 for c in qual) if qual is not None else b"\xff" * len(seq)
+        codes = np.frombuffer(seq.encode().translate(_SEQ_TABLE) + (b"\0" if len(seq) & 1 else b""), dtype=np.uint8)
+        packed = ((codes[0::2] << 4) | codes[1::2]).tobytes()
+        q = qual.encode().translate(_QUAL_TABLE) if qual is not None else b"\xff" * len(seq)
         body = struct.pack("<iiBBHHHIiii", 0, pos0, len(name), mapq, _reg2bin(pos0, pos0 + max(ref_span, 1)),
                            len(cigar), flag, len(seq), 0, nxt, 0) + name + ops + packed + q
         self._put(struct.pack("<i", len(body)) + body)

@@ -184,12 +184,38 @@ def main_singlecell(argv=None):
         return folder + '/work_dir/' + gene + '_fusion'
 
     fastas = split_anchor_fasta(args.file_anchored_cds, gene_names, lambda g: gene_prefix(g) + '_anchored_gene_sequence.fa')
-    for gene, fa in zip(gene_names, fastas):
-        ga = GeneAnchorer(fa, args.gpu_number, gene)      # one index upload + staging per gene, not per cell
-        for cell, f1, f2 in cells:
+    # Cells are independent and every output is a per-cell file, so a multi-GPU run is one process per
+    # GPU (torchrun) with the cells dealt round-robin to the ranks: no exchange at all.
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    gas = [GeneAnchorer(fa, args.gpu_number, gene) for gene, fa in zip(gene_names, fastas)]   # one index upload + staging per gene, not per cell
+    t0, n_pairs, n_cells = time.time(), 0, 0
+    for ci, (cell, f1, f2) in enumerate(cells):
+        if ci % world != rank:
+            continue
+        prefixes = []
+        for gene in gene_names:
             cell_dir = args.out_folder + '/' + gene + '/work_dir/' + cell
             _mkdir(cell_dir)
-            run_gene_sample(fa, gene, args.fastq_dir + '/' + f1, args.fastq_dir + '/' + f2, cell_dir + '/' + gene + '_fusion', args, ga)
+            prefixes.append(cell_dir + '/' + gene + '_fusion')
+        todo = [k for k, pre in enumerate(prefixes)
+                if not (os.path.exists(pre + '_anchored_reads.bam') and os.path.exists(pre + '_realign_reads.bam'))]
+        if not todo:
+            continue
+        q1, q2 = args.fastq_dir + '/' + f1, args.fastq_dir + '/' + f2
+        if len(todo) == 1:
+            k = todo[0]
+            stats = run_gene_sample(fastas[k], gene_names[k], q1, q2, prefixes[k], args, gas[k])
+            n_pairs += stats['pairs'] if stats else 0
+        else:
+            # several genes: the cell's FASTQ pair is decoded and packed once (the reference reads it once per gene)
+            all_stats = anchor_stage_multi([gas[k] for k in todo], q1, q2, [prefixes[k] for k in todo])
+            for k, stats in zip(todo, all_stats):
+                write_split_points(stats, gene_names[k], prefixes[k] + '_split_points.txt')
+            n_pairs += all_stats[0]['pairs']
+        n_cells += 1
+    dt = time.time() - t0
+    print('[anchoring] rank %d/%d: %d cells, %d pairs, %d genes, %.2f s (%.0f pairs/s)'
+          % (rank, world, n_cells, n_pairs, len(gene_names), dt, n_pairs / max(dt, 1e-9)))
     return 0
 
 

@@ -118,25 +118,22 @@ class HostBuffers:
 
 def peek_max_read_len(path, n_records=2000):
     """Longest read among the first records, rounded up to a packed word (16 bases)."""
-    import gzip
-    opener = gzip.open if path.endswith(".gz") else open
-    longest = 1
-    with opener(path, "rt") as fh:
-        for i, line in enumerate(fh):
-            if i >= 4 * n_records:
-                break
-            if i % 4 == 1:
-                longest = max(longest, len(line.rstrip("\r\n")))
-    return min(_lib.MAX_READ_LEN, (longest + 15) // 16 * 16)
+    longest = ctypes.c_int32(0)
+    check(lib().af_fastq_peek(path.encode(), n_records, ctypes.byref(longest)))
+    return min(_lib.MAX_READ_LEN, (max(longest.value, 1) + 15) // 16 * 16)
 
 
 def resolve_device(gpu_number):
     """--gpu_number is a string in the reference ('-1' = CPU for its filter model, Model.py:14-19).
-    The anchoring path has no CPU fallback, so '-1' means 'the first visible GPU' here."""
+    The anchoring path has no CPU fallback, so '-1' means 'the first visible GPU' here -- or, in a
+    process started by torchrun, the GPU of its LOCAL_RANK."""
+    import os
     try:
         g = int(gpu_number)
     except (TypeError, ValueError):
         g = -1
+    if g < 0:
+        g = int(os.environ.get("LOCAL_RANK", "0"))
     return max(g, 0)
 
 

@@ -149,6 +149,8 @@ int af_unpack_read(const void *packed, int32_t max_read_len, int64_t read_id, in
  * valid until the next af_fastq_next on the same reader. */
 int af_fastq_open(const char *path1, const char *path2, af_fastq_t **out);
 void af_fastq_close(af_fastq_t *fq);
+/* longest read among the first n_records records (the packed width must be known before reading) */
+int af_fastq_peek(const char *path, int32_t n_records, int32_t *max_len_out);
 /* Reads up to max_pairs pairs; packs them like af_pack_pairs.  *n_pairs_out = 0 at EOF. */
 int af_fastq_next(af_fastq_t *fq, int64_t max_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
                   uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,

@@ -143,3 +143,42 @@ def test_two_genes_one_pass_equals_two_separate_runs(bundled, tmp_path):
         assert len(r2) > 300 and [sam_line(r) for r in r2] == [sam_line(r) for r in r1]
         for suffix in ("_tmp_1.fastq", "_tmp_2.fastq", "_split_points.txt"):
             assert open(w2 + suffix).read() == open(w1 + suffix).read()
+
+
+def test_singlecell_two_genes_cells_dealt_to_ranks(bundled, tmp_path, monkeypatch):
+    """Config-5 shape: several cells, two anchored genes.  Each cell's FASTQ pair is decoded once for both
+    genes, and under torchrun's RANK / WORLD_SIZE the cells are dealt to the ranks with no exchange: two
+    'ranks' (run one after the other here) leave exactly the files of a single-process run."""
+    from anchored_fusion_b200.bam import read_bam, sam_line
+    from anchored_fusion_b200.cli import main_singlecell
+    d = str(tmp_path)
+    a = bundled["anchor"]
+    second = a[2500:6000][::-1].translate(str.maketrans("ACGT", "TGCA"))
+    fa = os.path.join(d, "two.fa")
+    open(fa, "w").write(bundled["header"] + "\n" + a + "\n>NM_000000.1 RCBCR [organism=Homo sapiens]\n" + second + "\n")
+    cells = os.path.join(d, "cells")
+    os.mkdir(cells)
+    n = len(bundled["seqs1"])
+    names = ["c%02d" % i for i in range(5)]
+    for i, c in enumerate(names):
+        _write_bundled_fastqs(bundled, cells, c, range(i, n, 5))
+    out1, out2 = os.path.join(d, "single"), os.path.join(d, "ranks")
+    assert main_singlecell(["--file_anchored_cds", fa, "--fastq_dir", cells, "--out_folder", out1]) == 0
+    for rank in (0, 1):
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("WORLD_SIZE", "2")
+        monkeypatch.setenv("LOCAL_RANK", "0")
+        assert main_singlecell(["--file_anchored_cds", fa, "--fastq_dir", cells, "--out_folder", out2]) == 0
+        done = [c for c in names if os.path.exists(os.path.join(out2, "BCR", "work_dir", c, "BCR_fusion_anchored_reads.bam"))]
+        assert done == (names[0::2] if rank == 0 else names)          # rank 0 took cells 0, 2, 4 only
+    total = 0
+    for gene in ("BCR", "RCBCR"):
+        for c in names:
+            w1 = os.path.join(out1, gene, "work_dir", c, gene + "_fusion")
+            w2 = os.path.join(out2, gene, "work_dir", c, gene + "_fusion")
+            r1, r2 = read_bam(w1 + "_anchored_reads.bam")[2], read_bam(w2 + "_anchored_reads.bam")[2]
+            assert [sam_line(r) for r in r1] == [sam_line(r) for r in r2]
+            total += len(r1)
+            for suffix in ("_tmp_1.fastq", "_tmp_2.fastq", "_split_points.txt"):
+                assert open(w1 + suffix).read() == open(w2 + suffix).read()
+    assert total > 1500
