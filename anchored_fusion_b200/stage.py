@@ -305,7 +305,7 @@ def anchor_stage_multi(gene_anchorers, fastq1, fastq2, out_prefixes, batch_pairs
 def anchor_stage(file_anchored_seq, fastq1, fastq2, out_prefix, thread="1", gpu_number="-1", gene_name=None,
                  batch_pairs=1 << 20, kp=0, gene_anchorer=None):
     """Drop-in for the anchoring stage.  file_anchored_seq is <work>_anchored_gene_sequence.fa;
-    `thread` is accepted for signature compatibility (the two zlib decode threads and the GPU do
+    `thread` is accepted for signature compatibility (two inflate + two parse/pack threads and the GPU do
     the work).  Returns a stats dict; see write_stage_outputs for the files."""
     ga = gene_anchorer or GeneAnchorer(file_anchored_seq, gpu_number, gene_name, kp)
     anchored, mates, stats = scan_fastq_pair(ga.index, fastq1, fastq2, batch_pairs=batch_pairs, engine=ga.engine)
