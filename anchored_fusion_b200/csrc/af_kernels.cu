@@ -228,7 +228,7 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     }
 }
 
-static int g_scan_threads = 768, g_scan_mode = 3, g_fused = 0, g_middle = 7, g_verify_smem = 1;
+static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1;
 // tuning knobs.  Scan variant (mode 0/3): register double buffer under an 85-register cap, up to 768
 // threads = 24 warps per SM (a 512-thread / 128-register variant and a 1024-thread variant without
 // prefetch measured the same and were dropped to keep the build short).
@@ -244,12 +244,10 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     // k_verify (10: membership from the L2-resident bitmap)
     if (mode == 9 || mode == 10) { g_verify_smem = mode == 9; return AF_OK; }
     if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off), 7/8 or 9/10"); return AF_ERR_ARG; }
-    mode = 3;
     const int maxt = 768;
     if (threads_per_block == 0) threads_per_block = maxt;
     if (threads_per_block < 64 || threads_per_block > maxt || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..%d, multiple of 32", maxt); return AF_ERR_ARG; }
     g_scan_threads = threads_per_block;
-    g_scan_mode = mode;
     return AF_OK;
 }
 

@@ -47,6 +47,9 @@ def test_no_cpu_fallback_device_entry_points_fail_loudly_without_a_gpu():
         idx.upload(0)
     with pytest.raises(af.AnchoredFusionError):
         af.Anchorer(idx, 0)
+    from anchored_fusion_b200.dist import HitExchange
+    with pytest.raises(af.AnchoredFusionError):
+        HitExchange(0, 1, 1, 64, 0)              # the hit exchange lives in device memory: no GPU, no exchange
 
 
 def test_product_never_touches_the_oracle():
