@@ -132,6 +132,38 @@ def test_variable_length_reads_with_n(af):
     assert hits_equal(hits2, want)
 
 
+def test_robustness_set_n_bases_and_trimmed_reads(af):
+    """SURVEY 8d robustness set: 200 k synthetic pairs with 0.1 % N bases, every third read trimmed to a
+    random length (adapter / quality trimming), 1 % fusion fragments -- resident path and host pipeline."""
+    from oracle import oracle
+    spec = af.synth_spec(seed=77, ref_len=400_000, anchor_start=150_000, anchor_len=6783, read_len=150,
+                         frag_mean=300, frag_sd=30, sub_ppm=15_000, fusion_ppm=10_000, n_ppm=1_000)
+    anchor = af.synth_anchor(spec)
+    n = 200_000
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    reads = _interleave(m1, m2)
+    rng = np.random.default_rng(3)
+    lens = np.full(2 * n, 150, dtype=np.uint16)
+    cut = np.arange(0, 2 * n, 3)
+    lens[cut] = rng.integers(30, 151, len(cut))
+    for i in cut:
+        reads[i, lens[i]:] = 4
+    assert (reads == 4).sum() > 10_000
+    want = oracle.anchor_reads(oracle.encode(anchor), reads, lens=lens, threads=8)
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    text = lut[reads]
+    seqs = [text[i, : lens[i]].tobytes() for i in range(2 * n)]
+    index = af.AnchorIndex(anchor)
+    host = af.pack_pairs(seqs[0::2], seqs[1::2], pad_byte=index.pad_byte)
+    assert host.uniform_len == 0 and host.n_nreads > 20_000
+    eng = af.Anchorer(index, 0)
+    hits, _ = eng.anchor(host.to_device(0))
+    assert len(want) > 3000
+    assert hits_equal(hits, want)
+    hits2, _ = eng.anchor_host(host, slot_pairs=1 << 16, n_slots=3)
+    assert hits_equal(hits2, want)
+
+
 @pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1025])
 def test_edge_batch_sizes(af, n):
     from oracle import oracle
