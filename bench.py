@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--kp", type=int, default=0)
     ap.add_argument("--scan-threads", type=int, default=0)
     ap.add_argument("--scan-mode", type=str, default="0", help="af_seed_scan_config mode(s), comma separated")
-    ap.add_argument("--slots", type=int, default=2, help="workspace slots / streams consecutive steps alternate between")
+    ap.add_argument("--slots", type=int, default=3, help="workspace slots / streams consecutive steps alternate between")
     ap.add_argument("--graphs", type=int, default=0, help="1: replay one CUDA graph per slot in the throughput region")
     ap.add_argument("--cand-cap", type=int, default=0, help="candidate capacity per batch (default 2 x pairs: every read)")
     ap.add_argument("--e2e-steps", type=int, default=3)
