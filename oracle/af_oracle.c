@@ -20,7 +20,9 @@
  * (BASELINE.json) specifies: "k-mer seed -> integer-scored ungapped/X-drop
  * extension".  What IS pinned by the reference is the interpretation of the
  * records this pass emits (functions.py:656-702 deal_cigar, :892-950
- * contact_reads); see oracle/ref_bridge.py and tests/golden/.
+ * contact_reads); see oracle/ref_bridge.py and tests/golden/.  The positions
+ * it reports on the reference's bundled sample are also checked against the
+ * ground truth in the wgsim read names of that sample (tests/test_oracle.py).
  *
  * Semantics (frozen; DESIGN.md "Anchoring spec v1"):
  *   anchor a[0..G), read r[0..L): base codes 0..3 = A,C,G,T; 4 = N/other.

@@ -93,3 +93,46 @@ def test_bundled_golden_is_what_the_oracle_computes(bundled):
     h1 = oracle.anchor_reads(oracle.encode(bundled["anchor"]), sub, threads=1)
     h2 = oracle.anchor_reads(oracle.encode(bundled["anchor"]), sub, lens=np.full(4000, 101, np.uint16), threads=3)
     assert hits_equal(h1, h2)
+
+
+def test_bundled_sample_hits_agree_with_the_simulators_ground_truth(bundled):
+    """The reference's bundled reads are wgsim simulations whose names carry the truth
+    (`contig_start_end_...`).  The BCR part of EU216071.1 (the BCR-ABL1 transcript) is the anchored CDS
+    in two colinear pieces (CDS position = transcript position + 452 resp. + 1175).  Every anchored read
+    of the frozen oracle output sits where wgsim drew it (+-3 for its indels), and every read that lies
+    inside one of the two pieces is anchored: an external pin of the positions (hence of strand and
+    clipping, which decide where a read's first base lands) that does not depend on this repo's own
+    arithmetic."""
+    hits, names, L = bundled["oracle_hits"], bundled["names1"], bundled["read_len"]
+    offsets = (452, 1175)
+
+    def truth(name):
+        parts = name.split("_")
+        return int(parts[-5]), int(parts[-4])
+
+    spans = {off: [10 ** 9, 0] for off in offsets}
+    for h in hits:
+        start, end = truth(names[int(h["read_id"]) >> 1])
+        first = int(h["pos"]) - int(h["clip_l"])                  # CDS position of the read's first base
+        where = [(base, off) for base in (start, end - L + 1) for off in offsets if abs(first - base - off) <= 3]
+        assert where, (names[int(h["read_id"]) >> 1], h)          # specificity: 1 261 of 1 261
+        base, off = where[0]
+        if not (h["clip_l"] or h["clip_r"]):
+            spans[off][0] = min(spans[off][0], base)
+            spans[off][1] = max(spans[off][1], base + L - 1)
+    assert spans[452][0] < 50 and spans[1175][1] > 2000
+    by_id = {int(h["read_id"]): h for h in hits}
+    expected = missed = 0
+    for p, name in enumerate(names):
+        if not name.startswith("EU216071.1"):
+            assert 2 * p not in by_id and 2 * p + 1 not in by_id       # the other five contigs never anchor
+            continue
+        start, end = truth(name)
+        for base in (start, end - L + 1):
+            for off, (lo, hi) in spans.items():
+                if base >= lo and base + L - 1 <= hi:
+                    expected += 1
+                    ok = any(abs(int(by_id[r]["pos"]) - int(by_id[r]["clip_l"]) - base - off) <= 3
+                             for r in (2 * p, 2 * p + 1) if r in by_id)
+                    missed += not ok
+    assert expected > 1100 and missed == 0                             # sensitivity: 1 159 of 1 159
