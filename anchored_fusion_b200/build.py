@@ -34,17 +34,24 @@ def build(force=False, verbose=False, extra=()):
     flags = " ".join(NVCC_FLAGS + list(extra))
     if not os.path.exists(tag) or open(tag).read() != flags:
         force = True
-    objs, rebuilt = [], False
+    objs, jobs = [], []
     for src in SOURCES:
         obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         path = os.path.join(CSRC, src)
         if force or _newer(obj, [path] + COMMON_DEPS):
-            cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra) + ["-x", "cu", "-c", path, "-o", obj]
+            jobs.append([nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + list(extra) + ["-x", "cu", "-c", path, "-o", obj])
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             subprocess.check_call(cmd, env=env)
-            rebuilt = True
+
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:     # the translation units compile side by side
+            list(pool.map(run, jobs))
+    rebuilt = bool(jobs)
     if rebuilt or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB, "-lz", "-lpthread"]
         if verbose:
