@@ -13,6 +13,7 @@ buffers) and the GPU pipeline; only the anchored reads and the mates of half-anc
 ever materialised as text.
 """
 import ctypes
+import sys
 
 import numpy as np
 
@@ -284,6 +285,13 @@ class GeneAnchorer:
         name, self.seq = read_single_fasta(file_anchored_seq)
         self.gene = gene_name or name.split()[0]
         self.index = AnchorIndex(self.seq, kp=kp)
+        info = self.index.info
+        if info.n_overflow * 200 > info.n_buckets:
+            # the shared-memory filter holds ~3 k'-mers per bucket; past ~12 kb of anchor more and more buckets
+            # overflow into "always hit" and the exact verify stage has to sort out the difference
+            print("[anchoring] %s: anchor of %d bp fills the seed filter (%d of %d buckets overflow); results are "
+                  "unaffected, the scan flags more reads than usual" % (self.gene, len(self.seq), info.n_overflow, info.n_buckets),
+                  file=sys.stderr)
         self.engine = Anchorer(self.index, resolve_device(gpu_number))
 
 
