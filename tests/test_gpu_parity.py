@@ -132,6 +132,24 @@ def test_variable_length_reads_with_n(af):
     assert hits_equal(hits2, want)
 
 
+def test_long_anchor_saturating_the_filter_stays_exact(af):
+    """A 40 kb anchor overflows thousands of filter buckets ("always hit"): most reads are flagged and the
+    exact verify stage decides -- the records must still equal the oracle's."""
+    from oracle import oracle
+    spec = af.synth_spec(seed=40, ref_len=600_000, anchor_start=200_000, anchor_len=40_000, read_len=150,
+                         frag_mean=300, frag_sd=30, sub_ppm=15_000, fusion_ppm=20_000)
+    anchor = af.synth_anchor(spec)
+    index = af.AnchorIndex(anchor)
+    assert index.info.n_overflow > 2000
+    eng = af.Anchorer(index, 0)
+    n = 60_000
+    hits, stats = eng.anchor(af.synth_pairs_device(spec, 0, n, index.pad_byte, 0))
+    assert stats["flagged"] > n                                     # more than half of the 2n reads
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    want = oracle.anchor_reads(oracle.encode(anchor), _interleave(m1, m2), threads=8)
+    assert len(want) > 5000 and hits_equal(hits, want)
+
+
 def test_robustness_set_n_bases_and_trimmed_reads(af):
     """SURVEY 8d robustness set: 200 k synthetic pairs with 0.1 % N bases, every third read trimmed to a
     random length (adapter / quality trimming), 1 % fusion fragments -- resident path and host pipeline."""
