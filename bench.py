@@ -106,6 +106,38 @@ def cpu_reference_rate(args, n_pairs, threads):
     return n_pairs / dt, dt, len(hits)
 
 
+def fastq_gz_rate(args, spec, index, eng):
+    """A bounded sample of the workload written as two FASTQ.gz files, then read back through the whole
+    host path (inflate threads, parser, packer, pinned staging, GPU pipeline, record retrieval)."""
+    import gzip
+    import shutil
+    import tempfile
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200.stage import scan_fastq_pair
+    n = args.fastq_pairs
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    d = tempfile.mkdtemp(prefix="af_bench_fq_")
+    try:
+        p1, p2 = os.path.join(d, "s_1.fastq.gz"), os.path.join(d, "s_2.fastq.gz")
+        qual = "I" * args.read_len
+        with gzip.open(p1, "wt", compresslevel=1) as f1, gzip.open(p2, "wt", compresslevel=1) as f2:
+            for lo in range(0, n, 100_000):
+                m1, m2 = af.synth_pairs_host(spec, lo, min(100_000, n - lo))
+                a1, a2 = lut[m1], lut[m2]
+                f1.write("".join("@frag%d/1\n%s\n+\n%s\n" % (lo + i, a1[i].tobytes().decode(), qual) for i in range(len(a1))))
+                f2.write("".join("@frag%d/2\n%s\n+\n%s\n" % (lo + i, a2[i].tobytes().decode(), qual) for i in range(len(a2))))
+        scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 18)          # warm-up: allocations, page cache
+        t0 = time.perf_counter()
+        anchored, mates, stats = scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 20)
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "pairs/s", "pairs": n, "seconds": dt, "anchored_reads": len(anchored),
+                "gz_bytes": os.path.getsize(p1) + os.path.getsize(p2),
+                "path": "two FASTQ.gz files -> 2 inflate + 2 parse/pack threads -> pinned tiles -> af_pipeline_run -> records",
+                "bound": "zlib inflate of the two files"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -152,6 +184,7 @@ def main():
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N > 1: how the ranks' hit lists reach every rank -- p2p: the hit-compaction kernel stores them "
                          "into every GPU's log over NVLink peer memory; nccl: one all-gather per step")
+    ap.add_argument("--fastq-pairs", type=int, default=500_000, help="pairs of the FASTQ.gz end-to-end sample (0: skip)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -386,6 +419,11 @@ def main():
         eng.close_pipeline()
         L.af_host_free(hptr)
 
+    # third rate: FASTQ.gz files on disk -> zlib reader -> packer -> pipeline -> records
+    fastq = None
+    if rank == 0 and world == 1 and args.fastq_pairs > 0 and not args.no_e2e:
+        fastq = fastq_gz_rate(args, spec, index, eng)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -400,7 +438,7 @@ def main():
         os.write(real_stdout, (json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": dict(config_dict(args, world), streams=n_slots, cuda_graphs=bool(args.graphs), exchange=exchange_info), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                          "config": dict(config_dict(args, world), streams=n_slots, cuda_graphs=bool(args.graphs), exchange=exchange_info), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq_gz": fastq,
                           "gpu_launches": int(launches), "clocks": clocks,
                           "per_step": {"flagged_reads": int(stats_counts[0]), "seeded_reads": int(stats_counts[3]),
                                        "anchored_reads": nh,
