@@ -52,14 +52,16 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     af_params_t P;
     if (params) P = *params; else af_default_params(&P);
     if (kp == 0) kp = 12;
-    if (P.k < 8 || P.k > 32 || kp < 8 || kp > 14 || kp > P.k || P.A <= 0 || P.B < 0 || P.X < 0) {
-        af_set_error("af_index_build: unsupported parameters (k=%d, kp=%d)", P.k, kp);
+    // The kernels are built for bwa-mem's seed length: they sample a read's k'-mers at stride 20 - k'
+    // (compile-time), which finds every exact match of >= 19 bases.  Scores, clip penalties, T and X are free.
+    if (P.k != 19 || (kp != 12 && kp != 13) || P.A <= 0 || P.B < 0 || P.X < 0) {
+        af_set_error("af_index_build: unsupported parameters (k=%d must be 19, kp=%d must be 12 or 13)", P.k, kp);
         return AF_ERR_ARG;
     }
     af_index *idx = new af_index();
     idx->P = P;
     idx->kp = kp;
-    idx->stride = P.k - kp + 1;
+    idx->stride = 20 - kp;
     idx->G = (int32_t)len;
     idx->codes.resize((size_t)len);
     for (int64_t i = 0; i < len; i++) idx->codes[(size_t)i] = af_code_of(anchor[i]);

@@ -52,6 +52,15 @@ def test_no_cpu_fallback_device_entry_points_fail_loudly_without_a_gpu():
         HitExchange(0, 1, 1, 64, 0)              # the hit exchange lives in device memory: no GPU, no exchange
 
 
+def test_only_the_seed_length_the_kernels_are_built_for_is_accepted():
+    import anchored_fusion_b200 as af
+    with pytest.raises(af.AnchoredFusionError, match="k=15 must be 19"):
+        af.AnchorIndex("ACGT" * 100, params=af.default_params(k=15))
+    with pytest.raises(af.AnchoredFusionError, match="kp=11"):
+        af.AnchorIndex("ACGT" * 100, kp=11)
+    af.AnchorIndex("ACGT" * 100, params=af.default_params(B=2, X=12, T=35, clip5=3, clip3=8))    # scores are free
+
+
 def test_product_never_touches_the_oracle():
     """anchored_fusion_b200/ must not import, link or call anything under oracle/."""
     pkg = os.path.join(ROOT, "anchored_fusion_b200")

@@ -132,6 +132,42 @@ def test_variable_length_reads_with_n(af):
     assert hits_equal(hits2, want)
 
 
+@pytest.mark.parametrize("over", [{"B": 2, "X": 12, "T": 35, "clip5": 3, "clip3": 8},
+                                  {"A": 2, "B": 5, "X": 30, "T": 50, "clip5": 0, "clip3": 0}])
+def test_other_scores_and_a_repetitive_anchor(af, over):
+    """Non-default match / mismatch scores, clip penalties, X-drop and threshold, on an anchor holding a
+    37-base unit five times and a 300-base segment three times (many seeded diagonals per read; ties go
+    to the higher score, then strand 0, then the smaller diagonal)."""
+    from oracle import oracle
+    rng = np.random.default_rng(23)
+    unit, seg = rng.integers(0, 4, 37), rng.integers(0, 4, 300)
+    codes = np.concatenate([rng.integers(0, 4, 500), np.tile(unit, 5), rng.integers(0, 4, 400), seg, rng.integers(0, 4, 200), seg,
+                            rng.integers(0, 4, 300), seg, rng.integers(0, 4, 500)]).astype(np.uint8)
+    G = len(codes)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    n, L = 20_000, 100
+    reads = rng.integers(0, 4, (2 * n, L)).astype(np.uint8)
+    for i in range(0, 2 * n, 2):                       # every other read comes from the anchor
+        p = int(rng.integers(-20, G - L + 20))
+        src = np.array([codes[j] if 0 <= j < G else rng.integers(0, 4) for j in range(p, p + L)], dtype=np.uint8)
+        if i % 3 == 0:
+            j = int(rng.integers(10, L - 10))
+            src[j:] = rng.integers(0, 4, L - j)
+        for _ in range(int(rng.integers(0, 4))):
+            src[rng.integers(0, L)] = rng.integers(0, 4)
+        reads[i] = src if i % 4 else (3 - src)[::-1]
+    want = oracle.anchor_reads(codes, reads, params=oracle.default_params(**over), threads=8)
+    index = af.AnchorIndex(lut[codes].tobytes(), params=af.default_params(**over))
+    host = af.pack_pairs([lut[r].tobytes() for r in reads[0::2]], [lut[r].tobytes() for r in reads[1::2]], pad_byte=index.pad_byte)
+    hits, _ = af.Anchorer(index, 0).anchor(host.to_device(0))
+    assert len(want) > 5000 and hits_equal(hits, want)
+
+
+def test_unsupported_seed_length_is_refused(af):
+    with pytest.raises(af.AnchoredFusionError, match="k=15 must be 19"):
+        af.AnchorIndex("ACGT" * 100, params=af.default_params(k=15))
+
+
 def test_long_anchor_saturating_the_filter_stays_exact(af):
     """A 40 kb anchor overflows thousands of filter buckets ("always hit"): most reads are flagged and the
     exact verify stage decides -- the records must still equal the oracle's."""

@@ -136,3 +136,36 @@ def test_bundled_sample_hits_agree_with_the_simulators_ground_truth(bundled):
                              for r in (2 * p, 2 * p + 1) if r in by_id)
                     missed += not ok
     assert expected > 1100 and missed == 0                             # sensitivity: 1 159 of 1 159
+
+
+def test_c_oracle_equals_bruteforce_with_other_parameters_and_repeats():
+    """Non-default scores / clip penalties / X-drop / T and an anchor made of a tandem repeat (many
+    diagonals tie: score desc, strand 0 first, smaller d) -- C oracle vs the index-free brute force."""
+    from oracle import bruteforce, oracle
+    rng = np.random.default_rng(11)
+    unit = rng.integers(0, 4, 37).astype(np.uint8)
+    a = np.concatenate([rng.integers(0, 4, 120), np.tile(unit, 5), rng.integers(0, 4, 120)]).astype(np.uint8)
+    G = len(a)
+    for over in ({"B": 2, "X": 12, "T": 35, "clip5": 3, "clip3": 8}, {"A": 2, "B": 5, "X": 30, "T": 50, "clip5": 0, "clip3": 0},
+                 {"k": 23, "T": 23, "X": 6}):
+        P = dict(bruteforce.DEFAULT, **over)
+        cp = oracle.default_params(**over)
+        reads = []
+        for t in range(150):
+            L = 70
+            p = int(rng.integers(-15, G - L + 15))
+            r = np.array([a[i] if 0 <= i < G else rng.integers(0, 4) for i in range(p, p + L)])
+            if t % 3 == 0:
+                j = int(rng.integers(8, L - 8))
+                r[j:] = rng.integers(0, 4, L - j)
+            for _ in range(int(rng.integers(0, 5))):
+                r[rng.integers(0, L)] = rng.integers(0, 5)
+            if t % 2:
+                r = np.array(_rc(list(r)))
+            reads.append(r.astype(np.uint8))
+        hits = oracle.anchor_reads(a, np.stack(reads), params=cp)
+        got = {int(h["read_id"]): (int(h["pos"]), int(h["clip_l"]), int(h["m_len"]), int(h["clip_r"]),
+                                   int(h["score_strand"]) & 1, int(h["score_strand"]) >> 1) for h in hits}
+        assert len(got) > 60, over
+        for i, r in enumerate(reads):
+            assert bruteforce.anchor_read(list(r), list(a), P) == got.get(i), (over, i)
