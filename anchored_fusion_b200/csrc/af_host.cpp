@@ -2,6 +2,7 @@
 // synthetic-read generator (host twin of the device generator), error plumbing.
 // No CUDA here; see af_kernels.cu for the device side.
 #include <algorithm>
+#include <array>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -209,10 +210,13 @@ struct PackSide {
 };
 
 static const uint8_t *code_lut() {
-    static uint8_t lut[256];
-    static bool init = false;
-    if (!init) { for (int c = 0; c < 256; c++) lut[c] = af_code_of((char)c); init = true; }
-    return lut;
+    // built once, thread-safely (function-local static): the two mates are packed by two threads
+    static const std::array<uint8_t, 256> lut = [] {
+        std::array<uint8_t, 256> t{};
+        for (int c = 0; c < 256; c++) t[(size_t)c] = af_code_of((char)c);
+        return t;
+    }();
+    return lut.data();
 }
 
 void af_pack_side(const SeqRef *r, int m, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
