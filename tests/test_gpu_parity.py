@@ -281,3 +281,54 @@ def test_capacity_overflow_is_reported_not_dropped(af):
     dev = af.synth_pairs_device(spec, 0, 50_000, index.pad_byte, 0)
     with pytest.raises(af.AnchoredFusionError):
         eng.anchor(dev, cand_cap=1000, hits_cap=1000)
+
+
+@pytest.mark.parametrize("modes", [(), (4,), (10,)])
+def test_kernels_stay_inside_their_buffers(af, modes):
+    """compute-sanitizer is not available on this pool, so out-of-bounds WRITES are looked for directly:
+    workspace, hit list, counters and the packed batch sit between 64 KB canary zones, which must come
+    back untouched (default path, the fused scan+verify kernel, the bitmap verify kernel), with a pair
+    count that is not a multiple of anything and capacities small enough to be hit exactly."""
+    import ctypes
+    import torch
+    from anchored_fusion_b200._lib import check, lib
+    spec = af.synth_spec(seed=91, ref_len=300_000, anchor_start=100_000, anchor_len=5000, read_len=150,
+                         frag_mean=300, sub_ppm=15_000, fusion_ppm=50_000)
+    index = af.AnchorIndex(af.synth_anchor(spec))
+    eng = af.Anchorer(index, 0)
+    n = 77_777
+    ref_hits, stats = eng.anchor(af.synth_pairs_device(spec, 0, n, index.pad_byte, 0))
+    G, dev = 1 << 16, torch.device("cuda", 0)
+
+    def guarded(nbytes):
+        big = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device=dev)
+        return big, big[G: G + nbytes]
+
+    lay = af.layout(150, n)
+    src = af.synth_pairs_device(spec, 0, n, index.pad_byte, 0)
+    big_p, packed = guarded(lay.packed_bytes)
+    packed.copy_(src.packed.view(torch.uint8)[: lay.packed_bytes])
+    cand_cap = stats["flagged"] + 1                      # just enough
+    hits_cap = len(ref_hits)                             # exactly enough
+    ws_bytes = lib().af_workspace_bytes(n, cand_cap)
+    big_w, ws = guarded(ws_bytes)
+    big_h, hits = guarded(hits_cap * 16)
+    big_c, counts = guarded(32)
+    batch = af.PackedBatch(packed.view(torch.int32), n, 150, 150)
+    cb = batch.c_struct()
+    for m in modes:
+        check(lib().af_seed_scan_config(0, m))
+    try:
+        check(lib().af_anchor_batch(eng.dindex._h, ctypes.byref(cb), ws.data_ptr(), ws_bytes, cand_cap, hits.data_ptr(), hits_cap,
+                                    counts.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        torch.cuda.synchronize()
+    finally:
+        check(lib().af_seed_scan_config(0, 5))
+        check(lib().af_seed_scan_config(0, 9))
+    c = counts.view(torch.int32).cpu().numpy()
+    assert c[2] == 0 and c[1] == len(ref_hits)
+    got = hits.cpu().numpy().view(af.HIT_DTYPE)
+    assert hits_equal(got, ref_hits)
+    for name, big, nbytes in (("packed", big_p, lay.packed_bytes), ("workspace", big_w, ws_bytes), ("hits", big_h, hits_cap * 16),
+                              ("counts", big_c, 32)):
+        assert bool((big[:G] == 0xA5).all()) and bool((big[G + nbytes:] == 0xA5).all()), name
