@@ -1,6 +1,5 @@
 """Host ingest: the C++ FASTQ(.gz) reader + packer (no GPU needed) and the BAM writer."""
 import gzip
-import os
 
 import numpy as np
 import pytest

@@ -4,10 +4,9 @@ import gzip
 import json
 import os
 
-import numpy as np
 import pytest
 
-from conftest import GOLDEN, hits_equal
+from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
