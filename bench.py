@@ -90,8 +90,8 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_rate(args, n_pairs, threads):
-    """The CPU arm: oracle/af_oracle.c (a port: the reference's own path is bwa/samtools, absent)."""
+def cpu_sample(args, n_pairs):
+    """The first n_pairs pairs of the workload as base codes for the CPU arm (generated once)."""
     import anchored_fusion_b200 as af
     from oracle import oracle
     spec = workload(args)
@@ -99,7 +99,14 @@ def cpu_reference_rate(args, n_pairs, threads):
     m1, m2 = af.synth_pairs_host(spec, 0, n_pairs)
     reads = np.empty((2 * n_pairs, spec.read_len), dtype=np.uint8)
     reads[0::2], reads[1::2] = m1, m2
-    oracle.anchor_reads(anchor, reads[:2000], threads=threads)   # warm the library
+    oracle.anchor_reads(anchor, reads[:2000], threads=os.cpu_count() or 1)   # warm the library
+    return anchor, reads
+
+
+def cpu_reference_rate(args, n_pairs, threads, sample=None):
+    """The CPU arm: oracle/af_oracle.c (a port: the reference's own path is bwa/samtools, absent)."""
+    from oracle import oracle
+    anchor, reads = sample if sample is not None else cpu_sample(args, n_pairs)
     t0 = time.perf_counter()
     hits = oracle.anchor_reads(anchor, reads, threads=threads)
     dt = time.perf_counter() - t0
@@ -144,9 +151,10 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     sample = args.ref_pairs
+    data = cpu_sample(args, sample)
     rates = []
     for i in range(args.warmup + args.steps):
-        rate, dt, nh = cpu_reference_rate(args, sample, threads)
+        rate, dt, nh = cpu_reference_rate(args, sample, threads, data)
         if i >= args.warmup:
             rates.append((rate, dt))
     value = sample * len(rates) / sum(dt for _, dt in rates)
@@ -178,7 +186,7 @@ def main():
     ap.add_argument("--cand-cap", type=int, default=0, help="candidate capacity per batch (default 2 x pairs: every read)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-pairs", type=int, default=5_000_000, help="bounded sample for cpu_baseline")
-    ap.add_argument("--ref-pairs", type=int, default=250_000, help="pairs per step of the reference arm")
+    ap.add_argument("--ref-pairs", type=int, default=2_000_000, help="pairs per step of the reference arm")
     ap.add_argument("--gather-cap", type=int, default=0, help="hit records per rank in the per-step all-gather "
                     "(0: sized from a probe pass, 1.25 x the largest per-rank hit count, rounded up to 4096)")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",

@@ -101,6 +101,17 @@ static afo_ent *build_index(const uint8_t *a, int32_t G, int k, int64_t *n_out) 
     return e;
 }
 
+/* A presence bitmap over a hash of the anchor's k-mers: a read window whose bit is clear cannot be in
+ * the sorted index, so the binary search is skipped.  Purely a shortcut of the lookup -- the set of
+ * (window, anchor position) matches is unchanged -- that makes the full-size parity runs affordable. */
+#define AFO_PRESENT_BITS (1u << 22)
+static inline uint32_t present_slot(uint64_t km) { return (uint32_t)((km * 0x9E3779B97F4A7C15ULL) >> 42); }
+static uint64_t *build_present(const afo_ent *e, int64_t n) {
+    uint64_t *b = (uint64_t *)calloc(AFO_PRESENT_BITS / 64, sizeof(uint64_t));
+    for (int64_t i = 0; i < n; i++) { uint32_t s = present_slot(e[i].kmer); b[s >> 6] |= 1ULL << (s & 63); }
+    return b;
+}
+
 static int64_t lower_bound(const afo_ent *e, int64_t n, uint64_t key) {
     int64_t lo = 0, hi = n;
     while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (e[mid].kmer < key) lo = mid + 1; else hi = mid; }
@@ -158,7 +169,7 @@ static int i32_cmp(const void *x, const void *y) {
 typedef struct { int32_t *v; size_t cap; } afo_scratch;
 
 static int anchor_read(const uint8_t *r, int32_t L, const uint8_t *a, int32_t G, const afo_ent *idx,
-                       int64_t nidx, const afo_params *P, uint8_t *q, afo_scratch *S, afo_hit *h) {
+                       int64_t nidx, const uint64_t *present, const afo_params *P, uint8_t *q, afo_scratch *S, afo_hit *h) {
     int k = P->k, found = 0;
     int32_t best_sc = -1, best_qb = 0, best_qe = 0, best_d = 0, best_s = 0;
     if (L < k) return 0;
@@ -172,6 +183,8 @@ static int anchor_read(const uint8_t *r, int32_t L, const uint8_t *a, int32_t G,
             if (q[i] < 4) { km = ((km << 2) | q[i]) & mask; run++; } else { run = 0; km = 0; }
             if (run < k) continue;
             int32_t qpos = i - k + 1;
+            const uint32_t ps = present_slot(km);
+            if (!((present[ps >> 6] >> (ps & 63)) & 1ULL)) continue;
             for (int64_t e = lower_bound(idx, nidx, km); e < nidx && idx[e].kmer == km; e++) {
                 if ((size_t)nd == S->cap) { S->cap *= 2; S->v = (int32_t *)realloc(S->v, sizeof(int32_t) * S->cap); }
                 S->v[nd++] = idx[e].pos - qpos;
@@ -207,6 +220,7 @@ int afo_anchor_reads(const uint8_t *anchor, int32_t G, const uint8_t *reads, con
                      int64_t *n_out, int nthreads) {
     int64_t nidx = 0;
     afo_ent *idx = build_index(anchor, G, P->k, &nidx);
+    uint64_t *present = build_present(idx, nidx);
     uint8_t *ok = (uint8_t *)calloc((size_t)(n_reads > 0 ? n_reads : 1), 1);
     afo_hit *tmp = (afo_hit *)malloc(sizeof(afo_hit) * (size_t)(n_reads > 0 ? n_reads : 1));
 #ifdef _OPENMP
@@ -224,7 +238,7 @@ int afo_anchor_reads(const uint8_t *anchor, int32_t G, const uint8_t *reads, con
         for (int64_t i = 0; i < n_reads; i++) {
             int32_t L = lens ? lens[i] : stride;
             afo_hit h;
-            if (anchor_read(reads + i * (int64_t)stride, L, anchor, G, idx, nidx, P, q, &S, &h)) {
+            if (anchor_read(reads + i * (int64_t)stride, L, anchor, G, idx, nidx, present, P, q, &S, &h)) {
                 h.read_id = (uint32_t)i;
                 tmp[i] = h;
                 ok[i] = 1;
@@ -235,7 +249,7 @@ int afo_anchor_reads(const uint8_t *anchor, int32_t G, const uint8_t *reads, con
     int64_t n = 0;
     for (int64_t i = 0; i < n_reads; i++) if (ok[i]) { if (n < cap) out[n] = tmp[i]; n++; }
     *n_out = n;
-    free(idx); free(ok); free(tmp);
+    free(idx); free(present); free(ok); free(tmp);
     return n <= cap ? 0 : -1;
 }
 
