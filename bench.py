@@ -91,15 +91,24 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_sample(args, n_pairs):
-    """The first n_pairs pairs of the workload as base codes for the CPU arm (generated once)."""
+    """The first n_pairs pairs of the workload as base codes for the CPU arm (generated once, by all cores)."""
+    from concurrent.futures import ThreadPoolExecutor
     import anchored_fusion_b200 as af
     from oracle import oracle
     spec = workload(args)
     anchor = oracle.encode(af.synth_anchor(spec))
-    m1, m2 = af.synth_pairs_host(spec, 0, n_pairs)
     reads = np.empty((2 * n_pairs, spec.read_len), dtype=np.uint8)
-    reads[0::2], reads[1::2] = m1, m2
-    oracle.anchor_reads(anchor, reads[:2000], threads=os.cpu_count() or 1)   # warm the library
+    threads = os.cpu_count() or 1
+    step = (n_pairs + threads - 1) // threads
+
+    def fill(lo):
+        hi = min(lo + step, n_pairs)
+        m1, m2 = af.synth_pairs_host(spec, lo, hi - lo)          # a ctypes call: runs without the GIL
+        reads[2 * lo: 2 * hi: 2], reads[2 * lo + 1: 2 * hi: 2] = m1, m2
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        list(pool.map(fill, range(0, n_pairs, step)))
+    oracle.anchor_reads(anchor, reads[:2000], threads=threads)   # warm the library
     return anchor, reads
 
 
@@ -185,8 +194,8 @@ def main():
     ap.add_argument("--graphs", type=int, default=0, help="1: replay one CUDA graph per slot in the throughput region")
     ap.add_argument("--cand-cap", type=int, default=0, help="candidate capacity per batch (default 2 x pairs: every read)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-pairs", type=int, default=5_000_000, help="bounded sample for cpu_baseline")
-    ap.add_argument("--ref-pairs", type=int, default=2_000_000, help="pairs per step of the reference arm")
+    ap.add_argument("--cpu-pairs", type=int, default=10_000_000, help="bounded sample for cpu_baseline")
+    ap.add_argument("--ref-pairs", type=int, default=10_000_000, help="pairs per step of the reference arm")
     ap.add_argument("--gather-cap", type=int, default=0, help="hit records per rank in the per-step all-gather "
                     "(0: sized from a probe pass, 1.25 x the largest per-rank hit count, rounded up to 4096)")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
