@@ -1,7 +1,10 @@
-"""Full-size runs (BASELINE.json configs 2-4 shapes) checked through size-independent properties:
-the oracle re-derives every reported record from the hit reads alone, a random sample of
-unreported reads must stay unreported, results do not depend on how the job is cut into batches,
-and planted anchor fragments are recovered."""
+"""Full-size runs (BASELINE.json configs 2-4 shapes): every record of the whole run equals the oracle's
+(chunk by chunk on all host cores), and the size-independent properties hold -- the oracle re-derives
+every reported record from the hit reads alone, a random sample of unreported reads stays unreported,
+results do not depend on how the job is cut into batches, planted anchor fragments are recovered."""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import pytest
 
@@ -27,6 +30,22 @@ def _oracle_on_reads(af, oracle, spec, anchor_codes, read_ids):
     return h, set((2 * pairs[:, None] + np.arange(2)[None, :]).reshape(-1).tolist())
 
 
+def _oracle_on_range(af, oracle, spec, anchor_codes, lo, hi):
+    """Oracle records (read ids relative to `lo`) of pairs [lo, hi), generated and anchored on all host cores."""
+    n, threads = hi - lo, os.cpu_count() or 1
+    reads = np.empty((2 * n, spec.read_len), dtype=np.uint8)
+    step = (n + threads - 1) // threads
+
+    def fill(a):
+        b = min(a + step, n)
+        m1, m2 = af.synth_pairs_host(spec, lo + a, b - a)
+        reads[2 * a: 2 * b: 2], reads[2 * a + 1: 2 * b: 2] = m1, m2
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        list(pool.map(fill, range(0, n, step)))
+    return oracle.anchor_reads(anchor_codes, reads, threads=threads)
+
+
 @pytest.mark.parametrize("name,n,anchor_len,sub_ppm,fusion_ppm", [
     ("config2_10M_pairs", 10_000_000, 6783, 10_000, 0),
     ("config4_long_anchor_fusions", 5_000_000, 10_000, 15_000, 10_000),
@@ -48,6 +67,13 @@ def test_full_size_properties(name, n, anchor_len, sub_ppm, fusion_ppm):
     assert np.all(np.diff(hits["read_id"].astype(np.int64)) > 0)
     assert np.all(hits["clip_l"].astype(int) + hits["m_len"] + hits["clip_r"] == 150)
     assert np.all((hits["score_strand"] >> 1) >= 30) and np.all(hits["pos"] >= 1) and np.all(hits["pos"] + hits["m_len"].astype(int) - 1 <= anchor_len)
+    # (1b) the whole run, record for record, against the oracle (2.5 M pairs at a time)
+    for lo in range(0, n, 2_500_000):
+        hi = min(lo + 2_500_000, n)
+        want_part = _oracle_on_range(af, oracle, spec, acodes, lo, hi)
+        want_part["read_id"] += np.uint32(2 * lo)
+        part = hits[(hits["read_id"] >= 2 * lo) & (hits["read_id"] < 2 * hi)]
+        assert hits_equal(part, want_part), (name, lo)
     # (2) the oracle, given only the reported pairs, reproduces every record bit for bit (both
     #     mates of those pairs: an unreported mate of a reported pair must stay unreported)
     want, _ = _oracle_on_reads(af, oracle, spec, acodes, hits["read_id"])
