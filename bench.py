@@ -444,10 +444,14 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        rate, dt, nh = cpu_reference_rate(args, args.cpu_pairs, threads)
+        data = cpu_sample(args, args.cpu_pairs)
+        rate, dt, nh = cpu_reference_rate(args, args.cpu_pairs, threads, data)
+        n1 = min(args.cpu_pairs, 2_000_000)                      # and one core alone, on the first 2 M pairs
+        rate1, dt1, _ = cpu_reference_rate(args, n1, 1, (data[0], data[1][: 2 * n1]))
         cpu = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port",
                "sample": "first %d pairs of the workload, oracle/af_oracle.c, %d OpenMP threads, %.1f s"
-                         % (args.cpu_pairs, threads, dt)}
+                         % (args.cpu_pairs, threads, dt),
+               "value_1_core": rate1, "sample_1_core": "first %d pairs, 1 thread, %.1f s" % (n1, dt1)}
 
     if rank == 0:
         nh = int(stats_counts[1])
