@@ -142,7 +142,7 @@ def fastq_gz_rate(args, spec, index, eng):
                 a1, a2 = lut[m1], lut[m2]
                 f1.write("".join("@frag%d/1\n%s\n+\n%s\n" % (lo + i, a1[i].tobytes().decode(), qual) for i in range(len(a1))))
                 f2.write("".join("@frag%d/2\n%s\n+\n%s\n" % (lo + i, a2[i].tobytes().decode(), qual) for i in range(len(a2))))
-        scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 18)          # warm-up: allocations, page cache
+        scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 20)          # warm-up: staging buffers, page cache
         t0 = time.perf_counter()
         anchored, mates, stats = scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 20)
         dt = time.perf_counter() - t0

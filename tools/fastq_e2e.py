@@ -37,7 +37,7 @@ with gzip.open(p1, "wt", compresslevel=1) as f1, gzip.open(p2, "wt", compresslev
 gen_s = time.time() - t0
 index = af.AnchorIndex(anchor)
 eng = af.Anchorer(index, 0)
-scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 18)          # warm-up (allocations, page cache)
+scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 20)          # warm-up (staging buffers, page cache)
 t0 = time.time()
 anchored, mates, stats = scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 20)
 dt = time.time() - t0
