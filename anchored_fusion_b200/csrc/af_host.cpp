@@ -59,6 +59,11 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
         af_set_error("af_index_build: unsupported parameters (k=%d must be 19, kp=%d must be 12 or 13)", P.k, kp);
         return AF_ERR_ARG;
     }
+    // a record stores score*2 + strand in 16 bits; the best possible score is A * read length
+    if ((int64_t)2 * P.A * AF_MAX_READ_LEN + 1 > 65535 || P.B > 32767 || P.clip5 < 0 || P.clip3 < 0) {
+        af_set_error("af_index_build: match score A=%d too large (2*A*%d+1 must fit 16 bits), or negative clip penalties", P.A, AF_MAX_READ_LEN);
+        return AF_ERR_ARG;
+    }
     af_index *idx = new af_index();
     idx->P = P;
     idx->kp = kp;

@@ -98,6 +98,7 @@ struct af_dev_index {
     int anchor_has_n;
     int pad_byte;
     int num_sms;
+    bool saturated;      // many filter buckets overflowed (long anchor): flagged reads take the exact k_verify route
 };
 
 // ------------------------------------------------------------------------------------------
@@ -208,6 +209,7 @@ __device__ __forceinline__ uint32_t tile_valid_mask(long long tile, long long n_
 }
 
 static const int SCAN_LOCAL_CHUNKS = 64;
+static const int RQ_CAP = 96;   // per-warp refine queue: up to 31 waiting + the 64 reads of one tile
 
 // flags[tile] = (ballot of mate-1 flags, ballot of mate-2 flags), lanes past n_pairs cleared.
 // The number of flagged reads per compaction chunk is accumulated in shared memory (cc_local,
@@ -233,19 +235,99 @@ __device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long 
     }
 }
 
+// ---- in-scan refinement (RQ = true) --------------------------------------------------------
+// 1.8 % of the reads pass the filter, 86 % of them because one sampled k'-mer really is an anchor
+// k'-mer by chance.  A second look removes nearly all of them (af_neighbour_ok: a >= k match
+// around a sample also holds the k'-mer 4 bases to its left or right; 362 k -> 16 k reads per
+// 10 M pairs) but costs a branch per sample, which halves the speed of the probe loop when it is
+// taken lane by lane.  So the scan only QUEUES the flagged reads' ids (per warp, shared memory)
+// and, whenever 32 are waiting, the warp runs the second look for 32 flagged reads at once:
+// dense lanes, the reads' quads fetched again from L2 (they were streamed a few microseconds
+// ago), ~2 % of the scan's instructions.  What survives is OR-ed into the flag words, so the
+// stage that used to re-fetch 362 k scattered reads from HBM (k_verify_smem + k_sel_scatter,
+// 45 us) disappears: the survivors go straight to k_extend.
+template <int W, int KP, int Q>
+__device__ __forceinline__ void refine_pass(const uint4 *__restrict__ packed, uint32_t rid, bool have, int nprobe,
+                                            const uint32_t *filt, uint32_t fmul, uint32_t nb,
+                                            uint32_t *__restrict__ flags, uint32_t *__restrict__ chunk_counts) {
+    const uint32_t pair = rid >> 1, mate = rid & 1u;
+    const uint4 *src = packed + (size_t)(pair >> 5) * (Q * 32) + (pair & 31);
+    uint32_t w[W + 1];
+#pragma unroll
+    for (int t = 0; t <= W; t++) w[t] = 0u;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (have) v = __ldg(src + q * 32);
+        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int wi = 4 * q + e;
+            if (wi < W) w[wi] = mate ? w[wi] : vv[e];
+            else if (wi < 2 * W) w[wi - W] = mate ? vv[e] : w[wi - W];
+        }
+    }
+    const uint32_t r = af_scan_read<W, KP, 0, W + 1, true>(w, nprobe, filt, fmul, nb);
+    if (have && r) {
+        atomicOr(&flags[(size_t)(pair >> 5) * 2 + mate], 1u << (pair & 31));
+        atomicAdd(&chunk_counts[(pair >> 5) / CB_PER_BLOCK], 1u);
+    }
+}
+
+template <int W, int KP, int Q>
+__device__ __forceinline__ void rq_drain(uint32_t *q, int &qn, int lane, int threshold, const uint4 *__restrict__ packed,
+                                         int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
+                                         uint32_t *__restrict__ flags, uint32_t *__restrict__ chunk_counts) {
+    while (qn >= threshold && qn > 0) {                      // warp-uniform
+        __syncwarp();                                        // queue entries and the zeroed flag words of this warp are visible
+        const bool have = lane < qn;
+        const uint32_t rid = have ? q[lane] : 0u;
+        const uint32_t m1 = 32 + lane < qn ? q[32 + lane] : 0u, m2 = 64 + lane < qn ? q[64 + lane] : 0u;
+        __syncwarp();
+        q[lane] = m1; q[32 + lane] = m2;
+        __syncwarp();
+        qn = qn > 32 ? qn - 32 : 0;
+        refine_pass<W, KP, Q>(packed, rid, have, nprobe, filt, fmul, nb, flags, chunk_counts);
+    }
+}
+
+template <int W, int KP, int Q>
+__device__ __forceinline__ void scan_tile_rq(const uint32_t (&w)[4 * Q], long long tile, long long n_pairs, int lane,
+                                             int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
+                                             const uint4 *__restrict__ packed, uint32_t *__restrict__ flags,
+                                             uint32_t *__restrict__ chunk_counts, uint32_t *q, int &qn, uint32_t &nflag) {
+    uint32_t a1 = af_scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
+    uint32_t a2 = af_scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
+    const uint32_t vm = tile_valid_mask(tile, n_pairs);
+    const uint32_t b1 = __ballot_sync(FULL, a1 != 0) & vm, b2 = __ballot_sync(FULL, a2 != 0) & vm;
+    if (lane == 0) reinterpret_cast<uint2 *>(flags)[tile] = make_uint2(0u, 0u);   // refined bits are OR-ed in later
+    if (b1 | b2) {
+        const uint32_t lt = (1u << lane) - 1u, rid = (uint32_t)(tile * 32 + lane) * 2u;
+        if ((b1 >> lane) & 1u) q[qn + __popc(b1 & lt)] = rid;
+        qn += __popc(b1);
+        if ((b2 >> lane) & 1u) q[qn + __popc(b2 & lt)] = rid + 1u;
+        qn += __popc(b2);
+        nflag += __popc(b1) + __popc(b2);
+        rq_drain<W, KP, Q>(q, qn, lane, 32, packed, nprobe, filt, fmul, nb, flags, chunk_counts);
+    }
+}
+
 // Persistent kernel, one CTA per SM: the anchor filter is staged into shared memory once, then
 // the CTA's warps walk its contiguous range of tiles (32 pairs per tile, one pair per lane, all
 // of it in registers).
 // PF = true (<= 768 threads): the loads of the warp's NEXT tile are issued before the current
 // tile is scanned (register double buffer), so HBM latency overlaps the probes of the same warp.
 // PF = false (<= 1024 threads, 64 registers): latency is hidden by occupancy alone.
-template <int W, int KP, int MAXT, bool PF>
+// RQ = true: flags[] receives the REFINED flag words (see refine_pass), chunk_counts their per-chunk
+// counts and counts[AF_CNT_FLAGGED] the number of reads that passed the plain filter.
+template <int W, int KP, int MAXT, bool PF, bool RQ>
 __global__ void __launch_bounds__(MAXT, 1)
 k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pairs, int nprobe,
             const uint32_t *__restrict__ g_filter, uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags,
-            uint32_t *__restrict__ chunk_counts) {
+            uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ counts) {
     extern __shared__ __align__(128) uint32_t filt[];
     __shared__ uint32_t cc_local[SCAN_LOCAL_CHUNKS];
+    __shared__ uint32_t rq[RQ ? (MAXT / 32) * RQ_CAP : 1];
     constexpr int Q = (2 * W + 3) / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const long long t_begin = n_tiles * blockIdx.x / gridDim.x, t_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
@@ -253,6 +335,13 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     const long long stride = nwarps;
     long long tile = t_begin + warp;
     if (threadIdx.x < SCAN_LOCAL_CHUNKS) cc_local[threadIdx.x] = 0;
+    uint32_t *q = rq + (RQ ? warp * RQ_CAP : 0);
+    int qn = 0;
+    uint32_t nflag = 0;
+    auto do_tile = [&](const uint32_t (&w)[4 * Q], long long t) {
+        if constexpr (RQ) scan_tile_rq<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, packed, (uint32_t *)flags, chunk_counts, q, qn, nflag);
+        else scan_tile<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
+    };
     if constexpr (PF) {
         uint32_t wa[4 * Q], wb[4 * Q];
         if (tile < t_end) load_tile<Q>(wa, packed, tile, lane);   // in flight while the filter is staged
@@ -261,11 +350,11 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
         while (tile < t_end) {
             const long long t2 = tile + stride;
             if (t2 < t_end) load_tile<Q>(wb, packed, t2, lane);
-            scan_tile<W, KP, Q>(wa, tile, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
+            do_tile(wa, tile);
             if (t2 >= t_end) break;
             const long long t3 = t2 + stride;
             if (t3 < t_end) load_tile<Q>(wa, packed, t3, lane);
-            scan_tile<W, KP, Q>(wb, t2, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
+            do_tile(wb, t2);
             tile = t3;
         }
     } else {
@@ -274,16 +363,21 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
         for (; tile < t_end; tile += stride) {
             uint32_t w[4 * Q];
             load_tile<Q>(w, packed, tile, lane);
-            scan_tile<W, KP, Q>(w, tile, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
+            do_tile(w, tile);
         }
     }
-    if (chunk_counts) {
+    if constexpr (RQ) {
+        rq_drain<W, KP, Q>(q, qn, lane, 1, packed, nprobe, filt, fmul, nb, (uint32_t *)flags, chunk_counts);
+        if (lane == 0 && nflag) atomicAdd(&cc_local[0], nflag);
+        __syncthreads();
+        if (threadIdx.x == 0 && cc_local[0]) atomicAdd(&counts[AF_CNT_FLAGGED], cc_local[0]);
+    } else if (chunk_counts) {
         __syncthreads();
         if (threadIdx.x < SCAN_LOCAL_CHUNKS && cc_local[threadIdx.x]) atomicAdd(&chunk_counts[chunk0 + threadIdx.x], cc_local[threadIdx.x]);
     }
 }
 
-static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1;
+static int g_scan_threads = 768, g_fused = 0, g_middle = 11, g_verify_smem = 1;
 // tuning knobs.  Scan variant (mode 0/3): register double buffer under an 85-register cap, up to 768
 // threads = 24 warps per SM (a 512-thread / 128-register variant and a 1024-thread variant without
 // prefetch measured the same and were dropped to keep the build short).
@@ -295,10 +389,14 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     // against the table and the anchor), 8 = nothing (every flagged read gets a warp of k_extend; for
     // experiments with a scan built with the neighbour test, af_scan_read<..., REFINE = true>)
     if (mode == 7 || mode == 8) { g_middle = mode == 8 ? 0 : 7; return AF_OK; }
+    // mode 11 (default): the second look at flagged reads happens inside the scan (refine queue, see
+    // refine_pass) and the survivors go straight to k_extend; an index whose filter is saturated
+    // (long anchor) still takes the k_verify route, where the exact test does the sorting out
+    if (mode == 11) { g_middle = 11; return AF_OK; }
     // modes 9 / 10: k_verify_smem (9, default: membership from a half-size filter in shared memory) or
     // k_verify (10: membership from the L2-resident bitmap)
     if (mode == 9 || mode == 10) { g_verify_smem = mode == 9; return AF_OK; }
-    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off), 7/8 or 9/10"); return AF_ERR_ARG; }
+    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off), 7/8/11 or 9/10"); return AF_ERR_ARG; }
     const int maxt = 768;
     if (threads_per_block == 0) threads_per_block = maxt;
     if (threads_per_block < 64 || threads_per_block > maxt || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..%d, multiple of 32", maxt); return AF_ERR_ARG; }
@@ -306,21 +404,21 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     return AF_OK;
 }
 
-template <int W, int KP, int MAXT, bool PF>
+template <int W, int KP, int MAXT, bool PF, bool RQ>
 static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
-                       uint32_t *chunk_counts, cudaStream_t st) {
+                       uint32_t *chunk_counts, uint32_t *counts, cudaStream_t st) {
     size_t smem = (size_t)d->nb * 4;
     static bool attr_set[64] = {false};  // per device
     if (!attr_set[d->device & 63]) {
-        int rc = allow_full_smem(k_seed_scan<W, KP, MAXT, PF>, nullptr);      // the filter + a few static words (chunk counters, mbarrier)
+        int rc = allow_full_smem(k_seed_scan<W, KP, MAXT, PF, RQ>, nullptr);  // the filter + a few static words (chunk counters, mbarrier, refine queues)
         if (rc) return rc;
         attr_set[d->device & 63] = true;
     }
     int nwarps = g_scan_threads / 32;
     long long want = (n_tiles + nwarps - 1) / nwarps;
     int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
-    k_seed_scan<W, KP, MAXT, PF><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
-                                                                     d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts);
+    k_seed_scan<W, KP, MAXT, PF, RQ><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
+                                                                         d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts, counts);
     g_launches++;
     AF_CUDA(cudaGetLastError());
     return AF_OK;
@@ -328,14 +426,15 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
 
 template <int W, int KP>
 static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
-                            uint32_t *cc, cudaStream_t st) {
-    return launch_scan<W, KP, AF_SCAN_BOUND, true>(d, b, n_tiles, nprobe, flags, cc, st);
+                            uint32_t *cc, uint32_t *counts, bool rq, cudaStream_t st) {
+    if (rq) return launch_scan<W, KP, AF_SCAN_BOUND, true, true>(d, b, n_tiles, nprobe, flags, cc, counts, st);
+    return launch_scan<W, KP, AF_SCAN_BOUND, true, false>(d, b, n_tiles, nprobe, flags, cc, counts, st);
 }
 
-#define AF_SCAN_CASE(WW)                                                                       \
-    case WW:                                                                                   \
-        return kp == 12 ? launch_scan_mode<WW, 12>(d, b, n_tiles, nprobe, flags, cc, st)       \
-                        : launch_scan_mode<WW, 13>(d, b, n_tiles, nprobe, flags, cc, st);
+#define AF_SCAN_CASE(WW)                                                                                 \
+    case WW:                                                                                             \
+        return kp == 12 ? launch_scan_mode<WW, 12>(d, b, n_tiles, nprobe, flags, cc, counts, rq, st)     \
+                        : launch_scan_mode<WW, 13>(d, b, n_tiles, nprobe, flags, cc, counts, rq, st);
 
 static int batch_check(const af_dev_index *d, const af_batch_t *b, af_layout_t *lay) {
     if (!d || !b) { af_set_error("null index or batch"); return AF_ERR_ARG; }
@@ -348,7 +447,8 @@ static int batch_check(const af_dev_index *d, const af_batch_t *b, af_layout_t *
     return AF_OK;
 }
 
-static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *flags, uint32_t *cc, cudaStream_t st) {
+static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *flags, uint32_t *cc, uint32_t *counts, bool rq,
+                          cudaStream_t st) {
     af_layout_t lay;
     int rc = batch_check(d, b, &lay);
     if (rc) return rc;
@@ -370,7 +470,7 @@ static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *
 
 extern "C" int af_seed_scan(const af_dev_index_t *d, const af_batch_t *batch, uint32_t *d_flags, void *stream) {
     AF_CUDA(cudaSetDevice(d ? d->device : 0));
-    return seed_scan_impl(d, batch, d_flags, nullptr, (cudaStream_t)stream);
+    return seed_scan_impl(d, batch, d_flags, nullptr, nullptr, false, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1367,10 +1467,19 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
         prof_mark(&ev, st);
         g_launches -= 2;                                    // this path has 4 kernels, the code below counts 5 more
     } else {
-    rc = seed_scan_impl(d, b, flags, cc1, st);
+    const bool rq = g_middle == 11 && !d->saturated;
+    rc = seed_scan_impl(d, b, flags, cc1, d_counts, rq, st);
     if (rc) return rc;
     prof_span(ev, st, ST_SCAN);
     prof_mark(&ev, st);
+    if (rq) {
+        // the flag words already hold the refined survivors: one compaction, then k_extend
+        k_flag_scatter<<<(int)(w.nch1 < (uint32_t)scatter_grid ? w.nch1 : scatter_grid), CB_THREADS, 0, st>>>(
+            (const uint2 *)flags, lay.n_tiles, cc1, w.nch1, cand2, (uint32_t)cand_cap, d_counts, AF_CNT_SEEDED, -1);
+        prof_span(ev, st, ST_COMPACT1);
+        prof_mark(&ev, st);
+        g_launches -= 2;                                    // 4 kernels on this path
+    } else
     if (g_middle == 0) {
         // the flagged reads go straight to k_extend (a flagged read without a seeded diagonal yields no record)
         k_flag_scatter<<<(int)(w.nch1 < (uint32_t)scatter_grid ? w.nch1 : scatter_grid), CB_THREADS, 0, st>>>(
@@ -1467,6 +1576,7 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     d->device = device; d->P = idx->P; d->kp = idx->kp; d->stride = idx->stride; d->G = idx->G;
     d->fmul = idx->fmul; d->nb = idx->nb; d->tmask = idx->tmask; d->pad_byte = idx->pad_byte;
     d->num_sms = prop.multiProcessorCount;
+    d->saturated = (long long)idx->n_overflow * 200 > (long long)idx->nb;
     d->d_filter = nullptr; d->d_table = nullptr; d->d_anchor = nullptr; d->d_member = nullptr;
     d->d_apk[0] = d->d_apk[1] = nullptr;
     d->anchor_has_n = idx->anchor_has_n;

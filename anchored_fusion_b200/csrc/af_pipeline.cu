@@ -126,8 +126,28 @@ static int collect(af_pipeline *p, Slot &s, af_hit_t *h_hits, int64_t hits_cap, 
     return AF_OK;
 }
 
+// After an error some slots may still have copies and kernels in flight that read the caller's host
+// buffers and would otherwise be collected -- with the old run's read-id rebase -- by the next run.
+// Wait for them and forget their results.
+static void drain_all(af_pipeline *p) {
+    for (Slot &s : p->slots) {
+        if (s.st) cudaStreamSynchronize(s.st);
+        s.busy = false;
+    }
+}
+
+static int pipeline_run_impl(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h_hits, int64_t hits_cap,
+                             int64_t *n_hits_out, int64_t *n_flagged_out);
+
 extern "C" int af_pipeline_run(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h_hits, int64_t hits_cap,
                                int64_t *n_hits_out, int64_t *n_flagged_out) {
+    const int rc = pipeline_run_impl(p, hb, h_hits, hits_cap, n_hits_out, n_flagged_out);
+    if (rc != AF_OK && p) drain_all(p);        // keeps af_last_error() of the failing call
+    return rc;
+}
+
+static int pipeline_run_impl(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h_hits, int64_t hits_cap,
+                             int64_t *n_hits_out, int64_t *n_flagged_out) {
     if (!p || !hb || !n_hits_out || (hits_cap > 0 && !h_hits)) { af_set_error("af_pipeline_run: null argument"); return AF_ERR_ARG; }
     if (hb->max_read_len != p->max_read_len) { af_set_error("af_pipeline_run: batch max_read_len %d, pipeline built for %d", hb->max_read_len, p->max_read_len); return AF_ERR_ARG; }
     if (hb->n_pairs >= (1ll << 31)) { af_set_error("af_pipeline_run: a host batch holds at most 2^31-1 pairs"); return AF_ERR_ARG; }

@@ -22,12 +22,71 @@ class Params(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("k", "A", "B", "clip5", "clip3", "T", "X")]
 
 
+_SYNTH_SO = os.path.join(_HERE, "libaf_synth.so")
+_SYNTH_SRC = os.path.join(_HERE, "af_synth.cpp")
+_SYNTH_HDR = os.path.join(_HERE, "..", "anchored_fusion_b200", "csrc", "af_common.h")
+
+
 def build(force=False):
-    """Compile af_oracle.c with gcc (no reference sources involved)."""
+    """Compile af_oracle.c with gcc (no reference sources involved) and the CPU arm's pair generator."""
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libaf_oracle.so"],
-                              stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libaf_oracle.so"], stdout=subprocess.DEVNULL, env=env)
+    if force or not os.path.exists(_SYNTH_SO) or os.path.getmtime(_SYNTH_SO) < max(os.path.getmtime(_SYNTH_SRC), os.path.getmtime(_SYNTH_HDR)):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libaf_synth.so"], stdout=subprocess.DEVNULL, env=env)
     return _SO
+
+
+class Synth(ctypes.Structure):
+    """af_synth_t (include/anchored_fusion.h): the seeded generator's description."""
+    _fields_ = [("seed", ctypes.c_uint64), ("ref_len", ctypes.c_int64), ("anchor_start", ctypes.c_int64),
+                ("anchor_len", ctypes.c_int32), ("read_len", ctypes.c_int32), ("frag_mean", ctypes.c_int32),
+                ("frag_sd", ctypes.c_int32), ("sub_ppm", ctypes.c_uint32), ("fusion_ppm", ctypes.c_uint32),
+                ("n_ppm", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+_synth = None
+
+
+def _synth_lib():
+    global _synth
+    if _synth is None:
+        build()
+        _synth = ctypes.CDLL(_SYNTH_SO)
+        _synth.afo_synth_anchor.restype = ctypes.c_int
+        _synth.afo_synth_anchor.argtypes = [ctypes.POINTER(Synth), ctypes.c_void_p]
+        _synth.afo_synth_reads.restype = ctypes.c_int
+        _synth.afo_synth_reads.argtypes = [ctypes.POINTER(Synth), ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_int64, ctypes.c_int]
+    return _synth
+
+
+def synth_spec(seed=1, ref_len=10_000_000, anchor_start=1_000_000, anchor_len=6783, read_len=150, frag_mean=300,
+               frag_sd=30, sub_ppm=0, fusion_ppm=0, n_ppm=0):
+    return Synth(seed, ref_len, anchor_start, anchor_len, read_len, frag_mean, frag_sd, sub_ppm, fusion_ppm, n_ppm, 0)
+
+
+def as_synth(spec):
+    """Any object with af_synth_t's fields (e.g. the product's Synth structure) -> this module's Synth."""
+    return Synth(*[getattr(spec, n) for n, _ in Synth._fields_])
+
+
+def synth_anchor(spec):
+    spec = as_synth(spec)
+    buf = ctypes.create_string_buffer(spec.anchor_len)
+    assert _synth_lib().afo_synth_anchor(ctypes.byref(spec), ctypes.cast(buf, ctypes.c_void_p)) == 0
+    return buf.raw[: spec.anchor_len]
+
+
+def synth_reads(spec, first_pair, n_pairs, threads=1, out=None):
+    """(2*n_pairs, read_len) uint8 codes, mates interleaved, of the seeded generator the GPU arm uses."""
+    spec = as_synth(spec)
+    reads = out if out is not None else np.empty((2 * n_pairs, spec.read_len), dtype=np.uint8)
+    assert reads.shape[0] >= 2 * n_pairs and reads.strides[1] == 1
+    assert _synth_lib().afo_synth_reads(ctypes.byref(spec), first_pair, n_pairs, reads.ctypes.data, reads.strides[0], threads) == 0
+    return reads[: 2 * n_pairs]
 
 
 _lib = None

@@ -91,6 +91,31 @@ def test_synthetic_pairs_match_oracle(af, read_len, kp, n):
     assert hits_equal(hits, want)
 
 
+@pytest.mark.parametrize("mode", [7, 8])
+def test_other_middle_stages_give_the_same_records(af, mode):
+    """af_seed_scan_config(0, 7): flagged reads go through k_verify_smem (the route a saturated filter takes
+    by itself); (0, 8): every flagged read goes to k_extend.  Default is 11, the refinement inside the scan."""
+    from oracle import oracle
+    from anchored_fusion_b200._lib import check, lib
+    spec = af.synth_spec(seed=77, ref_len=300_000, anchor_start=100_000, anchor_len=8000, read_len=150,
+                         sub_ppm=15_000, fusion_ppm=30_000)
+    anchor = af.synth_anchor(spec)
+    index = af.AnchorIndex(anchor)
+    eng = af.Anchorer(index, 0)
+    n = 150_000
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    want = oracle.anchor_reads(oracle.encode(anchor), _interleave(m1, m2), threads=8)
+    dev = af.synth_pairs_device(spec, 0, n, index.pad_byte, 0)
+    ref, st_ref = eng.anchor(dev)
+    check(lib().af_seed_scan_config(0, mode))
+    try:
+        hits, st = eng.anchor(dev)
+    finally:
+        check(lib().af_seed_scan_config(0, 11))
+    assert hits_equal(ref, want) and hits_equal(hits, want)
+    assert st["flagged"] == st_ref["flagged"]            # both count the reads that pass the plain filter
+
+
 def test_variable_length_reads_with_n(af):
     """ragged lengths (19..150), Ns (mismatch; no seed across an N), reads off both anchor ends."""
     from oracle import oracle
@@ -245,7 +270,7 @@ def test_pipeline_equals_resident_path_and_counts_launches(af):
     before = lib().af_kernel_launches()
     hits2, _ = eng.anchor_host(host, slot_pairs=65_536, n_slots=3)
     assert hits_equal(hits, hits2)
-    assert lib().af_kernel_launches() - before == 6 * ((n + 65_535) // 65_536)
+    assert lib().af_kernel_launches() - before == 4 * ((n + 65_535) // 65_536)   # scan(+refine), compaction, extend, compaction
 
 
 def test_fused_scan_verify_kernel_gives_the_same_records(af, bundled):
@@ -274,6 +299,28 @@ def test_fused_scan_verify_kernel_gives_the_same_records(af, bundled):
         check(lib().af_seed_scan_config(0, 5))
 
 
+def test_pipeline_retry_after_a_capacity_error_returns_clean_records(af):
+    """A too small host hit buffer fails with AF_ERR_CAPACITY; the natural retry with a larger buffer on the
+    same pipeline must not see anything of the failed run (its in-flight slots are drained)."""
+    from oracle import oracle
+    spec = af.synth_spec(seed=19, ref_len=200_000, anchor_start=50_000, anchor_len=6783, read_len=150,
+                         sub_ppm=10_000, fusion_ppm=20_000)
+    anchor = af.synth_anchor(spec)
+    index = af.AnchorIndex(anchor)
+    eng = af.Anchorer(index, 0)
+    n = 200_000
+    dev = af.synth_pairs_device(spec, 0, n, index.pad_byte, 0)
+    host = af.PackedBatch(dev.packed.cpu().numpy().view(np.uint32), n, 150, 150)
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    want = oracle.anchor_reads(oracle.encode(anchor), _interleave(m1, m2), threads=8)
+    assert len(want) > 2000
+    small = np.zeros(len(want) // 3, dtype=af.HIT_DTYPE)         # overflows in the second or third chunk
+    with pytest.raises(af.AnchoredFusionError):
+        eng.anchor_host(host, slot_pairs=32_768, n_slots=3, hits_out=small)
+    hits, _ = eng.anchor_host(host, slot_pairs=32_768, n_slots=3)
+    assert hits_equal(hits, want)
+
+
 def test_capacity_overflow_is_reported_not_dropped(af):
     spec = af.synth_spec(seed=4, ref_len=20_000, anchor_start=1_000, anchor_len=15_000, read_len=150)
     index = af.AnchorIndex(af.synth_anchor(spec))
@@ -283,11 +330,12 @@ def test_capacity_overflow_is_reported_not_dropped(af):
         eng.anchor(dev, cand_cap=1000, hits_cap=1000)
 
 
-@pytest.mark.parametrize("modes", [(), (4,), (10,)])
+@pytest.mark.parametrize("modes", [(), (7,), (4,), (7, 10), (8,)])
 def test_kernels_stay_inside_their_buffers(af, modes):
     """compute-sanitizer is not available on this pool, so out-of-bounds WRITES are looked for directly:
     workspace, hit list, counters and the packed batch sit between 64 KB canary zones, which must come
-    back untouched (default path, the fused scan+verify kernel, the bitmap verify kernel), with a pair
+    back untouched (default path = scan with the in-kernel refinement; the separate k_verify_smem route; the
+    fused scan+verify kernel; the bitmap verify kernel; no middle stage at all), with a pair
     count that is not a multiple of anything and capacities small enough to be hit exactly."""
     import ctypes
     import torch
@@ -325,6 +373,7 @@ def test_kernels_stay_inside_their_buffers(af, modes):
     finally:
         check(lib().af_seed_scan_config(0, 5))
         check(lib().af_seed_scan_config(0, 9))
+        check(lib().af_seed_scan_config(0, 11))
     c = counts.view(torch.int32).cpu().numpy()
     assert c[2] == 0 and c[1] == len(ref_hits)
     got = hits.cpu().numpy().view(af.HIT_DTYPE)

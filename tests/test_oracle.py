@@ -169,3 +169,16 @@ def test_c_oracle_equals_bruteforce_with_other_parameters_and_repeats():
         assert len(got) > 60, over
         for i, r in enumerate(reads):
             assert bruteforce.anchor_read(list(r), list(a), P) == got.get(i), (over, i)
+
+
+def test_cpu_arm_generator_equals_the_product_host_generator():
+    """oracle/af_synth.cpp (what bench.py's reference arm and the full-size parity tests feed the oracle) and
+    the product's af_synth_pairs_host are the same pure function of (seed, pair index), Ns included."""
+    import anchored_fusion_b200 as af
+    from oracle import oracle
+    spec = af.synth_spec(seed=3, ref_len=200_000, anchor_start=50_000, anchor_len=6783, read_len=150, sub_ppm=10_000,
+                         fusion_ppm=20_000, n_ppm=700)
+    m1, m2 = af.synth_pairs_host(spec, 987, 3000)
+    r = oracle.synth_reads(spec, 987, 3000, threads=3)
+    assert (r[0::2] == m1).all() and (r[1::2] == m2).all()
+    assert oracle.synth_anchor(spec) == af.synth_anchor(spec)
