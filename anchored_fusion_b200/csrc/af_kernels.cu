@@ -244,8 +244,13 @@ __device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long 
 // and, whenever 32 are waiting, the warp runs the second look for 32 flagged reads at once:
 // dense lanes, the reads' quads fetched again from L2 (they were streamed a few microseconds
 // ago), ~2 % of the scan's instructions.  What survives is OR-ed into the flag words, so the
-// stage that used to re-fetch 362 k scattered reads from HBM (k_verify_smem + k_sel_scatter,
-// 45 us) disappears: the survivors go straight to k_extend.
+// stage that re-fetches 362 k scattered reads from HBM (k_verify_smem + k_sel_scatter, 45 us)
+// disappears: the survivors go straight to k_extend.
+// MEASURED (B200, 10 M pairs): the scan goes from 186 us to 233 us -- 8.8 % more instructions, 22 %
+// more DRAM reads (the re-fetched quads mostly miss L2), and the warps that sit in a refinement pass
+// leave the other warps of their scheduler short of latency cover (LSU pipe 92 % -> 79 % busy).  The
+// step does not get shorter (0.306 vs 0.299 ms) and the scan's roofline fraction drops to 0.50, so
+// this stays an option (af_seed_scan_config(0, 11)) and the separate verify stage is the default.
 template <int W, int KP, int Q>
 __device__ __forceinline__ void refine_pass(const uint4 *__restrict__ packed, uint32_t rid, bool have, int nprobe,
                                             const uint32_t *filt, uint32_t fmul, uint32_t nb,
@@ -377,7 +382,7 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     }
 }
 
-static int g_scan_threads = 768, g_fused = 0, g_middle = 11, g_verify_smem = 1;
+static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1;
 // tuning knobs.  Scan variant (mode 0/3): register double buffer under an 85-register cap, up to 768
 // threads = 24 warps per SM (a 512-thread / 128-register variant and a 1024-thread variant without
 // prefetch measured the same and were dropped to keep the build short).
@@ -389,9 +394,9 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     // against the table and the anchor), 8 = nothing (every flagged read gets a warp of k_extend; for
     // experiments with a scan built with the neighbour test, af_scan_read<..., REFINE = true>)
     if (mode == 7 || mode == 8) { g_middle = mode == 8 ? 0 : 7; return AF_OK; }
-    // mode 11 (default): the second look at flagged reads happens inside the scan (refine queue, see
-    // refine_pass) and the survivors go straight to k_extend; an index whose filter is saturated
-    // (long anchor) still takes the k_verify route, where the exact test does the sorting out
+    // mode 11 (experiment, measured slower: profiles/r02_scan_refine_queue_ncu.md): the second look at flagged
+    // reads happens inside the scan (refine queue, see refine_pass) and the survivors go straight to k_extend;
+    // an index whose filter is saturated (long anchor) still takes the k_verify route
     if (mode == 11) { g_middle = 11; return AF_OK; }
     // modes 9 / 10: k_verify_smem (9, default: membership from a half-size filter in shared memory) or
     // k_verify (10: membership from the L2-resident bitmap)

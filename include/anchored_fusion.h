@@ -162,10 +162,9 @@ int af_fastq_record(const af_fastq_t *fq, int64_t read_id, const char **name, in
 
 /* ---- the hot path on one GPU: replaces `bwa mem -M | samtools view -F 772` -------------- */
 size_t af_workspace_bytes(int64_t n_pairs, int64_t cand_cap);
-/* seed scan (with the in-kernel second look at flagged reads) -> compaction -> extend -> compaction:
- * 4 kernels, all on `stream`, no host sync (an index whose filter is saturated by a long anchor takes
- * 6: scan -> compaction -> verify -> compaction -> extend -> compaction).  counts[AF_CNT_FLAGGED] reads
- * passed the plain filter, counts[AF_CNT_SEEDED] were handed to the extension,
+/* seed scan -> compaction -> verify -> compaction -> extend -> compaction: 6 kernels, all on `stream`,
+ * no host sync.  counts[AF_CNT_FLAGGED] reads passed the scan's filter, counts[AF_CNT_SEEDED] were handed
+ * to the extension (with the default verify stage: they hold a true >= k-base exact match),
  * counts[AF_CNT_HITS] are anchored (score >= T).
  * d_hits[0..counts[AF_CNT_HITS]) come back ordered by read_id. */
 int af_anchor_batch(const af_dev_index_t *d, const af_batch_t *batch, void *workspace, size_t workspace_bytes,
@@ -179,7 +178,7 @@ int af_debug_scan_pair(const af_index_t *idx, const uint32_t *words, int32_t wor
                        int32_t with_neighbour_test, int32_t *flag1, int32_t *flag2);
 /* tuning knobs.  mode 0/3: threads_per_block of the scan (64..768, 0 = default).  Other modes ignore
  * threads_per_block: 4/5 fused scan+verify kernel on/off; what stands between scan and extension --
- * 11 (default) second look inside the scan, 7 k_verify, 8 nothing; 9/10 k_verify_smem / k_verify. */
+ * 7 (default) k_verify, 11 second look inside the scan (refine queue), 8 nothing; 9/10 k_verify_smem / k_verify. */
 int af_seed_scan_config(int32_t threads_per_block, int32_t mode);
 int64_t af_kernel_launches(void); /* kernels this library has launched since it was loaded */
 /* per-stage device time of af_anchor_batch, CUDA events on the launching stream: begin, run,

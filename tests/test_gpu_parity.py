@@ -91,10 +91,11 @@ def test_synthetic_pairs_match_oracle(af, read_len, kp, n):
     assert hits_equal(hits, want)
 
 
-@pytest.mark.parametrize("mode", [7, 8])
+@pytest.mark.parametrize("mode", [11, 8])
 def test_other_middle_stages_give_the_same_records(af, mode):
-    """af_seed_scan_config(0, 7): flagged reads go through k_verify_smem (the route a saturated filter takes
-    by itself); (0, 8): every flagged read goes to k_extend.  Default is 11, the refinement inside the scan."""
+    """af_seed_scan_config(0, 11): the second look at flagged reads happens inside the scan (refine queue) and
+    the survivors go straight to k_extend; (0, 8): every flagged read goes to k_extend.  Default is 7,
+    k_verify_smem between scan and extension."""
     from oracle import oracle
     from anchored_fusion_b200._lib import check, lib
     spec = af.synth_spec(seed=77, ref_len=300_000, anchor_start=100_000, anchor_len=8000, read_len=150,
@@ -111,7 +112,7 @@ def test_other_middle_stages_give_the_same_records(af, mode):
     try:
         hits, st = eng.anchor(dev)
     finally:
-        check(lib().af_seed_scan_config(0, 11))
+        check(lib().af_seed_scan_config(0, 7))
     assert hits_equal(ref, want) and hits_equal(hits, want)
     assert st["flagged"] == st_ref["flagged"]            # both count the reads that pass the plain filter
 
@@ -270,7 +271,7 @@ def test_pipeline_equals_resident_path_and_counts_launches(af):
     before = lib().af_kernel_launches()
     hits2, _ = eng.anchor_host(host, slot_pairs=65_536, n_slots=3)
     assert hits_equal(hits, hits2)
-    assert lib().af_kernel_launches() - before == 4 * ((n + 65_535) // 65_536)   # scan(+refine), compaction, extend, compaction
+    assert lib().af_kernel_launches() - before == 6 * ((n + 65_535) // 65_536)
 
 
 def test_fused_scan_verify_kernel_gives_the_same_records(af, bundled):
@@ -330,12 +331,12 @@ def test_capacity_overflow_is_reported_not_dropped(af):
         eng.anchor(dev, cand_cap=1000, hits_cap=1000)
 
 
-@pytest.mark.parametrize("modes", [(), (7,), (4,), (7, 10), (8,)])
+@pytest.mark.parametrize("modes", [(), (11,), (4,), (10,), (8,)])
 def test_kernels_stay_inside_their_buffers(af, modes):
     """compute-sanitizer is not available on this pool, so out-of-bounds WRITES are looked for directly:
     workspace, hit list, counters and the packed batch sit between 64 KB canary zones, which must come
-    back untouched (default path = scan with the in-kernel refinement; the separate k_verify_smem route; the
-    fused scan+verify kernel; the bitmap verify kernel; no middle stage at all), with a pair
+    back untouched (default path; the scan with the in-kernel refinement queue; the fused scan+verify kernel;
+    the bitmap verify kernel; no middle stage at all), with a pair
     count that is not a multiple of anything and capacities small enough to be hit exactly."""
     import ctypes
     import torch
@@ -373,7 +374,7 @@ def test_kernels_stay_inside_their_buffers(af, modes):
     finally:
         check(lib().af_seed_scan_config(0, 5))
         check(lib().af_seed_scan_config(0, 9))
-        check(lib().af_seed_scan_config(0, 11))
+        check(lib().af_seed_scan_config(0, 7))
     c = counts.view(torch.int32).cpu().numpy()
     assert c[2] == 0 and c[1] == len(ref_hits)
     got = hits.cpu().numpy().view(af.HIT_DTYPE)
