@@ -65,6 +65,13 @@ SIGNATURES = {
                                      P(c_i64), P(c_i32)]),
     "af_unpack_read": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i32, c_vp]),
     "af_fastq_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, P(c_vp)]),
+    "af_fastq_open_threads": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, c_i32, P(c_vp)]),
+    "af_fastq_open_multi": (ctypes.c_int, [P(ctypes.c_char_p), P(ctypes.c_char_p), c_i32, c_i32, P(c_vp)]),
+    "af_fastq_threads": (ctypes.c_int, [c_vp]),
+    "af_fastq_skip": (ctypes.c_int, [c_vp, c_i64, P(c_i64)]),
+    "af_fastq_records": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, P(c_i64)]),
+    "af_fastq_file_starts": (ctypes.c_int, [c_vp, c_vp, c_i32]),
+    "af_fastq_batch_first_pair": (c_i64, [c_vp]),
     "af_fastq_peek": (ctypes.c_int, [ctypes.c_char_p, c_i32, P(c_i32)]),
     "af_fastq_close": (None, [c_vp]),
     "af_fastq_next": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64), P(c_i32),
@@ -81,7 +88,9 @@ SIGNATURES = {
     "af_pipeline_create": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, P(c_vp)]),
     "af_pipeline_free": (None, [c_vp]),
     "af_pipeline_run": (ctypes.c_int, [c_vp, P(Batch), c_vp, c_i64, P(c_i64), P(c_i64)]),
+    "af_pipeline_run_multi": (ctypes.c_int, [c_vp, c_i32, c_vp, P(Batch), c_vp, c_vp, c_vp, c_vp]),
     "af_pipeline_launches": (c_i64, [c_vp]),
+    "af_pipeline_h2d_bytes": (c_i64, [c_vp]),
     "af_exchange_create": (ctypes.c_int, [ctypes.c_int, c_i32, c_i32, c_i32, c_i64, P(c_vp)]),
     "af_exchange_free": (None, [c_vp]),
     "af_exchange_handle": (ctypes.c_int, [c_vp, c_vp]),

@@ -15,7 +15,7 @@ import sys
 import time
 
 from .functions import combine_split_reads, split_records
-from .stage import GeneAnchorer, anchor_stage, anchor_stage_multi
+from .stage import GeneAnchorer, anchor_cells, anchor_stage, anchor_stage_multi
 
 
 def _common_flags(p):
@@ -34,7 +34,7 @@ def _tail_flags(p):
     p.add_argument('--positive_samples', type=str, default='./data/positive_samples.txt', help='Accepted for compatibility.')
     p.add_argument('--homo_gene_file', type=str, default='./data/homo_gene.npy', help='Accepted for compatibility.')
     p.add_argument('--negative_samples', type=str, default='./Model/negative_samples.txt', help='Accepted for compatibility.')
-    p.add_argument('--thread', type=str, default='1', help='The threads number you want use.')
+    p.add_argument('--thread', type=str, default='1', help='The threads number you want use (FASTQ decode / pack workers; the reference hands it to bwa mem -t).')
     p.add_argument('--gpu_number', type=str, default='-1', help="The gpu number you want use ('-1': first visible GPU).")
     return p
 
@@ -106,6 +106,8 @@ def run_gene_sample(file_anchored_seq, gene, fastq1, fastq2, out_dir_name, args,
     t0 = time.time()
     stats = anchor_stage(file_anchored_seq, fastq1, fastq2, out_dir_name, thread=args.thread,
                          gpu_number=args.gpu_number, gene_name=gene, gene_anchorer=gene_anchorer)
+    if stats is None:               # a rank other than 0 of a torchrun job: rank 0 writes the files
+        return None
     groups = write_split_points(stats, gene, out_dir_name + '_split_points.txt')
     dt = time.time() - t0
     print('[anchoring] %s: %d pairs, %d anchored reads, %d half-anchored pairs, %d split-point groups, %.2f s (%.0f pairs/s)'
@@ -122,6 +124,9 @@ def main_bulk(argv=None):
     args = p.parse_args(argv)
     gene_names = parse_gene_names(args.file_anchored_cds, args.gene_names)
     _mkdir(args.out_folder)
+    # Under torchrun (one process per GPU) the read batches of the ONE FASTQ pair are dealt to the ranks,
+    # every rank anchors its share on its own GPU and rank 0 writes the one set of files.
+    rank = int(os.environ.get('RANK', '0'))
 
     def work_prefix(gene):      # <out>/<gene>_fusion/work_dir/<gene>_fusion   (Anchored_Fusion.py:127-131)
         folder = args.out_folder + '/' + gene + '_fusion'
@@ -129,25 +134,37 @@ def main_bulk(argv=None):
         _mkdir(folder + '/model_dir/')
         return folder + '/work_dir/' + gene + '_fusion'
 
-    fastas = split_anchor_fasta(args.file_anchored_cds, gene_names, lambda g: work_prefix(g) + '_anchored_gene_sequence.fa')
+    if rank == 0:
+        fastas = split_anchor_fasta(args.file_anchored_cds, gene_names, lambda g: work_prefix(g) + '_anchored_gene_sequence.fa')
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        from .stage import _host_group
+        import torch.distributed as dist
+        _, _, group = _host_group()
+        dist.barrier(group=group)           # the per-gene FASTA files exist before any rank reads them
+    fastas = [work_prefix(g) + '_anchored_gene_sequence.fa' for g in gene_names]
     todo = [(g, fa) for g, fa in zip(gene_names, fastas)
             if not (os.path.exists(work_prefix(g) + '_anchored_reads.bam') and os.path.exists(work_prefix(g) + '_realign_reads.bam'))]
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        import torch.distributed as dist
+        dist.barrier(group=group)           # every rank decided on the same list before rank 0 starts writing
     for g in gene_names:
-        if g not in [t[0] for t in todo]:
+        if g not in [t[0] for t in todo] and rank == 0:
             print('[anchoring] %s: outputs exist, skipping (same existence guard as the reference)' % work_prefix(g))
     if len(todo) == 1:
         run_gene_sample(todo[0][1], todo[0][0], args.fastq1, args.fastq2, work_prefix(todo[0][0]), args)
     elif todo:
-        # several anchored genes: decode and pack the FASTQ pair once, scan it for every gene
-        # (the reference re-reads both files once per gene, Anchored_Fusion.py:126,182)
+        # several anchored genes: decode and pack the FASTQ pair once, copy every batch to the GPU once and
+        # scan it for every gene while it is resident (the reference re-reads both files once per gene,
+        # Anchored_Fusion.py:126,182)
         t0 = time.time()
         gas = [GeneAnchorer(fa, args.gpu_number, g) for g, fa in todo]
-        all_stats = anchor_stage_multi(gas, args.fastq1, args.fastq2, [work_prefix(g) for g, _ in todo])
-        for (g, _), stats in zip(todo, all_stats):
-            groups = write_split_points(stats, g, work_prefix(g) + '_split_points.txt')
-            print('[anchoring] %s: %d pairs, %d anchored reads, %d half-anchored pairs, %d split-point groups'
-                  % (g, stats['pairs'], stats['anchored'], stats['half_anchored_pairs'], len(groups)))
-        print('[anchoring] %d genes in one pass over the reads, %.2f s' % (len(todo), time.time() - t0))
+        all_stats = anchor_stage_multi(gas, args.fastq1, args.fastq2, [work_prefix(g) for g, _ in todo], thread=args.thread)
+        if all_stats is not None:
+            for (g, _), stats in zip(todo, all_stats):
+                groups = write_split_points(stats, g, work_prefix(g) + '_split_points.txt')
+                print('[anchoring] %s: %d pairs, %d anchored reads, %d half-anchored pairs, %d split-point groups'
+                      % (g, stats['pairs'], stats['anchored'], stats['half_anchored_pairs'], len(groups)))
+            print('[anchoring] %d genes in one pass over the reads, %.2f s' % (len(todo), time.time() - t0))
     return 0
 
 
@@ -188,31 +205,35 @@ def main_singlecell(argv=None):
     # GPU (torchrun) with the cells dealt round-robin to the ranks: no exchange at all.
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
     gas = [GeneAnchorer(fa, args.gpu_number, gene) for gene, fa in zip(gene_names, fastas)]   # one index upload + staging per gene, not per cell
-    t0, n_pairs, n_cells = time.time(), 0, 0
+
+    def prefix_of(gene, cell):  # <out>/<gene>/work_dir/<cell>/<gene>_fusion   (Anchored_Fusion_singlecell.py:208)
+        return args.out_folder + '/' + gene + '/work_dir/' + cell + '/' + gene + '_fusion'
+
+    t0 = time.time()
+    mine = []
     for ci, (cell, f1, f2) in enumerate(cells):
         if ci % world != rank:
             continue
-        prefixes = []
         for gene in gene_names:
-            cell_dir = args.out_folder + '/' + gene + '/work_dir/' + cell
-            _mkdir(cell_dir)
-            prefixes.append(cell_dir + '/' + gene + '_fusion')
-        todo = [k for k, pre in enumerate(prefixes)
-                if not (os.path.exists(pre + '_anchored_reads.bam') and os.path.exists(pre + '_realign_reads.bam'))]
-        if not todo:
+            _mkdir(args.out_folder + '/' + gene + '/work_dir/' + cell)
+        # a cell is skipped only when every gene's outputs exist (same existence guards as the reference)
+        if all(os.path.exists(prefix_of(g, cell) + '_anchored_reads.bam') and os.path.exists(prefix_of(g, cell) + '_realign_reads.bam')
+               for g in gene_names):
             continue
-        q1, q2 = args.fastq_dir + '/' + f1, args.fastq_dir + '/' + f2
-        if len(todo) == 1:
-            k = todo[0]
-            stats = run_gene_sample(fastas[k], gene_names[k], q1, q2, prefixes[k], args, gas[k])
-            n_pairs += stats['pairs'] if stats else 0
-        else:
-            # several genes: the cell's FASTQ pair is decoded and packed once (the reference reads it once per gene)
-            all_stats = anchor_stage_multi([gas[k] for k in todo], q1, q2, [prefixes[k] for k in todo])
-            for k, stats in zip(todo, all_stats):
-                write_split_points(stats, gene_names[k], prefixes[k] + '_split_points.txt')
-            n_pairs += all_stats[0]['pairs']
-        n_cells += 1
+        mine.append((cell, args.fastq_dir + '/' + f1, args.fastq_dir + '/' + f2))
+    n_pairs = n_cells = 0
+    if mine:
+        # All of this rank's cells go through ONE reader: their files are decoded concurrently, packed back to
+        # back into shared batches (1 M pairs per GPU pass instead of one pass per 5 k-pair cell) and every
+        # batch is scanned for all genes while resident; the hit lists are split back per cell on the host.
+        def on_cell(cell, cell_stats):
+            for gene, st in zip(gene_names, cell_stats):
+                write_split_points(st, gene, prefix_of(gene, cell) + '_split_points.txt')
+
+        res = anchor_cells(gas, mine, prefix_of, thread=args.thread, on_cell=on_cell)
+        n_pairs, n_cells = res['pairs'], res['cells']
+        print('[anchoring] rank %d/%d: scan %.2f s, per-cell files %.2f s (%.2f ms per cell), %d reader threads'
+              % (rank, world, res['seconds_scan'], res['seconds_write'], 1e3 * res['seconds_write'] / max(n_cells, 1), res['threads']))
     dt = time.time() - t0
     print('[anchoring] rank %d/%d: %d cells, %d pairs, %d genes, %.2f s (%.0f pairs/s)'
           % (rank, world, n_cells, n_pairs, len(gene_names), dt, n_pairs / max(dt, 1e-9)))

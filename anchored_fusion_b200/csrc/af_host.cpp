@@ -224,8 +224,52 @@ static const uint8_t *code_lut() {
     return lut.data();
 }
 
-void af_pack_side(const SeqRef *r, int m, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
-                  uint16_t *lens_out, PackSide &st) {
+// 16 bases -> one packed word.  ACGT (either case) map to 0..3 through ((c >> 1) ^ (c >> 2)) & 3; everything
+// else is N: the word keeps the pad pattern there and the position is reported in nbits.
+static inline uint32_t pack16_scalar(const char *seq, int cnt, uint32_t padw, const uint8_t *lut, uint32_t *nbits) {
+    uint32_t word = padw, nb = 0;
+    for (int i = 0; i < cnt; i++) {
+        const uint8_t c = lut[(uint8_t)seq[i]];
+        if (c == 4) { nb |= 1u << i; continue; }
+        word = (word & ~(3u << (2 * i))) | ((uint32_t)c << (2 * i));
+    }
+    *nbits = nb;
+    return word;
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define AF_HAVE_X86_PACK 1
+// the same for 16 whole bases with SSSE3 + BMI2: codes by shifts, validity by looking the code's letter up
+// again (pshufb) and comparing with the upper-cased input, 2-bit compaction with pext
+__attribute__((target("ssse3,bmi2,sse4.1"))) static inline uint32_t pack16_x86(const char *seq, uint32_t padw, uint32_t *nbits) {
+    const __m128i c = _mm_loadu_si128((const __m128i *)seq);
+    const __m128i up = _mm_and_si128(c, _mm_set1_epi8((char)0xDF));
+    const __m128i s1 = _mm_and_si128(_mm_srli_epi16(c, 1), _mm_set1_epi8(0x7F));
+    const __m128i s2 = _mm_and_si128(_mm_srli_epi16(c, 2), _mm_set1_epi8(0x3F));
+    const __m128i code = _mm_and_si128(_mm_xor_si128(s1, s2), _mm_set1_epi8(3));
+    const __m128i letters = _mm_setr_epi8('A', 'C', 'G', 'T', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m128i expect = _mm_shuffle_epi8(letters, code);
+    const uint32_t valid = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(expect, up));      // bit i: base i is ACGT
+    const uint64_t lo = (uint64_t)_mm_cvtsi128_si64(code), hi = (uint64_t)_mm_extract_epi64(code, 1);
+    const uint32_t packed = (uint32_t)_pext_u64(lo, 0x0303030303030303ull) | ((uint32_t)_pext_u64(hi, 0x0303030303030303ull) << 16);
+    const uint32_t vm = (uint32_t)_pdep_u32(valid, 0x55555555u) * 3u;                    // 2 mask bits per base
+    *nbits = ~valid & 0xFFFFu;
+    return (packed & vm) | (padw & ~vm);
+}
+static bool x86_pack_ok() {
+    static const bool ok = __builtin_cpu_supports("ssse3") && __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("sse4.1");
+    return ok;
+}
+#endif
+
+// One mate's words of pairs [p0, p1) of a batch of n_pairs (mate 0 also writes the zero words that pad a
+// pair to whole quads); r[0 .. p1 - p0) are the reads of those pairs.  p0 must be a multiple of 32 and
+// p1 either a multiple of 32 or n_pairs: a range then owns whole tiles (the pairs past n_pairs in the last
+// tile are written as pad), so ranges -- and the two mates, which touch disjoint 32-bit words -- can be
+// packed by different threads at once.  N positions and the tail past a read keep the pad pattern.
+void af_pack_range(const SeqRef *r, int m, int64_t p0, int64_t p1, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte,
+                   void *packed_out, uint16_t *lens_out, PackSide &st) {
     af_layout_t lay;
     st.rc = af_layout(max_read_len, n_pairs, &lay);
     if (st.rc) return;
@@ -234,14 +278,18 @@ void af_pack_side(const SeqRef *r, int m, int64_t n_pairs, int32_t max_read_len,
     uint32_t *out = (uint32_t *)packed_out;
     uint32_t padw = 0;  // 16 bases of the period-4 pad pattern
     for (int i = 0; i < 16; i++) padw |= (uint32_t)((pad_byte >> (2 * (i & 3))) & 3) << (2 * i);
-    for (int64_t p = 0; p < lay.n_tiles * AF_TILE_PAIRS; p++) {
+#ifdef AF_HAVE_X86_PACK
+    const bool fast = x86_pack_ok();
+#endif
+    const int64_t p_end = p1 == n_pairs ? lay.n_tiles * AF_TILE_PAIRS : p1;
+    for (int64_t p = p0; p < p_end; p++) {
         const int64_t tile = p >> 5, lane = p & 31;
         uint32_t *pair_base = out + (tile * Q * 32 + lane) * 4;       // word wi of the pair at pair_base[(wi>>2)*128 + (wi&3)]
         if (m == 0) for (int wi = 2 * W; wi < 4 * Q; wi++) pair_base[(wi >> 2) * 128 + (wi & 3)] = 0u;
         int32_t len = 0;
         const char *seq = nullptr;
         if (p < n_pairs) {
-            len = r[p].len; seq = r[p].p;
+            len = r[p - p0].len; seq = r[p - p0].p;
             if (len > max_read_len || len < 0) {
                 char buf[160];
                 snprintf(buf, sizeof(buf), "af_pack: read %lld/%d has %d bases, max_read_len is %d", (long long)p, m + 1, len, max_read_len);
@@ -252,23 +300,29 @@ void af_pack_side(const SeqRef *r, int m, int64_t n_pairs, int32_t max_read_len,
             if (lens_out) lens_out[2 * p + m] = (uint16_t)len;
         }
         uint32_t nm[AF_NMASK_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
-        bool hasn = false;
+        uint32_t anyn = 0;
         for (int t = 0; t < W; t++) {
-            uint32_t word = padw;
             const int i0 = 16 * t, cnt = len - i0 < 16 ? (len - i0 > 0 ? len - i0 : 0) : 16;
-            for (int i = 0; i < cnt; i++) {
-                const uint8_t c = lut[(uint8_t)seq[i0 + i]];
-                if (c == 4) { hasn = true; nm[(i0 + i) >> 5] |= 1u << ((i0 + i) & 31); continue; }   // keeps the pad base
-                word = (word & ~(3u << (2 * i))) | ((uint32_t)c << (2 * i));
-            }
+            uint32_t word = padw, nb = 0;
+#ifdef AF_HAVE_X86_PACK
+            if (cnt == 16 && fast) word = pack16_x86(seq + i0, padw, &nb);
+            else
+#endif
+            if (cnt) word = pack16_scalar(seq + i0, cnt, padw, lut, &nb);
+            if (nb) { anyn = 1; nm[i0 >> 5] |= nb << (i0 & 31); }
             const int wi = m * W + t;
             pair_base[(wi >> 2) * 128 + (wi & 3)] = word;
         }
-        if (hasn) {
+        if (anyn) {
             st.nids.push_back((uint32_t)(2 * p + m));
             st.nmask.insert(st.nmask.end(), nm, nm + AF_NMASK_WORDS);
         }
     }
+}
+
+void af_pack_side(const SeqRef *r, int m, int64_t n_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
+                  uint16_t *lens_out, PackSide &st) {
+    af_pack_range(r, m, 0, n_pairs, n_pairs, max_read_len, pad_byte, packed_out, lens_out, st);
 }
 
 // merge the two sides' N lists (each sorted by read id) into the caller's arrays

@@ -24,17 +24,21 @@
     } while (0)
 
 
+static const int MAX_GENES = 64;     // anchor indexes one pipeline can scan a resident chunk for
+
 struct Slot {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     void *d_packed = nullptr, *d_ws = nullptr;
     uint16_t *d_lens = nullptr;
-    uint32_t *d_nids = nullptr, *d_nmask = nullptr, *d_counts = nullptr;
-    af_hit_t *d_hits = nullptr;
-    uint32_t *h_counts = nullptr;   // pinned
+    uint32_t *d_nids = nullptr, *d_nmask = nullptr;
+    std::vector<uint32_t *> d_counts;   // per anchor index
+    std::vector<af_hit_t *> d_hits;     // per anchor index
+    uint32_t *h_counts = nullptr;   // pinned, MAX_GENES x AF_N_COUNTS
     uint32_t *h_nids = nullptr;     // pinned staging of rebased N-read ids
     af_hit_t *h_hits = nullptr;     // pinned
     bool busy = false;
+    int n_genes = 0;                // anchor indexes the chunk in flight was scanned for
     int64_t first_pair = 0, n_pairs = 0;
 };
 
@@ -46,6 +50,7 @@ struct af_pipeline {
     size_t ws_bytes = 0;
     std::vector<Slot> slots;
     long long launches0 = 0;
+    long long h2d_bytes = 0;        // bytes copied host -> device so far (tiles, lengths, N lists)
 };
 
 
@@ -55,7 +60,8 @@ extern "C" void af_pipeline_free(af_pipeline_t *p) {
     for (Slot &s : p->slots) {
         if (s.st) cudaStreamSynchronize(s.st);
         cudaFree(s.d_packed); cudaFree(s.d_ws); cudaFree(s.d_lens); cudaFree(s.d_nids); cudaFree(s.d_nmask);
-        cudaFree(s.d_counts); cudaFree(s.d_hits);
+        for (uint32_t *c : s.d_counts) cudaFree(c);
+        for (af_hit_t *h : s.d_hits) cudaFree(h);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_nids); cudaFreeHost(s.h_hits);
         if (s.done) cudaEventDestroy(s.done);
         if (s.st) cudaStreamDestroy(s.st);
@@ -90,9 +96,10 @@ extern "C" int af_pipeline_create(const af_dev_index_t *d, int64_t slot_pairs, i
         if (e == cudaSuccess) e = cudaMalloc(&s.d_lens, (size_t)slot_pairs * 2 * sizeof(uint16_t));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_nids, (size_t)p->ncap * 4);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_nmask, (size_t)p->ncap * AF_NMASK_WORDS * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&s.d_counts, AF_N_COUNTS * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&s.d_hits, (size_t)p->hits_cap * sizeof(af_hit_t));
-        if (e == cudaSuccess) e = cudaHostAlloc(&s.h_counts, AF_N_COUNTS * 4, cudaHostAllocDefault);
+        s.d_counts.assign(1, nullptr); s.d_hits.assign(1, nullptr);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_counts[0], AF_N_COUNTS * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_hits[0], (size_t)p->hits_cap * sizeof(af_hit_t));
+        if (e == cudaSuccess) e = cudaHostAlloc(&s.h_counts, (size_t)MAX_GENES * AF_N_COUNTS * 4, cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaHostAlloc(&s.h_nids, (size_t)p->ncap * 4, cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaHostAlloc(&s.h_hits, (size_t)p->hits_cap * sizeof(af_hit_t), cudaHostAllocDefault);
     }
@@ -106,22 +113,27 @@ extern "C" int af_pipeline_create(const af_dev_index_t *d, int64_t slot_pairs, i
 }
 
 extern "C" int64_t af_pipeline_launches(const af_pipeline_t *p) { return p ? af_kernel_launches() - p->launches0 : 0; }
+extern "C" int64_t af_pipeline_h2d_bytes(const af_pipeline_t *p) { return p ? p->h2d_bytes : 0; }
 
-// wait for a slot, append its hits (rebased to batch read ids)
-static int collect(af_pipeline *p, Slot &s, af_hit_t *h_hits, int64_t hits_cap, int64_t &n_hits, int64_t &n_flagged) {
+// wait for a slot, append its hits (rebased to batch read ids) to each anchor index's list
+static int collect(af_pipeline *p, Slot &s, af_hit_t *const *h_hits, const int64_t *hits_cap, int64_t *n_hits, int64_t *n_flagged) {
     if (!s.busy) return AF_OK;
     AF_CUDA(cudaEventSynchronize(s.done));
     s.busy = false;
-    uint32_t status = s.h_counts[AF_CNT_STATUS], nh = s.h_counts[AF_CNT_HITS];
-    n_flagged += s.h_counts[AF_CNT_FLAGGED];
-    if (status) { af_set_error("af_pipeline_run: device capacity overflow (status %u)", status); return AF_ERR_CAPACITY; }
-    if (nh == 0) return AF_OK;
-    if (n_hits + nh > hits_cap) { af_set_error("af_pipeline_run: hit buffer holds %lld records, need more", (long long)hits_cap); return AF_ERR_CAPACITY; }
-    AF_CUDA(cudaMemcpyAsync(s.h_hits, s.d_hits, (size_t)nh * sizeof(af_hit_t), cudaMemcpyDeviceToHost, s.st));
-    AF_CUDA(cudaStreamSynchronize(s.st));
-    const uint32_t base = (uint32_t)(2 * s.first_pair);
-    for (uint32_t i = 0; i < nh; i++) { h_hits[n_hits + i] = s.h_hits[i]; h_hits[n_hits + i].read_id += base; }
-    n_hits += nh;
+    for (int g = 0; g < s.n_genes; g++) {
+        const uint32_t *c = s.h_counts + (size_t)g * AF_N_COUNTS;
+        const uint32_t status = c[AF_CNT_STATUS], nh = c[AF_CNT_HITS];
+        n_flagged[g] += c[AF_CNT_FLAGGED];
+        if (status) { af_set_error("af_pipeline_run: device capacity overflow (status %u)", status); return AF_ERR_CAPACITY; }
+        if (nh == 0) continue;
+        if (n_hits[g] + nh > hits_cap[g]) { af_set_error("af_pipeline_run: hit buffer holds %lld records, need more", (long long)hits_cap[g]); return AF_ERR_CAPACITY; }
+        AF_CUDA(cudaMemcpyAsync(s.h_hits, s.d_hits[g], (size_t)nh * sizeof(af_hit_t), cudaMemcpyDeviceToHost, s.st));
+        AF_CUDA(cudaStreamSynchronize(s.st));
+        const uint32_t base = (uint32_t)(2 * s.first_pair);
+        af_hit_t *dst = h_hits[g] + n_hits[g];
+        for (uint32_t i = 0; i < nh; i++) { dst[i] = s.h_hits[i]; dst[i].read_id += base; }
+        n_hits[g] += nh;
+    }
     (void)p;
     return AF_OK;
 }
@@ -136,32 +148,63 @@ static void drain_all(af_pipeline *p) {
     }
 }
 
-static int pipeline_run_impl(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h_hits, int64_t hits_cap,
-                             int64_t *n_hits_out, int64_t *n_flagged_out);
+static int pipeline_run_impl(af_pipeline_t *p, int n_genes, const af_dev_index_t *const *idx, const af_batch_t *hb,
+                             af_hit_t *const *h_hits, const int64_t *hits_cap, int64_t *n_hits_out, int64_t *n_flagged_out);
 
 extern "C" int af_pipeline_run(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h_hits, int64_t hits_cap,
                                int64_t *n_hits_out, int64_t *n_flagged_out) {
-    const int rc = pipeline_run_impl(p, hb, h_hits, hits_cap, n_hits_out, n_flagged_out);
-    if (rc != AF_OK && p) drain_all(p);        // keeps af_last_error() of the failing call
+    if (!p || !n_hits_out) { af_set_error("af_pipeline_run: null argument"); return AF_ERR_ARG; }
+    int64_t nf = 0;
+    const int rc = pipeline_run_impl(p, 1, &p->d, hb, &h_hits, &hits_cap, n_hits_out, &nf);
+    if (rc != AF_OK) drain_all(p);             // keeps af_last_error() of the failing call
+    else if (n_flagged_out) *n_flagged_out = nf;
     return rc;
 }
 
-static int pipeline_run_impl(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h_hits, int64_t hits_cap,
-                             int64_t *n_hits_out, int64_t *n_flagged_out) {
-    if (!p || !hb || !n_hits_out || (hits_cap > 0 && !h_hits)) { af_set_error("af_pipeline_run: null argument"); return AF_ERR_ARG; }
+// One pass over a HOST batch for several anchor indexes (all uploaded to the pipeline's device): every
+// chunk is copied to the GPU ONCE and scanned for each index in turn while it is resident, so the
+// host->device traffic does not depend on the number of anchored genes (the reference re-reads both
+// FASTQ files once per gene, Anchored_Fusion.py:126,182).
+extern "C" int af_pipeline_run_multi(af_pipeline_t *p, int32_t n_indexes, const af_dev_index_t *const *indexes,
+                                     const af_batch_t *hb, af_hit_t *const *h_hits, const int64_t *hits_cap,
+                                     int64_t *n_hits_out, int64_t *n_flagged_out) {
+    if (!p || !indexes || !h_hits || !hits_cap || !n_hits_out || !n_flagged_out || n_indexes < 1 || n_indexes > MAX_GENES) {
+        af_set_error("af_pipeline_run_multi: bad argument (1..%d indexes)", MAX_GENES);
+        return AF_ERR_ARG;
+    }
+    for (int g = 0; g < n_indexes; g++)
+        if (!indexes[g] || af_dev_index_device(indexes[g]) != p->device) { af_set_error("af_pipeline_run_multi: index %d is not on device %d", g, p->device); return AF_ERR_ARG; }
+    const int rc = pipeline_run_impl(p, n_indexes, indexes, hb, h_hits, hits_cap, n_hits_out, n_flagged_out);
+    if (rc != AF_OK) drain_all(p);
+    return rc;
+}
+
+static int pipeline_run_impl(af_pipeline_t *p, int n_genes, const af_dev_index_t *const *idx, const af_batch_t *hb,
+                             af_hit_t *const *h_hits, const int64_t *hits_cap, int64_t *n_hits_out, int64_t *n_flagged_out) {
+    if (!p || !hb || !n_hits_out) { af_set_error("af_pipeline_run: null argument"); return AF_ERR_ARG; }
+    for (int g = 0; g < n_genes; g++) if (hits_cap[g] > 0 && !h_hits[g]) { af_set_error("af_pipeline_run: null hit buffer"); return AF_ERR_ARG; }
     if (hb->max_read_len != p->max_read_len) { af_set_error("af_pipeline_run: batch max_read_len %d, pipeline built for %d", hb->max_read_len, p->max_read_len); return AF_ERR_ARG; }
     if (hb->n_pairs >= (1ll << 31)) { af_set_error("af_pipeline_run: a host batch holds at most 2^31-1 pairs"); return AF_ERR_ARG; }
     af_layout_t lay;
     int rc = af_layout(hb->max_read_len, hb->n_pairs, &lay);
     if (rc) return rc;
     AF_CUDA(cudaSetDevice(p->device));
-    int64_t n_hits = 0, n_flagged = 0;
+    for (Slot &s : p->slots)                      // per-index result buffers, grown on first use
+        while ((int)s.d_counts.size() < n_genes) {
+            uint32_t *c = nullptr; af_hit_t *h = nullptr;
+            AF_CUDA(cudaMalloc(&c, AF_N_COUNTS * 4));
+            s.d_counts.push_back(c);
+            s.d_hits.push_back(nullptr);
+            AF_CUDA(cudaMalloc(&h, (size_t)p->hits_cap * sizeof(af_hit_t)));
+            s.d_hits.back() = h;
+        }
+    std::vector<int64_t> n_hits((size_t)n_genes, 0), n_flagged((size_t)n_genes, 0);
     const size_t tile_bytes = (size_t)lay.quads_per_pair * 512;
     size_t si = 0;
     for (int64_t first = 0; first < hb->n_pairs; first += p->slot_pairs) {
         Slot &s = p->slots[si];
         si = (si + 1) % p->slots.size();
-        rc = collect(p, s, h_hits, hits_cap, n_hits, n_flagged);   // results come back in chunk order
+        rc = collect(p, s, h_hits, hits_cap, n_hits.data(), n_flagged.data());   // results come back in chunk order
         if (rc) return rc;
         const int64_t n = std::min<int64_t>(p->slot_pairs, hb->n_pairs - first);
         const int64_t tiles = (n + 31) / 32;
@@ -169,6 +212,7 @@ static int pipeline_run_impl(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h
         s.n_pairs = n;
         AF_CUDA(cudaMemcpyAsync(s.d_packed, (const char *)hb->packed + (size_t)(first / 32) * tile_bytes,
                                 (size_t)tiles * tile_bytes, cudaMemcpyHostToDevice, s.st));
+        p->h2d_bytes += (long long)((size_t)tiles * tile_bytes);
         af_batch_t db;
         db.packed = s.d_packed;
         db.n_pairs = n;
@@ -177,6 +221,7 @@ static int pipeline_run_impl(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h
         db.lens = nullptr;
         if (hb->uniform_len <= 0) {
             AF_CUDA(cudaMemcpyAsync(s.d_lens, hb->lens + 2 * first, (size_t)n * 2 * sizeof(uint16_t), cudaMemcpyHostToDevice, s.st));
+            p->h2d_bytes += (long long)((size_t)n * 2 * sizeof(uint16_t));
             db.lens = s.d_lens;
         }
         // the chunk's slice of the sorted N-read list, ids rebased to the chunk
@@ -191,22 +236,25 @@ static int pipeline_run_impl(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h
                 AF_CUDA(cudaMemcpyAsync(s.d_nids, s.h_nids, (size_t)cnt * 4, cudaMemcpyHostToDevice, s.st));
                 AF_CUDA(cudaMemcpyAsync(s.d_nmask, hb->nmask + (size_t)(lo - b) * AF_NMASK_WORDS,
                                         (size_t)cnt * AF_NMASK_WORDS * 4, cudaMemcpyHostToDevice, s.st));
+                p->h2d_bytes += (long long)((size_t)cnt * (4 + AF_NMASK_WORDS * 4));
                 db.nread_ids = s.d_nids; db.nmask = s.d_nmask; db.n_nreads = cnt;
             }
         }
-        rc = af_anchor_batch(p->d, &db, s.d_ws, p->ws_bytes, p->cand_cap, s.d_hits, p->hits_cap, s.d_counts, s.st);
-        if (rc) return rc;
-        AF_CUDA(cudaMemcpyAsync(s.h_counts, s.d_counts, AF_N_COUNTS * 4, cudaMemcpyDeviceToHost, s.st));
+        for (int g = 0; g < n_genes; g++) {        // the chunk stays resident: one scan per anchor index
+            rc = af_anchor_batch(idx[g], &db, s.d_ws, p->ws_bytes, p->cand_cap, s.d_hits[g], p->hits_cap, s.d_counts[g], s.st);
+            if (rc) return rc;
+            AF_CUDA(cudaMemcpyAsync(s.h_counts + (size_t)g * AF_N_COUNTS, s.d_counts[g], AF_N_COUNTS * 4, cudaMemcpyDeviceToHost, s.st));
+        }
+        s.n_genes = n_genes;
         AF_CUDA(cudaEventRecord(s.done, s.st));
         s.busy = true;
     }
     // drain in chunk order: continue round-robin from the oldest slot
     for (size_t k = 0; k < p->slots.size(); k++) {
         Slot &s = p->slots[(si + k) % p->slots.size()];
-        rc = collect(p, s, h_hits, hits_cap, n_hits, n_flagged);
+        rc = collect(p, s, h_hits, hits_cap, n_hits.data(), n_flagged.data());
         if (rc) return rc;
     }
-    *n_hits_out = n_hits;
-    if (n_flagged_out) *n_flagged_out = n_flagged;
+    for (int g = 0; g < n_genes; g++) { n_hits_out[g] = n_hits[g]; n_flagged_out[g] = n_flagged[g]; }
     return AF_OK;
 }

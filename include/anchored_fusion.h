@@ -145,9 +145,18 @@ int af_pack_pairs(const char *seq1, const int64_t *off1, const char *seq2, const
 /* inverse, for tests: codes 0..3 (pad bases come back as their 2-bit value) */
 int af_unpack_read(const void *packed, int32_t max_read_len, int64_t read_id, int32_t len, uint8_t *codes_out);
 
-/* paired FASTQ / FASTQ.gz reader (zlib), two decode threads.  Text of the current batch stays
- * valid until the next af_fastq_next on the same reader. */
-int af_fastq_open(const char *path1, const char *path2, af_fastq_t **out);
+/* Paired FASTQ reader: plain text, gzip (any number of members) and BGZF (bgzip), detected per file.
+ * n_threads workers (the reference forwards `--thread` to `bwa mem -t`, Anchored_Fusion.py:29,182;
+ * 0 = one per host core) inflate BGZF blocks / copy text, index lines, check CRCs and pack 2-bit tiles in
+ * parallel; a plain gzip member is one serial bit stream and is inflated by one thread per file.
+ * Record text of the current batch stays valid until the next af_fastq_next / af_fastq_skip. */
+int af_fastq_open(const char *path1, const char *path2, af_fastq_t **out);                 /* n_threads = 0 */
+int af_fastq_open_threads(const char *path1, const char *path2, int32_t n_threads, af_fastq_t **out);
+/* Several file pairs read back to back as ONE stream of pairs (Anchored_Fusion_singlecell.py:86-113: one
+ * FASTQ pair per cell): small files are decoded whole, many at a time, and a batch may span many cells. */
+int af_fastq_open_multi(const char *const *paths1, const char *const *paths2, int32_t n_files, int32_t n_threads,
+                        af_fastq_t **out);
+int af_fastq_threads(const af_fastq_t *fq);
 void af_fastq_close(af_fastq_t *fq);
 /* longest read among the first n_records records (the packed width must be known before reading) */
 int af_fastq_peek(const char *path, int32_t n_records, int32_t *max_len_out);
@@ -155,10 +164,21 @@ int af_fastq_peek(const char *path, int32_t n_records, int32_t *max_len_out);
 int af_fastq_next(af_fastq_t *fq, int64_t max_pairs, int32_t max_read_len, int32_t pad_byte, void *packed_out,
                   uint16_t *lens_out, uint32_t *nread_ids_out, uint32_t *nmask_out, int64_t ncap,
                   int64_t *n_nreads_out, int32_t *uniform_len_out, int64_t *n_pairs_out);
+/* the same without packing: a rank of a multi-GPU job steps over the batches of the other ranks */
+int af_fastq_skip(af_fastq_t *fq, int64_t max_pairs, int64_t *n_pairs_out);
 /* record text of read_id of the current batch: name (up to first blank, /1 /2 stripped as bwa
  * does), bases, qualities.  Pointers are not NUL-terminated. */
 int af_fastq_record(const af_fastq_t *fq, int64_t read_id, const char **name, int32_t *name_len,
                     const char **seq, const char **qual, int32_t *len);
+/* many records at once: name, bases, qualities of read_ids[i] copied back to back into `text`;
+ * offs[4i .. 4i+3] = start of name / bases / qualities / end.  AF_ERR_CAPACITY (with *text_used = bytes
+ * needed) when text_cap is too small; text may be NULL to size the buffer. */
+int af_fastq_records(const af_fastq_t *fq, const int64_t *read_ids, int64_t n, char *text, int64_t text_cap,
+                     int64_t *offs, int64_t *text_used);
+/* index (over the whole run) of the first pair of every input file started so far; returns the count */
+int af_fastq_file_starts(const af_fastq_t *fq, int64_t *first_pair_out, int32_t cap);
+/* index (over the whole run) of the current batch's first pair */
+int64_t af_fastq_batch_first_pair(const af_fastq_t *fq);
 
 /* ---- the hot path on one GPU: replaces `bwa mem -M | samtools view -F 772` -------------- */
 size_t af_workspace_bytes(int64_t n_pairs, int64_t cand_cap);
@@ -196,7 +216,15 @@ void af_pipeline_free(af_pipeline_t *p);
  * read_id; read_ids are relative to the batch. */
 int af_pipeline_run(af_pipeline_t *p, const af_batch_t *host_batch, af_hit_t *h_hits, int64_t hits_cap,
                     int64_t *n_hits_out, int64_t *n_flagged_out);
+/* The same for several anchor indexes (all on the pipeline's device) in ONE pass over the host batch: each
+ * chunk is copied once and scanned for every index while resident (the reference re-reads
+ * both FASTQ files once per gene, Anchored_Fusion.py:126,182).  h_hits / hits_cap / n_hits_out / n_flagged_out
+ * are arrays of n_indexes entries. */
+int af_pipeline_run_multi(af_pipeline_t *p, int32_t n_indexes, const af_dev_index_t *const *indexes,
+                          const af_batch_t *host_batch, af_hit_t *const *h_hits, const int64_t *hits_cap,
+                          int64_t *n_hits_out, int64_t *n_flagged_out);
 int64_t af_pipeline_launches(const af_pipeline_t *p); /* kernels launched so far */
+int64_t af_pipeline_h2d_bytes(const af_pipeline_t *p); /* bytes copied host -> device so far */
 void *af_host_alloc(size_t bytes);                    /* cudaHostAlloc (pinned) */
 void af_host_free(void *p);
 

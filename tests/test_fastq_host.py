@@ -157,3 +157,234 @@ def test_cli_gene_names_and_anchor_split(tmp_path, bundled):
         (d / f).write_text("")
     assert discover_cells(str(d)) == [("c1", "c1_1.fastq.gz", "c1_2.fastq.gz"), ("c2", "c2_1.fq", "c2_2.fq"),
                                       ("c4", "c4_1.fq.gz", "c4_2.fq.gz")]
+
+
+# ---- round 2: the task-parallel reader (BGZF, multi-member gzip, many files, threads) ---------------------
+def _bgzf_bytes(data, level=6, block=0xFF00):
+    import struct
+    import zlib
+    out = bytearray()
+    for i in range(0, len(data), block):
+        blk = data[i:i + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(blk) + co.flush()
+        out += b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp
+        out += struct.pack("<II", zlib.crc32(blk) & 0xFFFFFFFF, len(blk))
+    return bytes(out) + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def _fastq_text(names, seqs, quals):
+    return "".join("@%s\n%s\n+\n%s\n" % t for t in zip(names, seqs, quals)).encode()
+
+
+def _random_pairs(n, seed, lo=30, hi=151, with_n=True):
+    rng = np.random.default_rng(seed)
+    alpha, p = (list("ACGTN"), [.2475, .2475, .2475, .2475, .01]) if with_n else (list("ACGT"), None)
+    s1 = ["".join(rng.choice(alpha, p=p, size=rng.integers(lo, hi))) for _ in range(n)]
+    s2 = ["".join(rng.choice(alpha, p=p, size=rng.integers(lo, hi))) for _ in range(n)]
+    q1 = ["".join(chr(33 + int(x)) for x in rng.integers(2, 41, len(s))) for s in s1]
+    q2 = ["F" * len(s) for s in s2]
+    return s1, s2, q1, q2
+
+
+def _read_all(reader):
+    """[(n_pairs, packed copy, lens copy, nids copy, first pair)] of every batch + records of all reads."""
+    out, recs = [], []
+    while True:
+        b = reader.next_batch()
+        if b is None:
+            break
+        lay_words = __import__("anchored_fusion_b200").layout(b.max_read_len, b.n_pairs).packed_bytes // 4
+        out.append((b.n_pairs, b.packed[:lay_words].copy(), b.lens.copy(), None if b.nread_ids is None else b.nread_ids.copy(),
+                    reader.first_pair))
+        recs += reader.records(np.arange(2 * b.n_pairs))
+    return out, recs
+
+
+@pytest.mark.parametrize("fmt", ["bgzf", "multi_member", "gzip", "plain", "bgzf_then_gzip"])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_reader_formats_and_thread_counts_give_identical_batches(tmp_path, fmt, threads):
+    """The same 40 k pairs as BGZF, as concatenated gzip members, as one gzip member, as plain text and as a
+    BGZF file with plain gzip members appended: identical packed batches, lengths, N lists and record text,
+    for any worker count (the parallel paths cut the text at other places than the serial one)."""
+    import gzip as gz
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200.stage import FastqPairReader
+    n = 40_000
+    s1, s2, q1, q2 = _random_pairs(n, 5)
+    names = ["r%d/1 comment" % i for i in range(n)]
+    t1, t2 = _fastq_text(names, s1, q1), _fastq_text(["r%d/2" % i for i in range(n)], s2, q2)
+
+    def enc(t):
+        if fmt == "bgzf":
+            return _bgzf_bytes(t)
+        if fmt == "multi_member":
+            return b"".join(gz.compress(t[i:i + 700_001], compresslevel=1 + (i // 700_001) % 9) for i in range(0, len(t), 700_001))
+        if fmt == "gzip":
+            return gz.compress(t, compresslevel=6)
+        if fmt == "bgzf_then_gzip":
+            cut = len(t) // 2
+            cut = t.index(b"\n@r", cut) + 1
+            return _bgzf_bytes(t[:cut])[:-28] + gz.compress(t[cut:])
+        return t
+    ext = ".fastq" if fmt == "plain" else ".fastq.gz"
+    p1, p2 = str(tmp_path / ("f_1" + ext)), str(tmp_path / ("f_2" + ext))
+    open(p1, "wb").write(enc(t1))
+    open(p2, "wb").write(enc(t2))
+    rd = FastqPairReader(p1, p2, 160, 0xE4, 16_384, threads=threads)
+    assert rd.threads == threads
+    batches, recs = _read_all(rd)
+    rd.close()
+    assert sum(b[0] for b in batches) == n and [b[4] for b in batches] == [0, 16_384, 32_768]
+    assert recs == [x for i in range(n) for x in (("r%d" % i, s1[i], q1[i]), ("r%d" % i, s2[i], q2[i]))]
+    lo = 0
+    for npairs, packed, lens, nids, _ in batches:
+        want = af.pack_pairs(s1[lo:lo + npairs], s2[lo:lo + npairs], max_read_len=160, pad_byte=0xE4)
+        assert np.array_equal(packed, want.packed) and np.array_equal(lens, want.lens)
+        assert (nids is None and want.n_nreads == 0) or np.array_equal(nids, want.nread_ids)
+        lo += npairs
+
+
+def test_reader_many_cells_as_one_stream_and_skip(tmp_path):
+    """Single-cell layout: 37 small file pairs (gzip, BGZF, plain, one empty cell) read as ONE stream; batches
+    span cells, file_starts() gives each cell's first pair, skip_batch() steps over a batch without packing."""
+    import gzip as gz
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200.stage import FastqPairReader
+    rng = np.random.default_rng(8)
+    f1, f2, all1, all2, sizes = [], [], [], [], []
+    for c in range(37):
+        n = 0 if c == 5 else int(rng.integers(1, 900))
+        s1, s2, q1, q2 = _random_pairs(n, 100 + c, 40, 101, with_n=False)
+        t1 = _fastq_text(["c%d_%d/1" % (c, i) for i in range(n)], s1, q1)
+        t2 = _fastq_text(["c%d_%d/2" % (c, i) for i in range(n)], s2, q2)
+        kind = c % 3
+        ext = (".fastq.gz", ".fq.gz", ".fastq")[kind]
+        p1, p2 = str(tmp_path / ("cell%02d_1%s" % (c, ext))), str(tmp_path / ("cell%02d_2%s" % (c, ext)))
+        for p, t in ((p1, t1), (p2, t2)):
+            open(p, "wb").write(gz.compress(t) if kind == 0 else _bgzf_bytes(t) if kind == 1 else t)
+        f1.append(p1)
+        f2.append(p2)
+        all1 += s1
+        all2 += s2
+        sizes.append(n)
+    total = sum(sizes)
+    rd = FastqPairReader(f1, f2, 112, 0xE4, 4096, threads=4)
+    got1, got2, i = [], [], 0
+    while True:
+        if i % 3 == 1:
+            n = rd.skip_batch()
+            if n == 0:
+                break
+            recs = rd.records(np.arange(2 * n))                 # text of a skipped batch is still there
+        else:
+            b = rd.next_batch()
+            if b is None:
+                break
+            n = b.n_pairs
+            lo = rd.first_pair
+            want = af.pack_pairs(all1[lo:lo + n], all2[lo:lo + n], max_read_len=112, pad_byte=0xE4)
+            assert np.array_equal(b.packed[: len(want.packed)], want.packed)
+            recs = rd.records(np.arange(2 * n))
+        got1 += [r[1] for r in recs[0::2]]
+        got2 += [r[1] for r in recs[1::2]]
+        i += 1
+    assert got1 == all1 and got2 == all2 and len(got1) == total
+    assert list(rd.file_starts()) == list(np.concatenate([[0], np.cumsum(sizes)[:-1]]))
+    rd.close()
+
+
+def test_reader_reports_damage(tmp_path):
+    """Truncated gzip (no silent partial sample), a flipped byte (CRC), a cell whose two files differ in size,
+    a BGZF block cut short."""
+    import gzip as gz
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200.stage import FastqPairReader
+    s1, s2, q1, q2 = _random_pairs(30_000, 3, 100, 101, with_n=False)
+    names = ["r%d" % i for i in range(len(s1))]
+    g1, g2 = gz.compress(_fastq_text(names, s1, q1)), gz.compress(_fastq_text(names, s2, q2))
+    good1, good2 = str(tmp_path / "g_1.fastq.gz"), str(tmp_path / "g_2.fastq.gz")
+    open(good1, "wb").write(g1)
+    open(good2, "wb").write(g2)
+
+    def drain(p1, p2):
+        rd = FastqPairReader(p1, p2, 112, 0xE4, 8192, threads=2)
+        try:
+            while rd.next_batch() is not None:
+                pass
+        finally:
+            rd.close()
+
+    drain(good1, good2)
+    bad = str(tmp_path / "bad_1.fastq.gz")
+    open(bad, "wb").write(g1[: len(g1) * 2 // 3])                          # both cut at the same fraction would once pass silently
+    cut2 = str(tmp_path / "bad_2.fastq.gz")
+    open(cut2, "wb").write(g2[: len(g2) * 2 // 3])
+    with pytest.raises(af.AnchoredFusionError, match="truncated"):
+        drain(bad, cut2)
+    flipped = bytearray(g1)
+    flipped[len(flipped) // 2] ^= 0x10
+    open(bad, "wb").write(bytes(flipped))
+    with pytest.raises(af.AnchoredFusionError, match="CRC|corrupt|truncated|FASTQ"):
+        drain(bad, good2)
+    b1 = _bgzf_bytes(_fastq_text(names, s1, q1))
+    open(bad, "wb").write(b1[: len(b1) // 2])
+    with pytest.raises(af.AnchoredFusionError, match="truncated|corrupt"):
+        drain(bad, good2)
+    # two cells, the second one's mate file is one record short
+    c1a, c1b = str(tmp_path / "ca_1.fastq"), str(tmp_path / "ca_2.fastq")
+    c2a, c2b = str(tmp_path / "cb_1.fastq"), str(tmp_path / "cb_2.fastq")
+    open(c1a, "wb").write(_fastq_text(names[:10], s1[:10], q1[:10]))
+    open(c1b, "wb").write(_fastq_text(names[:9], s2[:9], q2[:9]))
+    open(c2a, "wb").write(_fastq_text(names[:10], s1[:10], q1[:10]))
+    open(c2b, "wb").write(_fastq_text(names[:11], s2[:11], q2[:11]))
+    with pytest.raises(af.AnchoredFusionError, match="out of step"):
+        rd = FastqPairReader([c1a, c2a], [c1b, c2b], 112, 0xE4, 8192, threads=2)
+        try:
+            while rd.next_batch() is not None:
+                pass
+        finally:
+            rd.close()
+
+
+def test_inflater_equals_zlib_on_many_streams(tmp_path):
+    """af_inflate.h against zlib through the reader: stored / fixed / dynamic blocks, every compression level
+    and strategy, tiny and empty members, long runs, binary noise (compared as 'FASTQ' whose lines are the data)."""
+    import zlib
+    from anchored_fusion_b200.stage import FastqPairReader
+    rng = np.random.default_rng(17)
+    n = 6000
+    seqs = []
+    for i in range(n):
+        kind = i % 4
+        L = int(rng.integers(1, 200))
+        if kind == 0:
+            seqs.append("".join(rng.choice(list("ACGT"), size=L)))
+        elif kind == 1:
+            seqs.append("ACGT"[i % 4] * L)                                   # runs: distance-1 matches
+        elif kind == 2:
+            seqs.append(("ACGTTGCA" * 30)[:L])                               # short-period repeats: overlapping copies
+        else:
+            seqs.append("".join(rng.choice(list("ACGTNacgtnRYKM"), size=L)))
+    quals = ["".join(chr(33 + int(x)) for x in rng.integers(0, 60, len(s))) for s in seqs]
+    text = _fastq_text(["n%d" % i for i in range(n)], seqs, quals)
+    variants = []
+    for level in (0, 1, 3, 6, 9):
+        for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED):
+            for wbits in (31, 25):                                             # 32 KB and 512 B windows
+                co = zlib.compressobj(level, zlib.DEFLATED, wbits, 9 if level else 1, strategy)
+                variants.append(co.compress(text) + co.flush())
+    # sync-flushed stream (empty stored blocks inside) and a stream of tiny members
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    variants.append(b"".join(co.compress(text[i:i + 5000]) + co.flush(zlib.Z_SYNC_FLUSH) for i in range(0, len(text), 5000)) + co.flush())
+    import gzip as gz
+    variants.append(b"".join(gz.compress(text[i:i + 997]) for i in range(0, len(text), 997)) + gz.compress(b""))
+    other = str(tmp_path / "o_2.fastq")
+    open(other, "wb").write(text)
+    for k, blob in enumerate(variants):
+        p = str(tmp_path / ("v%d_1.fastq.gz" % k))
+        open(p, "wb").write(blob + b"\0" * 16 if k % 7 == 3 else blob)          # trailing garbage is ignored, as gzip does
+        rd = FastqPairReader(p, other, 208, 0xE4, 4096, threads=2)
+        _, recs = _read_all(rd)
+        rd.close()
+        assert [r[1] for r in recs[0::2]] == seqs and [r[2] for r in recs[0::2]] == quals, k
