@@ -55,9 +55,13 @@ int af_pack_finish(PackSide &a, PackSide &b, uint32_t *nread_ids_out, uint32_t *
 namespace {
 
 static const size_t HEAD = 64u << 10;          // bytes of the previous segment kept in front of a segment's text
+#ifdef AF_FASTQ_TEST_SIZES                     // sanitizer / fuzz builds: many segments and slices out of small files
+static const size_t SEG_TEXT = 24u << 10, SLICE = 5000, SMALL_FILE = 2000;
+#else
 static const size_t SEG_TEXT = 8u << 20;       // decoded text per segment
 static const size_t SLICE = 1u << 20;          // newline-index / CRC / copy granularity inside a segment
 static const size_t SMALL_FILE = 3u << 20;     // files up to this size (on disk) are one task each
+#endif
 static const size_t AHEAD_BYTES = 192u << 20;  // decoded text a driver may hold ready ahead of the consumer
 
 // ---- worker pool ---------------------------------------------------------------------------------
@@ -173,6 +177,7 @@ struct CrcPiece { uint32_t crc; size_t len; bool member_end; uint32_t want_crc, 
 struct Segment {
     char *buf = nullptr;              // HEAD + capacity + slack (malloc: not zero-filled)
     size_t buf_size = 0;
+    size_t acct_bytes = 0;            // what the driver's read-ahead budget is charged (set before the segment is queued)
     char *text = nullptr;             // buf + HEAD
     size_t len = 0;                   // decoded bytes in text[0, len)
     int file_idx = 0;
@@ -272,7 +277,8 @@ struct Side {
     void push(const SegP &s) {
         std::unique_lock<std::mutex> lk(mu);
         ready.push_back(s);
-        ready_bytes += s->buf_size;
+        if (!s->acct_bytes) s->acct_bytes = s->buf_size ? s->buf_size : 1;
+        ready_bytes += s->acct_bytes;
         cv_data.notify_all();
     }
     bool wait_room() {               // false when the reader is being closed
@@ -311,6 +317,7 @@ struct Side {
         SegP seg = std::make_shared<Segment>();
         seg->file_idx = file_idx; seg->file_first = true; seg->file_end = true;
         Segment::Slice *sl0 = seg->add_slice(0, 0);
+        seg->acct_bytes = mf->n * 5 + HEAD;              // the task allocates (and may grow) the buffer itself
         seg->latch.add();
         SegP keep0 = seg;
         pool->submit([keep0, sl0, mf] {
@@ -597,7 +604,7 @@ struct Side {
             }
             s = ready.front();
             ready.pop_front();
-            ready_bytes -= s->buf_size;
+            ready_bytes -= s->acct_bytes;
         }
         cv_room.notify_all();
         s->latch.wait();
@@ -624,7 +631,10 @@ struct Side {
             carry = (size_t)((ptrdiff_t)last_final->len - last_final->rec_end);
             if (s->file_first) { err = "truncated FASTQ record"; eof = true; return false; }
             if (carry > HEAD) { err = "a FASTQ record longer than 64 KB"; eof = true; return false; }
-            memmove(s->text - carry, last_final->text + last_final->rec_end, carry);
+            // (a streamed gzip member's driver has put the same bytes there already -- its deflate window --
+            // and may be reading them for the next segment: compare first, write only when they differ)
+            if (memcmp(s->text - carry, last_final->text + last_final->rec_end, carry) != 0)
+                memmove(s->text - carry, last_final->text + last_final->rec_end, carry);
         }
         s->lstart = -(ptrdiff_t)carry;
         if (s->file_first && (int)file_first_rec.size() <= s->file_idx) file_first_rec.resize((size_t)s->file_idx + 1, recs_total);
