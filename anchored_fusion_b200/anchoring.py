@@ -245,6 +245,10 @@ class Anchorer:
             self._pipe, self._pipe_key = h, key
         return self._pipe
 
+    def pipeline_h2d_bytes(self):
+        """bytes the current host-buffer pipeline has copied to the GPU so far"""
+        return lib().af_pipeline_h2d_bytes(self._pipe) if self._pipe else 0
+
     def close_pipeline(self):
         if self._pipe and _lib._lib is not None:
             _lib._lib.af_pipeline_free(self._pipe)

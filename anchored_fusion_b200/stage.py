@@ -486,13 +486,20 @@ def finish_stage(ga, out_prefix, anchored, mates, stats, id_base=0):
     return stats
 
 
-def anchor_stage_multi(gene_anchorers, fastq1, fastq2, out_prefixes, batch_pairs=1 << 20, thread="0"):
+def default_batch_pairs():
+    """Pairs per packed host batch (AF_BATCH_PAIRS overrides it: tests use small batches to exercise the
+    multi-batch and multi-rank paths on small samples)."""
+    import os
+    return int(os.environ.get("AF_BATCH_PAIRS", str(1 << 20)))
+
+
+def anchor_stage_multi(gene_anchorers, fastq1, fastq2, out_prefixes, batch_pairs=None, thread="0"):
     """The anchoring stage for several genes with ONE pass over the FASTQ pair.  Under torchrun
     (WORLD_SIZE > 1) the batches are dealt to the ranks, each rank anchors its share on its own GPU and
     rank 0 -- which gets every rank's records -- writes the one set of files; the other ranks return None."""
     rank, world, group = _host_group()
-    results, _ = scan_fastq_pair_multi([(ga.index, ga.engine) for ga in gene_anchorers], fastq1, fastq2, batch_pairs,
-                                       threads=host_threads(thread), rank=rank, world=world)
+    results, _ = scan_fastq_pair_multi([(ga.index, ga.engine) for ga in gene_anchorers], fastq1, fastq2,
+                                       batch_pairs or default_batch_pairs(), threads=host_threads(thread), rank=rank, world=world)
     results = gather_results(results, group, rank, world)
     if results is None:
         return None
@@ -500,7 +507,7 @@ def anchor_stage_multi(gene_anchorers, fastq1, fastq2, out_prefixes, batch_pairs
 
 
 def anchor_stage(file_anchored_seq, fastq1, fastq2, out_prefix, thread="1", gpu_number="-1", gene_name=None,
-                 batch_pairs=1 << 20, kp=0, gene_anchorer=None):
+                 batch_pairs=None, kp=0, gene_anchorer=None):
     """Drop-in for the anchoring stage.  file_anchored_seq is <work>_anchored_gene_sequence.fa; `thread` is the
     reader's worker count, as it is bwa's in the reference.  Returns a stats dict (None on ranks other than 0
     of a torchrun job); see write_stage_outputs for the files."""
@@ -533,7 +540,7 @@ def empty_stage_files(prefix, gene, anchor_len, cache={}):
             "tmp1": prefix + "_tmp_1.fastq", "tmp2": prefix + "_tmp_2.fastq", "raw_sam": prefix + "_anchored_reads.raw.sam"}
 
 
-def anchor_cells(gene_anchorers, cell_files, prefix_of, batch_pairs=1 << 20, thread="0", on_cell=None):
+def anchor_cells(gene_anchorers, cell_files, prefix_of, batch_pairs=None, thread="0", on_cell=None):
     """Single-cell layout (Anchored_Fusion_singlecell.py:86-113,205-231: one FASTQ pair per cell, the stage run
     once per gene and cell).  All cells of `cell_files` ([(cell, fastq1, fastq2)]) are decoded concurrently and
     packed back to back into shared batches -- the GPU sees 1 M-pair launches, not one launch per 5 k-pair
@@ -544,8 +551,8 @@ def anchor_cells(gene_anchorers, cell_files, prefix_of, batch_pairs=1 << 20, thr
     t0 = time.time()
     f1 = [c[1] for c in cell_files]
     f2 = [c[2] for c in cell_files]
-    results, info = scan_fastq_pair_multi([(ga.index, ga.engine) for ga in gene_anchorers], f1, f2, batch_pairs,
-                                          threads=host_threads(thread))
+    results, info = scan_fastq_pair_multi([(ga.index, ga.engine) for ga in gene_anchorers], f1, f2,
+                                          batch_pairs or default_batch_pairs(), threads=host_threads(thread))
     t1 = time.time()
     starts = info["file_starts"]
     assert len(starts) == len(cell_files), "reader reported %d of %d cells" % (len(starts), len(cell_files))

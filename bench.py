@@ -3,8 +3,10 @@
 
   python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA path
   python bench.py --impl reference [...]                     the reference arm on the host cores
+  python bench.py --workload config3 ...                     100 M pairs read-sharded over the ranks (strong scaling)
+  python bench.py --workload singlecell ...                  configs[4]: 20 M pairs in thousands of per-cell FASTQ.gz pairs
 
-A step = one pass of the hot path (seed scan -> compaction -> verify/extend -> compaction)
+A step = one pass of the hot path (seed scan -> compaction -> verify -> extend -> compaction)
 over one batch of synthetic 2x150 bp pairs resident in HBM (BASELINE.json configs[1]:
 10M pairs against a 6 783 bp anchored CDS cut from a random 10 Mbp reference).  Under torchrun
 every rank owns its own 10M-pair shard (weak scaling) and every rank receives all ranks' hit
@@ -16,7 +18,9 @@ import argparse
 import ctypes
 import json
 import os
+import shutil
 import sys
+import tempfile
 import threading
 import time
 
@@ -25,28 +29,40 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALG_BYTES_PER_PAIR = {150: 76, 101: 52}   # 2 * ceil(2L/8), SURVEY.md 8d
 METRIC = "read_pairs_per_s_anchored"
 
 
 def alg_bytes(read_len):
-    return 2 * ((2 * read_len + 7) // 8)
+    return 2 * ((2 * read_len + 7) // 8)        # 76 B for 2x150, SURVEY.md 8d
 
 
-def workload(args):
-    import anchored_fusion_b200 as af
-    return af.synth_spec(seed=1, ref_len=10_000_000, anchor_start=2_000_000, anchor_len=args.anchor_len,
-                         read_len=args.read_len, frag_mean=2 * args.read_len, frag_sd=30, sub_ppm=args.sub_ppm,
-                         fusion_ppm=args.fusion_ppm)
+def spec_kwargs(args):
+    return dict(seed=1, ref_len=10_000_000, anchor_start=2_000_000, anchor_len=args.anchor_len, read_len=args.read_len,
+                frag_mean=2 * args.read_len, frag_sd=30, sub_ppm=args.sub_ppm, fusion_ppm=args.fusion_ppm)
+
+
+def pairs_per_gpu(args, n_gpus):
+    if args.workload == "config3":
+        return (args.total_pairs // n_gpus + 31) // 32 * 32
+    return args.pairs
 
 
 def config_dict(args, n_gpus):
-    return {"workload": "configs[1]: %d synthetic 2x%d bp pairs per GPU, one %d bp anchored CDS on a random 10 Mbp "
-                        "reference (seeded generator, %d ppm substitutions, %d ppm fusion fragments)"
-                        % (args.pairs, args.read_len, args.anchor_len, args.sub_ppm, args.fusion_ppm),
-            "pairs_per_gpu": args.pairs, "read_len": args.read_len, "anchor_len": args.anchor_len,
+    """The workload, identical for both arms (`--impl reference` included): nothing about HOW it is run."""
+    n = pairs_per_gpu(args, n_gpus)
+    if args.workload == "config3":
+        what = "configs[2]: %d synthetic 2x%d bp pairs, single anchor, read-sharded over %d GPU(s) (%d pairs each)" % (
+            args.total_pairs, args.read_len, n_gpus, n)
+    elif args.workload == "singlecell":
+        what = "configs[4]: single-cell layout, %d cells x %d synthetic 2x%d bp pairs as per-cell FASTQ.gz pairs, cells dealt to %d GPU(s)" % (
+            args.cells, args.pairs_per_cell, args.read_len, n_gpus)
+    else:
+        what = "configs[1]: %d synthetic 2x%d bp pairs per GPU" % (n, args.read_len)
+    return {"workload": what + ", one %d bp anchored CDS on a random 10 Mbp reference (seeded generator, %d ppm substitutions, "
+                               "%d ppm fusion fragments)" % (args.anchor_len, args.sub_ppm, args.fusion_ppm),
+            "pairs_per_gpu": n, "read_len": args.read_len, "anchor_len": args.anchor_len,
             "sharding": "reads x%d, hit lists delivered to every rank" % n_gpus,
-            "l2_policy": "input per step (%.0f MB) exceeds the 126 MB L2; no flush needed" % (args.pairs * 80 / 1e6)}
+            "l2_policy": "input per step (%.0f MB) exceeds the 126 MB L2; no flush needed" % (n * 80 / 1e6)}
 
 
 class ClockSampler(threading.Thread):
@@ -90,68 +106,26 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_sample(args, n_pairs):
-    """The first n_pairs pairs of the workload as base codes for the CPU arm (generated once, by all cores)."""
-    from concurrent.futures import ThreadPoolExecutor
-    import anchored_fusion_b200 as af
+# ---- the CPU arm: oracle/ only (its own generator, af_synth.cpp: no product library is loaded) ---------------
+def cpu_sample(args, n_pairs, first_pair=0):
+    """Pairs [first_pair, first_pair + n_pairs) of the workload as base codes (generated by all cores)."""
     from oracle import oracle
-    spec = workload(args)
-    anchor = oracle.encode(af.synth_anchor(spec))
-    reads = np.empty((2 * n_pairs, spec.read_len), dtype=np.uint8)
+    spec = oracle.synth_spec(**spec_kwargs(args))
+    anchor = oracle.encode(oracle.synth_anchor(spec))
     threads = os.cpu_count() or 1
-    step = (n_pairs + threads - 1) // threads
-
-    def fill(lo):
-        hi = min(lo + step, n_pairs)
-        m1, m2 = af.synth_pairs_host(spec, lo, hi - lo)          # a ctypes call: runs without the GIL
-        reads[2 * lo: 2 * hi: 2], reads[2 * lo + 1: 2 * hi: 2] = m1, m2
-
-    with ThreadPoolExecutor(max_workers=threads) as pool:
-        list(pool.map(fill, range(0, n_pairs, step)))
+    reads = oracle.synth_reads(spec, first_pair, n_pairs, threads=threads)
     oracle.anchor_reads(anchor, reads[:2000], threads=threads)   # warm the library
     return anchor, reads
 
 
-def cpu_reference_rate(args, n_pairs, threads, sample=None):
-    """The CPU arm: oracle/af_oracle.c (a port: the reference's own path is bwa/samtools, absent)."""
+def cpu_reference_rate(n_pairs, threads, sample):
+    """oracle/af_oracle.c (a port: the reference's own path is bwa/samtools, absent here and on the GPU box)."""
     from oracle import oracle
-    anchor, reads = sample if sample is not None else cpu_sample(args, n_pairs)
+    anchor, reads = sample
     t0 = time.perf_counter()
     hits = oracle.anchor_reads(anchor, reads, threads=threads)
     dt = time.perf_counter() - t0
-    return n_pairs / dt, dt, len(hits)
-
-
-def fastq_gz_rate(args, spec, index, eng):
-    """A bounded sample of the workload written as two FASTQ.gz files, then read back through the whole
-    host path (inflate threads, parser, packer, pinned staging, GPU pipeline, record retrieval)."""
-    import gzip
-    import shutil
-    import tempfile
-    import anchored_fusion_b200 as af
-    from anchored_fusion_b200.stage import scan_fastq_pair
-    n = args.fastq_pairs
-    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
-    d = tempfile.mkdtemp(prefix="af_bench_fq_")
-    try:
-        p1, p2 = os.path.join(d, "s_1.fastq.gz"), os.path.join(d, "s_2.fastq.gz")
-        qual = "I" * args.read_len
-        with gzip.open(p1, "wt", compresslevel=1) as f1, gzip.open(p2, "wt", compresslevel=1) as f2:
-            for lo in range(0, n, 100_000):
-                m1, m2 = af.synth_pairs_host(spec, lo, min(100_000, n - lo))
-                a1, a2 = lut[m1], lut[m2]
-                f1.write("".join("@frag%d/1\n%s\n+\n%s\n" % (lo + i, a1[i].tobytes().decode(), qual) for i in range(len(a1))))
-                f2.write("".join("@frag%d/2\n%s\n+\n%s\n" % (lo + i, a2[i].tobytes().decode(), qual) for i in range(len(a2))))
-        scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 20)          # warm-up: staging buffers, page cache
-        t0 = time.perf_counter()
-        anchored, mates, stats = scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 20)
-        dt = time.perf_counter() - t0
-        return {"value": n / dt, "unit": "pairs/s", "pairs": n, "seconds": dt, "anchored_reads": len(anchored),
-                "gz_bytes": os.path.getsize(p1) + os.path.getsize(p2),
-                "path": "two FASTQ.gz files -> 2 inflate + 2 parse/pack threads -> pinned tiles -> af_pipeline_run -> records",
-                "bound": "zlib inflate of the two files"}
-    finally:
-        shutil.rmtree(d, ignore_errors=True)
+    return n_pairs / dt, dt, hits
 
 
 def run_reference(args):
@@ -163,17 +137,146 @@ def run_reference(args):
     data = cpu_sample(args, sample)
     rates = []
     for i in range(args.warmup + args.steps):
-        rate, dt, nh = cpu_reference_rate(args, sample, threads, data)
+        rate, dt, _ = cpu_reference_rate(sample, threads, data)
         if i >= args.warmup:
             rates.append((rate, dt))
     value = sample * len(rates) / sum(dt for _, dt in rates)
     desc = "%d of the workload's pairs per step, oracle/af_oracle.c with %d OpenMP threads" % (sample, threads)
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(dt for _, dt in rates) / len(rates),
-                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                      "higher_is_better": True, "scaling": "strong" if args.workload == "config3" else "weak",
+                      "vs_baseline": None, "dtype": "u8",
                       "data": "synthetic", "config": config_dict(args, args.gpus),
                       "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
                       "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---- FASTQ files on disk -> records (the third rate) --------------------------------------------
+def fastq_rates(args, index, eng):
+    """A bounded sample of the workload written as FASTQ files by oracle/af_synth.cpp (Illumina-style names,
+    binned qualities), then read back through the whole host path (task-parallel reader, packer, pinned staging,
+    GPU pipeline, record retrieval) once per format."""
+    from oracle import oracle
+    from anchored_fusion_b200.stage import scan_fastq_pair
+    n = args.fastq_pairs
+    spec = oracle.synth_spec(**spec_kwargs(args))
+    d = tempfile.mkdtemp(prefix="af_bench_fq_")
+    out = {}
+    try:
+        for key, fmt, ext, level in (("bgzf", oracle.FASTQ_BGZF, ".fastq.gz", 1), ("gzip", oracle.FASTQ_GZIP, ".fastq.gz", 1),
+                                     ("plain", oracle.FASTQ_PLAIN, ".fastq", 0)):
+            p1, p2 = os.path.join(d, key + "_1" + ext), os.path.join(d, key + "_2" + ext)
+            oracle.synth_fastq(spec, 0, n, [p1], [p2], fmt, level, threads=2)
+            scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 19, threads=args.threads)      # warm-up: staging, page cache
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                anchored, mates, stats = scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 19, threads=args.threads)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            out[key] = {"value": n / best, "unit": "pairs/s", "pairs": n, "seconds": best, "anchored_reads": len(anchored),
+                        "file_bytes": os.path.getsize(p1) + os.path.getsize(p2)}
+            os.remove(p1)
+            os.remove(p2)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    threads = args.threads or (os.cpu_count() or 1)
+    res = dict(out["bgzf"])
+    res.update({"format": "BGZF-compressed .fastq.gz (bgzip): independent <= 64 KB blocks, inflated in parallel",
+                "threads": threads, "host_cores": os.cpu_count(),
+                "path": "two FASTQ files -> %d-worker reader (own DEFLATE decoder, newline index, CRC, SIMD 2-bit pack) -> pinned "
+                        "tiles -> af_pipeline_run -> records" % threads,
+                "single_member_gzip": dict(out["gzip"], format="one gzip member per file (gzip / bcl2fastq style): a serial bit "
+                                           "stream, one inflate thread per file; index / CRC / pack on the workers"),
+                "plain_text": out["plain"],
+                "input": "oracle/af_synth.cpp: Illumina-style read names, binned qualities (F : , #), deflate level 1"})
+    return res
+
+
+# ---- configs[4]: the single-cell layout --------------------------------------------------------------------------
+def run_singlecell(args):
+    """Thousands of per-cell FASTQ.gz pairs through the single-cell stage (all of a rank's cells through one
+    reader, shared GPU batches, per-cell files).  Timed: decode -> pack -> H2D -> kernels -> D2H -> files."""
+    import torch
+    from anchored_fusion_b200.stage import GeneAnchorer, anchor_cells
+    from oracle import oracle
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    spec = oracle.synth_spec(**spec_kwargs(args))
+    root = tempfile.mkdtemp(prefix="af_bench_sc_%d_" % rank)
+    try:
+        cells_dir, out_dir = os.path.join(root, "cells"), os.path.join(root, "out")
+        os.makedirs(cells_dir)
+        mine = list(range(rank, args.cells, world))
+        f1 = [os.path.join(cells_dir, "cell%06d_1.fastq.gz" % c) for c in mine]
+        f2 = [os.path.join(cells_dir, "cell%06d_2.fastq.gz" % c) for c in mine]
+        t0 = time.perf_counter()
+        cores = max(1, (os.cpu_count() or 1) // world)
+        # cell c holds pairs [c * ppc, (c + 1) * ppc) of the generator; one generator call writes a run of
+        # consecutive cells (all of them when there is one rank), calls run side by side otherwise
+        ppc = args.pairs_per_cell
+        if world == 1:
+            for k in range(0, len(mine), 512):
+                oracle.synth_fastq(spec, mine[k] * ppc, ppc, f1[k: k + 512], f2[k: k + 512], oracle.FASTQ_GZIP, 1, threads=cores)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=max(1, cores // 2)) as pool:
+                list(pool.map(lambda k: oracle.synth_fastq(spec, mine[k] * ppc, ppc, [f1[k]], [f2[k]], oracle.FASTQ_GZIP, 1, threads=2),
+                              range(len(mine))))
+        gen_s = time.perf_counter() - t0
+        fa = os.path.join(root, "anchor.fa")
+        with open(fa, "w") as fh:
+            fh.write(">GENE0\n" + oracle.synth_anchor(spec).decode() + "\n")
+        ga = GeneAnchorer(fa, str(local), "GENE0")
+
+        def prefix_of(gene, cell):
+            dd = os.path.join(out_dir, gene, "work_dir", cell)
+            os.makedirs(dd, exist_ok=True)
+            return os.path.join(dd, gene + "_fusion")
+
+        cell_files = [("cell%06d" % c, a, b) for c, a, b in zip(mine, f1, f2)]
+        anchor_cells([ga], cell_files[: min(len(cell_files), 64)], prefix_of, thread=str(args.threads))     # warm-up: buffers, page cache
+        shutil.rmtree(out_dir, ignore_errors=True)
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        t0 = time.perf_counter()
+        res = anchor_cells([ga], cell_files, prefix_of, thread=str(args.threads))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        totals = [res["pairs"], res["anchored"], dt, res["seconds_scan"], res["seconds_write"]]
+        if world > 1:
+            box = [None] * world
+            dist.all_gather_object(box, totals)
+            totals = [sum(b[0] for b in box), sum(b[1] for b in box), max(b[2] for b in box), max(b[3] for b in box), max(b[4] for b in box)]
+        if rank == 0:
+            from anchored_fusion_b200._lib import lib
+            pairs, anchored, dt, t_scan, t_write = totals
+            value = pairs / dt
+            return ({
+                "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config_dict(args, world),
+                "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": int(pairs * 80), "d2h_bytes_per_step": int(anchored * 16),
+                        "path": "per-cell FASTQ.gz pairs -> one reader per rank (cells decoded concurrently, packed back to back) -> "
+                                "shared GPU batches -> hit lists split per cell -> per-cell BAM / FASTQ / SAM files"},
+                "singlecell": {"cells": args.cells, "pairs_per_cell": args.pairs_per_cell, "anchored_reads": anchored,
+                               "seconds_decode_and_gpu": t_scan, "seconds_per_cell_files": t_write,
+                               "ms_per_cell_files": 1e3 * t_write / max(len(mine), 1), "cells_per_s": args.cells / dt,
+                               "reader_threads_per_rank": res["threads"], "fixture_generation_s": gen_s},
+                "roofline": None, "cpu_baseline": None, "gpu_launches": int(lib().af_kernel_launches()), "clocks": clocks})
+        return None
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
 
 
 def main():
@@ -182,7 +285,13 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step")
+    ap.add_argument("--workload", default="config1", choices=["config1", "config3", "singlecell"],
+                    help="config1: BASELINE configs[1], 10 M pairs per GPU per step (weak scaling, default); config3: configs[2], "
+                         "--total-pairs read-sharded over the ranks (strong scaling); singlecell: configs[4] through the single-cell stage")
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step (config1)")
+    ap.add_argument("--total-pairs", type=int, default=100_000_000, help="pairs of the whole job (config3)")
+    ap.add_argument("--cells", type=int, default=4000)
+    ap.add_argument("--pairs-per-cell", type=int, default=5000)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--anchor-len", type=int, default=6783)
     ap.add_argument("--sub-ppm", type=int, default=10_000)
@@ -193,15 +302,17 @@ def main():
     ap.add_argument("--slots", type=int, default=3, help="workspace slots / streams consecutive steps alternate between")
     ap.add_argument("--graphs", type=int, default=0, help="1: replay one CUDA graph per slot in the throughput region")
     ap.add_argument("--cand-cap", type=int, default=0, help="candidate capacity per batch (default 2 x pairs: every read)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="iterations of the host-buffer end-to-end region (0: --steps, at most 50)")
     ap.add_argument("--cpu-pairs", type=int, default=10_000_000, help="bounded sample for cpu_baseline")
     ap.add_argument("--ref-pairs", type=int, default=10_000_000, help="pairs per step of the reference arm")
+    ap.add_argument("--parity-pairs", type=int, default=1_000_000, help="pairs per rank compared with the oracle after the clock (0: skip)")
+    ap.add_argument("--threads", type=int, default=0, help="FASTQ reader workers (0: one per host core)")
     ap.add_argument("--gather-cap", type=int, default=0, help="hit records per rank in the per-step all-gather "
                     "(0: sized from a probe pass, 1.25 x the largest per-rank hit count, rounded up to 4096)")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N > 1: how the ranks' hit lists reach every rank -- p2p: the hit-compaction kernel stores them "
                          "into every GPU's log over NVLink peer memory; nccl: one all-gather per step")
-    ap.add_argument("--fastq-pairs", type=int, default=500_000, help="pairs of the FASTQ.gz end-to-end sample (0: skip)")
+    ap.add_argument("--fastq-pairs", type=int, default=1_000_000, help="pairs of the FASTQ end-to-end samples (0: skip)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -214,6 +325,17 @@ def main():
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
+    if args.workload == "singlecell":
+        obj = run_singlecell(args)
+        if obj is not None:
+            emit(obj)
+        return
+
     import torch
     import anchored_fusion_b200 as af
     from anchored_fusion_b200 import dist as afdist
@@ -237,22 +359,25 @@ def main():
         for m in modes:
             check(L.af_seed_scan_config(0, m))
 
-    spec = workload(args)
+    spec = af.synth_spec(**spec_kwargs(args))
     index = af.AnchorIndex(af.synth_anchor(spec), kp=args.kp)
     eng = af.Anchorer(index, local)
-    n = args.pairs
-    batch = af.synth_pairs_device(spec, rank * n, n, index.pad_byte, local)   # this rank's shard
+    n = pairs_per_gpu(args, world)
+    first_pair = rank * n
+    batch = af.synth_pairs_device(spec, first_pair, n, index.pad_byte, local)   # this rank's shard
     torch.cuda.synchronize()
+    n_slots = max(1, args.slots)
+    cand_cap = args.cand_cap or 2 * n
+    if args.workload == "config3":
+        cand_cap = args.cand_cap or max(n // 4, 1 << 20)       # 2 % of the reads are flagged; 12.5 % is ample and keeps 3 slots small
     gather_cap = args.gather_cap
     if world > 1 and gather_cap <= 0:
-        _, probe = eng.anchor(batch)
+        _, probe = eng.anchor(batch, cand_cap=cand_cap)
         t = torch.tensor([probe["hits"]], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gather_cap = (int(t.item()) * 5 // 4 + 4095) // 4096 * 4096
 
     profiling = [False]
-    n_slots = max(1, args.slots)
-    cand_cap = args.cand_cap or 2 * n
     exchange = None
     if world > 1 and args.exchange == "p2p" and not args.graphs:
         # a log region takes the batches of one slot of one rank for a whole timed region
@@ -267,7 +392,6 @@ def main():
     graphs = {}
     if args.graphs:
         # one CUDA graph per workspace slot: memsets + kernels of af_anchor_batch, replayed each step
-        # (removes the host launch gaps between the eight small operations of a step)
         for sl in range(n_slots):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=streams[sl] if sl else None):
@@ -315,7 +439,7 @@ def main():
             cur.wait_event(join)
         return out
 
-    out = run_steps(args.warmup)
+    run_steps(args.warmup)
     barrier()
     if exchange is not None:
         exchange.reset()
@@ -326,7 +450,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    out = run_steps(args.steps)
+    run_steps(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -363,6 +487,53 @@ def main():
         step_base[0] = args.steps
         exchange.reset()
 
+    # ---- parity, outside the clock: what the ranks DELIVERED for the first --parity-pairs pairs of every shard
+    # (through the same exchange the timed steps used) against the CPU oracle on the same pairs; rank 0 judges
+    parity = None
+    if args.parity_pairs > 0:
+        pp = min(args.parity_pairs, n) // 32 * 32
+        lay_p = af.layout(args.read_len, pp)
+        sub = af.PackedBatch(batch.packed[: lay_p.packed_bytes // 4], pp, args.read_len, args.read_len)
+        delivered = {}
+        if exchange is not None:
+            with torch.cuda.stream(streams[0]):
+                eng.enqueue(sub, cand_cap=2 * pp, slot=0, exchange=exchange, pair_base=first_pair)
+            for src, base, h in exchange.collect():
+                delivered[src] = h.copy()
+            exchange.reset()
+        elif world > 1:
+            with torch.cuda.stream(streams[0]):
+                eng.enqueue(sub, cand_cap=2 * pp, slot=0)
+                ac, ah = afdist.gather_hits_tensor(eng.counts_and_hits(0), gather_cap)
+            torch.cuda.synchronize()
+            ac, ah = ac.cpu().numpy(), ah.cpu().numpy()
+            for r in range(world):
+                delivered[r] = np.ascontiguousarray(ah[r, : ac[r]]).view(np.uint8).reshape(-1).view(af.HIT_DTYPE).copy()
+        else:
+            delivered[0], _ = eng.anchor(sub)
+        if rank == 0:
+            from oracle import oracle
+            ospec = oracle.synth_spec(**spec_kwargs(args))
+            acodes = oracle.encode(oracle.synth_anchor(ospec))
+            equal, n_rec = True, 0
+            for r in range(world):
+                reads = oracle.synth_reads(ospec, r * n, pp, threads=os.cpu_count() or 1)
+                want = oracle.anchor_reads(acodes, reads, threads=os.cpu_count() or 1)
+                got_r = delivered.get(r)
+                ok = got_r is not None and len(got_r) == len(want) and got_r.tobytes() == want.tobytes()
+                equal = equal and ok
+                n_rec += len(want)
+            parity = {"pairs": pp * world, "records": n_rec, "equal": bool(equal),
+                      "compared": "16-byte records each rank delivered (%s) for the first %d pairs of its shard vs oracle/af_oracle.c on the same pairs"
+                                  % ("p2p hit log as rank 0 holds it" if exchange is not None else ("NCCL all-gather" if world > 1 else "af_anchor_batch"), pp)}
+        flag = torch.tensor([1 if (parity is None or parity["equal"]) else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.broadcast(flag, 0)
+        if int(flag.item()) == 0:
+            if rank == 0:
+                print("bench.py: PARITY FAILURE -- delivered records differ from the oracle: %s" % json.dumps(parity), file=sys.stderr)
+            sys.exit(3)
+
     # Second timed region, the same K steps on ONE stream, with CUDA events recorded on that stream
     # around every stage (af_profile_*): clean per-kernel durations for the roofline.  (In the
     # region above consecutive steps overlap across streams, which is right for throughput but
@@ -374,7 +545,7 @@ def main():
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     s0.record()
-    out = run_steps(args.steps)
+    run_steps(args.steps)
     s1.record()
     barrier()
     serial_ms_per_step = s0.elapsed_time(s1) / args.steps
@@ -405,6 +576,7 @@ def main():
                 "measured": "CUDA events on the launching stream around each of the %d launches of a second timed "
                             "region (same steps, one stream)" % stage_calls[0],
                 "serial_ms_per_step": serial_ms_per_step,
+                "whole_step_frac": alg_bytes(args.read_len) * n / (ms_per_step * 1e-3) / 1e9 / peak,
                 "stage_ms_per_step": {"seed_scan": stage_ms[0] / args.steps, "flag_compaction": stage_ms[1] / args.steps,
                                       "verify": stage_ms[2] / args.steps, "extend": stage_ms[3] / args.steps,
                                       "hit_compaction": stage_ms[4] / args.steps}}
@@ -412,42 +584,67 @@ def main():
     # end to end through the host-buffer C-ABI call: pinned host batch -> H2D -> kernels -> D2H hits
     e2e = None
     if not args.no_e2e:
+        e2e_steps = args.e2e_steps or min(args.steps, 50)
         lay = af.layout(args.read_len, n)
         hptr = L.af_host_alloc(lay.packed_bytes)
         host_packed = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint32)), (lay.packed_bytes // 4,))
         host_packed[:] = batch.packed.cpu().numpy().view(np.uint32)
         hb = af.PackedBatch(host_packed, n, args.read_len, args.read_len)
-        hits_out = np.zeros(1 << 20, dtype=af.HIT_DTYPE)
-        eng.anchor_host(hb, hits_out=hits_out)                  # warm-up (allocates the slots)
+        hits_out = np.zeros(max(1 << 20, n // 16), dtype=af.HIT_DTYPE)
+        for _ in range(3):
+            eng.anchor_host(hb, hits_out=hits_out)              # warm-up (allocates the slots)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+        for _ in range(e2e_steps):
             h, st = eng.anchor_host(hb, hits_out=hits_out)
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
+        dt = (time.perf_counter() - t0) / e2e_steps
+        # the ceiling the fabric in front of the GPUs sets for this: the same tiles through cudaMemcpyAsync alone,
+        # all ranks copying at once
+        h2d_stream = torch.cuda.Stream(device=dev)
+        pinned_view = torch.empty(host_packed.shape, dtype=torch.int32, pin_memory=True)
+        pinned_view.numpy()[:] = host_packed.view(np.int32)
+        dst = torch.empty_like(batch.packed)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(h2d_stream):
+            dst.copy_(pinned_view, non_blocking=True)
+        barrier()
+        with torch.cuda.stream(h2d_stream):
+            c0.record()
+            for _ in range(max(3, e2e_steps // 4)):
+                dst.copy_(pinned_view, non_blocking=True)
+            c1.record()
+        barrier()
+        copy_ms = c0.elapsed_time(c1) / max(3, e2e_steps // 4)
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt, copy_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt, copy_ms = float(t[0].item()), float(t[1].item())
         e2e = {"value": world * n / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(lay.packed_bytes),
                "d2h_bytes_per_step": int(len(h) * 16 + 32 * ((n + (1 << 20) - 1) >> 20)), "ms_per_step": dt * 1e3,
+               "steps": e2e_steps,
                "path": "af_pipeline_run: pinned host tiles -> cudaMemcpyAsync -> kernels -> hit list on host",
+               "h2d_only_ceiling": {"ms_per_step": copy_ms, "pairs_per_s": world * n / (copy_ms * 1e-3),
+                                    "gb_per_s_all_ranks": world * lay.packed_bytes / (copy_ms * 1e-3) / 1e9,
+                                    "what": "the same %d MB of tiles per rank through cudaMemcpyAsync alone, all %d rank(s) at once, max over ranks"
+                                            % (lay.packed_bytes // 1_000_000, world)},
                "host_cpus_rank0": ("%d CPUs local to the GPU (NVML affinity)" % len(cpus)) if cpus else "unbound"}
+        del dst, pinned_view
         eng.close_pipeline()
         L.af_host_free(hptr)
 
-    # third rate: FASTQ.gz files on disk -> zlib reader -> packer -> pipeline -> records
+    # third rate: FASTQ files on disk -> reader -> packer -> pipeline -> records
     fastq = None
-    if rank == 0 and world == 1 and args.fastq_pairs > 0 and not args.no_e2e:
-        fastq = fastq_gz_rate(args, spec, index, eng)
+    if rank == 0 and world == 1 and args.fastq_pairs > 0 and not args.no_e2e and args.workload == "config1":
+        fastq = fastq_rates(args, index, eng)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         data = cpu_sample(args, args.cpu_pairs)
-        rate, dt, nh = cpu_reference_rate(args, args.cpu_pairs, threads, data)
+        rate, dt, _ = cpu_reference_rate(args.cpu_pairs, threads, data)
         n1 = min(args.cpu_pairs, 2_000_000)                      # and one core alone, on the first 2 M pairs
-        rate1, dt1, _ = cpu_reference_rate(args, n1, 1, (data[0], data[1][: 2 * n1]))
+        rate1, dt1, _ = cpu_reference_rate(n1, 1, (data[0], data[1][: 2 * n1]))
         cpu = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port",
                "sample": "first %d pairs of the workload, oracle/af_oracle.c, %d OpenMP threads, %.1f s"
                          % (args.cpu_pairs, threads, dt),
@@ -455,15 +652,15 @@ def main():
 
     if rank == 0:
         nh = int(stats_counts[1])
-        sys.stdout.flush()
-        os.write(real_stdout, (json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": dict(config_dict(args, world), streams=n_slots, cuda_graphs=bool(args.graphs), exchange=exchange_info), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq_gz": fastq,
-                          "gpu_launches": int(launches), "clocks": clocks,
-                          "per_step": {"flagged_reads": int(stats_counts[0]), "seeded_reads": int(stats_counts[3]),
-                                       "anchored_reads": nh,
-                                       "kp": index.info.kp, "stride": index.info.stride}}) + "\n").encode())
+        emit({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+              "scaling": "strong" if args.workload == "config3" else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+              "config": config_dict(args, world),
+              "run": {"streams": n_slots, "cuda_graphs": bool(args.graphs), "exchange": exchange_info},
+              "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq_gz": fastq, "parity": parity,
+              "gpu_launches": int(launches), "clocks": clocks,
+              "per_step": {"flagged_reads": int(stats_counts[0]), "seeded_reads": int(stats_counts[3]),
+                           "anchored_reads": nh, "kp": index.info.kp, "stride": index.info.stride}})
     if exchange is not None:
         barrier()
         exchange.close()

@@ -33,3 +33,94 @@ extern "C" int afo_synth_reads(const af_synth_t *s, int64_t first_pair, int64_t 
     }
     return 0;
 }
+
+// ---- the same pairs as FASTQ files (measurement input for the ingest path) -------------------------------
+// Illumina-style names (both mates share the name up to the blank), binned qualities the way current
+// instruments write them (mostly 'F', ~8 % of the bases in one of three lower bins, in short runs).
+// format 0: plain text, 1: one gzip member (zlib), 2: BGZF (bgzip: independent <= 64 KB blocks).
+#include <zlib.h>
+#include <algorithm>
+#include <cstring>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+static void fastq_text(const af_synth_t *s, int64_t first_pair, int64_t n, int mate, std::string &out) {
+    const int L = s->read_len;
+    out.clear();
+    out.reserve((size_t)n * (size_t)(2 * L + 64));
+    char name[96];
+    for (int64_t p = 0; p < n; p++) {
+        const int64_t g = first_pair + p;
+        af_frag f = af_make_frag(*s, g);
+        const int nl = snprintf(name, sizeof(name), "@A00123:45:HXXXXXX:%d:%d:%d:%d %d:N:0:ACGTACGT\n", 1 + (int)((g >> 24) & 3),
+                                1101 + (int)((g >> 17) % 600), (int)((g * 7) % 32768), (int)(g % 100000), mate + 1);
+        out.append(name, (size_t)nl);
+        for (int i = 0; i < L; i++) out += "ACGTN"[af_read_base(*s, f, mate, i)];
+        out += "\n+\n";
+        uint32_t h = af_mix32((uint32_t)g * 2654435761u + (uint32_t)mate);
+        char q = 'F';
+        for (int i = 0; i < L; i++) {
+            if ((i & 7) == 0) h = af_mix32(h + (uint32_t)i);
+            const uint32_t r = (h >> ((i & 7) * 4)) & 15u;
+            if (r == 0) q = ":,#F"[(h >> 28) & 3];       // a new run starts: ~1 base in 16
+            else if (r < 6) q = 'F';
+            out += q;
+        }
+        out += '\n';
+    }
+}
+
+static bool write_bgzf(FILE *fh, const std::string &t, int level) {
+    std::vector<unsigned char> comp(70000);
+    for (size_t i = 0; i < t.size(); i += 0xFF00) {
+        const size_t n = std::min<size_t>(0xFF00, t.size() - i);
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+        zs.next_in = (Bytef *)t.data() + i; zs.avail_in = (uInt)n;
+        zs.next_out = comp.data(); zs.avail_out = (uInt)comp.size();
+        deflate(&zs, Z_FINISH);
+        const unsigned clen = (unsigned)zs.total_out, bsize = clen + 25;
+        deflateEnd(&zs);
+        const unsigned char hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (unsigned char)(bsize & 255), (unsigned char)(bsize >> 8)};
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)t.data() + i, (uInt)n), isz = (uint32_t)n;
+        unsigned char tail[8];
+        for (int k = 0; k < 4; k++) { tail[k] = (unsigned char)(crc >> (8 * k)); tail[4 + k] = (unsigned char)(isz >> (8 * k)); }
+        if (fwrite(hdr, 1, 18, fh) != 18 || fwrite(comp.data(), 1, clen, fh) != clen || fwrite(tail, 1, 8, fh) != 8) return false;
+    }
+    static const unsigned char eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    return fwrite(eof, 1, 28, fh) == 28;
+}
+
+static int write_one(const af_synth_t *s, int64_t first_pair, int64_t n, int mate, const char *path, int format, int level) {
+    std::string t;
+    fastq_text(s, first_pair, n, mate, t);
+    if (format == 1) {
+        char mode[8];
+        snprintf(mode, sizeof(mode), "wb%d", level);
+        gzFile g = gzopen(path, mode);
+        if (!g) return -1;
+        size_t off = 0;
+        while (off < t.size()) { const int w = gzwrite(g, t.data() + off, (unsigned)std::min<size_t>(t.size() - off, 1u << 30)); if (w <= 0) { gzclose(g); return -1; } off += (size_t)w; }
+        return gzclose(g) == Z_OK ? 0 : -1;
+    }
+    FILE *fh = fopen(path, "wb");
+    if (!fh) return -1;
+    bool ok = format == 2 ? write_bgzf(fh, t, level) : fwrite(t.data(), 1, t.size(), fh) == t.size();
+    return (fclose(fh) == 0 && ok) ? 0 : -1;
+}
+
+// n_files file pairs, file i holding pairs [first_pair + i * pairs_per_file, ... + pairs_per_file); paths1[i] / paths2[i]
+extern "C" int afo_synth_fastq(const af_synth_t *s, int64_t first_pair, int64_t pairs_per_file, int32_t n_files,
+                               const char *const *paths1, const char *const *paths2, int32_t format, int32_t level, int threads) {
+    if (!s || !paths1 || !paths2 || n_files <= 0 || pairs_per_file < 0) return -1;
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1) reduction(+ : bad)
+    for (int k = 0; k < 2 * n_files; k++) {
+        const int i = k >> 1, mate = k & 1;
+        if (write_one(s, first_pair + (int64_t)i * pairs_per_file, pairs_per_file, mate, mate ? paths2[i] : paths1[i], format, level)) bad++;
+    }
+    return bad ? -1 : 0;
+}

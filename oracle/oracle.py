@@ -60,7 +60,27 @@ def _synth_lib():
         _synth.afo_synth_reads.restype = ctypes.c_int
         _synth.afo_synth_reads.argtypes = [ctypes.POINTER(Synth), ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                            ctypes.c_int64, ctypes.c_int]
+        _synth.afo_synth_fastq.restype = ctypes.c_int
+        _synth.afo_synth_fastq.argtypes = [ctypes.POINTER(Synth), ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                           ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int]
     return _synth
+
+
+FASTQ_PLAIN, FASTQ_GZIP, FASTQ_BGZF = 0, 1, 2
+
+
+def synth_fastq(spec, first_pair, pairs_per_file, paths1, paths2, fmt=FASTQ_GZIP, level=6, threads=1):
+    """Write the generator's pairs as FASTQ files (measurement input of the ingest path): file i of paths1 /
+    paths2 holds mates 1 / 2 of pairs [first_pair + i * pairs_per_file, +pairs_per_file).  Illumina-style names,
+    binned qualities; fmt: FASTQ_PLAIN, FASTQ_GZIP (one member) or FASTQ_BGZF."""
+    spec = as_synth(spec)
+    n = len(paths1)
+    assert n == len(paths2) and n > 0
+    arr = ctypes.c_char_p * n
+    a1, a2 = arr(*[p.encode() for p in paths1]), arr(*[p.encode() for p in paths2])
+    rc = _synth_lib().afo_synth_fastq(ctypes.byref(spec), first_pair, pairs_per_file, n, a1, a2, fmt, level, threads)
+    assert rc == 0, "writing synthetic FASTQ files failed"
 
 
 def synth_spec(seed=1, ref_len=10_000_000, anchor_start=1_000_000, anchor_len=6783, read_len=150, frag_mean=300,

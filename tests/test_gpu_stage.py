@@ -181,3 +181,128 @@ def test_singlecell_two_genes_cells_dealt_to_ranks(bundled, tmp_path, monkeypatc
             for suffix in ("_tmp_1.fastq", "_tmp_2.fastq", "_split_points.txt"):
                 assert open(w1 + suffix).read() == open(w2 + suffix).read()
     assert total > 1500
+
+
+# ---- round 2 ---------------------------------------------------------------------------------------------------
+def _bulk_files(w):
+    return {s: open(w + s, "rb").read() for s in ("_anchored_reads.bam", "_realign_reads.bam", "_tmp_1.fastq", "_tmp_2.fastq",
+                                                 "_anchored_reads.raw.sam", "_split_points.txt")}
+
+
+def test_bulk_cli_two_torchrun_ranks_leave_byte_identical_files(bundled, tmp_path):
+    """Multi-GPU through the drop-in boundary: `torchrun --nproc-per-node 2 Anchored_Fusion.py ...` deals the read
+    batches to the ranks, each rank anchors its share on its GPU (the ranks share GPU 0 on a one-GPU box), rank 0
+    gets every rank's records and writes the one set of files -- byte for byte those of the one-process run."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from anchored_fusion_b200.cli import main_bulk
+    d = str(tmp_path)
+    a = bundled["anchor"]
+    second = a[2500:6000][::-1].translate(str.maketrans("ACGT", "TGCA"))
+    fa = os.path.join(d, "two.fa")
+    open(fa, "w").write(bundled["header"] + "\n" + a + "\n>NM_000000.1 RCBCR [organism=Homo sapiens]\n" + second + "\n")
+    p1, p2 = _write_bundled_fastqs(bundled, d)
+    os.environ["AF_BATCH_PAIRS"] = "1024"                     # 11 batches: every rank gets several
+    try:
+        out1 = os.path.join(d, "one")
+        assert main_bulk(["--file_anchored_cds", fa, "--fastq1", p1, "--fastq2", p2, "--out_folder", out1, "--thread", "3"]) == 0
+        out2 = os.path.join(d, "two")
+        env = dict(os.environ, AF_BATCH_PAIRS="1024")
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29571", os.path.join(ROOT, "Anchored_Fusion.py"), "--file_anchored_cds", fa, "--fastq1", p1,
+               "--fastq2", p2, "--out_folder", out2, "--thread", "3"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    finally:
+        os.environ.pop("AF_BATCH_PAIRS", None)
+    for gene in ("BCR", "RCBCR"):
+        w1 = os.path.join(out1, gene + "_fusion", "work_dir", gene + "_fusion")
+        w2 = os.path.join(out2, gene + "_fusion", "work_dir", gene + "_fusion")
+        f1, f2 = _bulk_files(w1), _bulk_files(w2)
+        assert len(f1["_anchored_reads.raw.sam"]) > 10_000
+        for k in f1:
+            assert f1[k] == f2[k], (gene, k)
+        assert not [f for f in os.listdir(os.path.dirname(w2)) if f.endswith(".partial")]
+
+
+def test_h2d_traffic_does_not_depend_on_the_number_of_genes(bundled):
+    """f4: a batch is copied to the GPU once and scanned for every anchor index while resident."""
+    import numpy as np
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200.stage import anchor_host_multi
+    a = bundled["anchor"]
+    seqs = [a, a[2500:6000][::-1].translate(str.maketrans("ACGT", "TGCA")), a[1000:4000], a[3000:]]
+    idx = [af.AnchorIndex(s) for s in seqs]
+    engs = [af.Anchorer(i, 0) for i in idx]
+    host = af.pack_pairs(bundled["seqs1"], bundled["seqs2"], pad_byte=idx[0].pad_byte)
+    singles = [e.anchor_host(host, slot_pairs=4096, n_slots=3)[0].copy() for e in engs]
+    one = engs[0].pipeline_h2d_bytes()
+    for e in engs:
+        e.close_pipeline()
+    multi = anchor_host_multi(engs, host, slot_pairs=4096, n_slots=3)
+    assert engs[0].pipeline_h2d_bytes() == one == af.layout(host.max_read_len, host.n_pairs).packed_bytes
+    for (h, st), want in zip(multi, singles):
+        assert len(want) > 200 and np.array_equal(h.view(np.uint8), want.view(np.uint8))
+
+
+def test_singlecell_20m_pairs_in_2000_cells_batched_across_cells(tmp_path):
+    """configs[4] at size: 2 000 cells x 10 000 pairs of per-cell FASTQ.gz files through the single-cell CLI.  The
+    cells are decoded concurrently and packed back to back into shared 1 M-pair GPU batches; the per-cell
+    files must hold exactly the oracle's records of that cell's pairs, and a cell run alone through the bulk
+    stage must leave byte-identical files."""
+    import time
+    import numpy as np
+    from oracle import oracle
+    from anchored_fusion_b200.bam import read_bam
+    from anchored_fusion_b200.cli import main_singlecell
+    from anchored_fusion_b200.stage import GeneAnchorer, anchor_stage
+    n_cells, ppc = 2000, 10_000
+    spec = oracle.synth_spec(seed=5, ref_len=10_000_000, anchor_start=2_000_000, anchor_len=6783, read_len=150,
+                             frag_mean=300, sub_ppm=10_000, fusion_ppm=2_000)
+    d = str(tmp_path)
+    cells = os.path.join(d, "cells")
+    os.mkdir(cells)
+    f1 = [os.path.join(cells, "cell%05d_1.fastq.gz" % c) for c in range(n_cells)]
+    f2 = [os.path.join(cells, "cell%05d_2.fastq.gz" % c) for c in range(n_cells)]
+    threads = os.cpu_count() or 1
+    for k in range(0, n_cells, 500):
+        oracle.synth_fastq(spec, k * ppc, ppc, f1[k:k + 500], f2[k:k + 500], oracle.FASTQ_GZIP, 1, threads=threads)
+    fa = os.path.join(d, "g.fa")
+    anchor = oracle.synth_anchor(spec).decode()
+    open(fa, "w").write(">NM_1.1 GENEX [organism=synthetic]\n" + anchor + "\n")
+    out = os.path.join(d, "out")
+    t0 = time.time()
+    assert main_singlecell(["--file_anchored_cds", fa, "--fastq_dir", cells, "--out_folder", out, "--thread", "0"]) == 0
+    dt = time.time() - t0
+    # the oracle on all 20 M pairs, cell by cell
+    acodes = oracle.encode(anchor)
+    total = 0
+    for k in range(0, n_cells, 200):
+        reads = oracle.synth_reads(spec, k * ppc, 200 * ppc, threads=threads)
+        want = oracle.anchor_reads(acodes, reads, threads=threads)
+        cell_of = (want["read_id"] >> 1) // ppc
+        for c in range(200):
+            w = want[cell_of == c]
+            _, _, recs = read_bam(os.path.join(out, "GENEX", "work_dir", "cell%05d" % (k + c), "GENEX_fusion_anchored_reads.bam"))
+            got = sorted((r["pos"], 1 if r["flag"] & 0x10 else 0, r["cigar"], 1 if r["flag"] & 0x80 else 0) for r in recs)
+            exp = sorted((int(h["pos"]), int(h["score_strand"]) & 1,
+                          ("%dS" % h["clip_l"] if h["clip_l"] else "") + "%dM" % h["m_len"] + ("%dS" % h["clip_r"] if h["clip_r"] else ""),
+                          int(h["read_id"]) & 1) for h in w)
+            assert got == exp, "cell %d" % (k + c)
+            total += len(recs)
+    assert total > 20_000
+    # three cells alone through the bulk stage: byte-identical files
+    ga = GeneAnchorer(os.path.join(out, "GENEX", "work_dir", "GENEX_fusion_anchored_gene_sequence.fa"), "-1", "GENEX")
+    for c in (0, 777, n_cells - 1):
+        pre = os.path.join(d, "alone%d" % c)
+        anchor_stage(None, f1[c], f2[c], pre, thread="2", gene_anchorer=ga)
+        w = os.path.join(out, "GENEX", "work_dir", "cell%05d" % c, "GENEX_fusion")
+        for s in ("_anchored_reads.bam", "_realign_reads.bam", "_tmp_1.fastq", "_tmp_2.fastq", "_anchored_reads.raw.sam"):
+            assert open(pre + s, "rb").read() == open(w + s, "rb").read(), (c, s)
+    rate = n_cells * ppc / dt
+    print("single-cell 20 M pairs / 2000 cells: %.1f s, %.2f M pairs/s, %d anchored reads" % (dt, rate / 1e6, total))
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "singlecell_20m_test.json") if os.path.isdir(
+            os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")) else os.devnull, "w") as fh:
+        json.dump({"cells": n_cells, "pairs_per_cell": ppc, "seconds": dt, "pairs_per_s": rate, "anchored_reads": total,
+                   "host_threads": threads}, fh)
