@@ -139,6 +139,37 @@ def test_bam_roundtrip(tmp_path):
     assert open(p, "rb").read()[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
+def test_bam_passes_an_independent_spec_check(tmp_path):
+    """The writer's twin (read_bam) proves nothing about validity: bam_spec_check unpacks the BGZF container with
+    Python's gzip module and checks every field against the SAM/BAM specification."""
+    from anchored_fusion_b200.bam import BamWriter
+    from bam_spec_check import check_bam
+    rng = np.random.default_rng(2)
+    p = str(tmp_path / "s.bam")
+    rows = []
+    with BamWriter(p, "GENE", 200_000) as w:
+        for i in range(5000):                                               # > 64 KB of records: several BGZF blocks
+            L = int(rng.integers(30, 151))
+            cl, cr = int(rng.integers(0, 12)), int(rng.integers(0, 12))
+            ops = ([(cl, "S")] if cl else []) + [(L - cl - cr, "M")] + ([(cr, "S")] if cr else [])
+            seq = "".join(rng.choice(list("ACGTN"), size=L))
+            qual = "".join(chr(33 + int(x)) for x in rng.integers(0, 42, L))
+            pos = 1 + 39 * i
+            flag = 0x1 | (0x40 if i & 1 else 0x80) | (0x10 if i % 3 == 0 else 0)
+            w.write("read%d" % i, flag, pos, 60, ops, seq, qual, next_pos=pos)
+            rows.append(("read%d" % i, flag, pos, "".join("%d%s" % o for o in ops), seq, qual))
+            if i % 50 == 0:
+                w.write("mate%d" % i, 0x1 | 0x4 | 0x80, pos, 0, [], "ACGTA", "IIIII", next_pos=pos, mapped=False)
+    res = check_bam(p)
+    assert res["blocks"] >= 4 and res["refs"] == [("GENE", 200_000)]
+    mapped = [r for r in res["records"] if not r["flag"] & 4]
+    assert [(r["qname"], r["flag"], r["pos"], r["cigar"], r["seq"], r["qual"]) for r in mapped] == rows
+    assert sum(1 for r in res["records"] if r["flag"] & 4) == 100
+    empty = str(tmp_path / "e.bam")
+    BamWriter(empty, "GENE", 10).close()
+    assert check_bam(empty)["records"] == []
+
+
 def test_cli_gene_names_and_anchor_split(tmp_path, bundled):
     from anchored_fusion_b200.cli import discover_cells, parse_gene_names, split_anchor_fasta
     fa = tmp_path / "t.fa"

@@ -85,6 +85,12 @@ def test_bulk_cli_on_the_bundled_sample(bundled, tmp_path):
     assert got == next(c for c in golden["contact_reads"] if c["name"] == "bundled_c1")["out"]
     sp = open(w + "_split_points.txt").read().split("\n")
     assert sp[1].split("\t")[:4] == ["BCR", "3235", "MS", "49"]
+    # the two BAMs against the specification, with a reader that shares no code with the writer
+    from bam_spec_check import check_bam
+    chk = check_bam(w + "_anchored_reads.bam")
+    assert chk["refs"] == [("BCR", 6783)] and [(r["qname"], r["pos"], r["cigar"], r["seq"]) for r in chk["records"]] == \
+        [(r["qname"], r["pos"], r["cigar"], r["seq"]) for r in recs]
+    assert len(check_bam(w + "_realign_reads.bam", expect_sorted=False)["records"]) == len(rl)
     # second run: outputs exist -> skipped, like the reference's existence guards
     assert main_bulk(["--file_anchored_cds", fa, "--fastq1", p1, "--fastq2", p2, "--out_folder", out]) == 0
 
@@ -270,7 +276,7 @@ def test_singlecell_20m_pairs_in_2000_cells_batched_across_cells(tmp_path):
         oracle.synth_fastq(spec, k * ppc, ppc, f1[k:k + 500], f2[k:k + 500], oracle.FASTQ_GZIP, 1, threads=threads)
     fa = os.path.join(d, "g.fa")
     anchor = oracle.synth_anchor(spec).decode()
-    open(fa, "w").write(">NM_1.1 GENEX [organism=synthetic]\n" + anchor + "\n")
+    open(fa, "w").write(">NM_1.1 SYNX [organism=synthetic]\n" + anchor + "\n")
     out = os.path.join(d, "out")
     t0 = time.time()
     assert main_singlecell(["--file_anchored_cds", fa, "--fastq_dir", cells, "--out_folder", out, "--thread", "0"]) == 0
@@ -284,7 +290,7 @@ def test_singlecell_20m_pairs_in_2000_cells_batched_across_cells(tmp_path):
         cell_of = (want["read_id"] >> 1) // ppc
         for c in range(200):
             w = want[cell_of == c]
-            _, _, recs = read_bam(os.path.join(out, "GENEX", "work_dir", "cell%05d" % (k + c), "GENEX_fusion_anchored_reads.bam"))
+            _, _, recs = read_bam(os.path.join(out, "SYNX", "work_dir", "cell%05d" % (k + c), "SYNX_fusion_anchored_reads.bam"))
             got = sorted((r["pos"], 1 if r["flag"] & 0x10 else 0, r["cigar"], 1 if r["flag"] & 0x80 else 0) for r in recs)
             exp = sorted((int(h["pos"]), int(h["score_strand"]) & 1,
                           ("%dS" % h["clip_l"] if h["clip_l"] else "") + "%dM" % h["m_len"] + ("%dS" % h["clip_r"] if h["clip_r"] else ""),
@@ -293,11 +299,11 @@ def test_singlecell_20m_pairs_in_2000_cells_batched_across_cells(tmp_path):
             total += len(recs)
     assert total > 20_000
     # three cells alone through the bulk stage: byte-identical files
-    ga = GeneAnchorer(os.path.join(out, "GENEX", "work_dir", "GENEX_fusion_anchored_gene_sequence.fa"), "-1", "GENEX")
+    ga = GeneAnchorer(os.path.join(out, "SYNX", "work_dir", "SYNX_fusion_anchored_gene_sequence.fa"), "-1", "SYNX")
     for c in (0, 777, n_cells - 1):
         pre = os.path.join(d, "alone%d" % c)
         anchor_stage(None, f1[c], f2[c], pre, thread="2", gene_anchorer=ga)
-        w = os.path.join(out, "GENEX", "work_dir", "cell%05d" % c, "GENEX_fusion")
+        w = os.path.join(out, "SYNX", "work_dir", "cell%05d" % c, "SYNX_fusion")
         for s in ("_anchored_reads.bam", "_realign_reads.bam", "_tmp_1.fastq", "_tmp_2.fastq", "_anchored_reads.raw.sam"):
             assert open(pre + s, "rb").read() == open(w + s, "rb").read(), (c, s)
     rate = n_cells * ppc / dt
