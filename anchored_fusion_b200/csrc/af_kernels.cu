@@ -219,7 +219,7 @@ template <int W, int KP, int Q>
 __device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long tile, long long n_pairs, int lane,
                                           int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
                                           uint2 *__restrict__ flags, uint32_t *cc_local, long long chunk0,
-                                          uint32_t *__restrict__ chunk_counts, bool local_ok = true) {
+                                          uint32_t *__restrict__ chunk_counts) {
     uint32_t a1 = af_scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
     uint32_t a2 = af_scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
     const uint32_t vm = tile_valid_mask(tile, n_pairs);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long 
         const uint32_t c = __popc(b1) + __popc(b2);
         if (chunk_counts && c) {
             const long long rel = tile / CB_PER_BLOCK - chunk0;
-            if (local_ok && rel < SCAN_LOCAL_CHUNKS) atomicAdd(&cc_local[rel], c);
+            if (rel < SCAN_LOCAL_CHUNKS) atomicAdd(&cc_local[rel], c);
             else atomicAdd(&chunk_counts[tile / CB_PER_BLOCK], c);
         }
     }
@@ -329,16 +329,13 @@ template <int W, int KP, int MAXT, bool PF, bool RQ>
 __global__ void __launch_bounds__(MAXT, 1)
 k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pairs, int nprobe,
             const uint32_t *__restrict__ g_filter, uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags,
-            uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ counts, long long n_static,
-            uint32_t *__restrict__ pool_counter) {
+            uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ counts) {
     extern __shared__ __align__(128) uint32_t filt[];
     __shared__ uint32_t cc_local[SCAN_LOCAL_CHUNKS];
     __shared__ uint32_t rq[RQ ? (MAXT / 32) * RQ_CAP : 1];
     constexpr int Q = (2 * W + 3) / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    // tiles [0, n_static) are split evenly over the CTAs; the rest (a sixteenth by default) is a pool the warps
-    // drain four tiles at a time once their own range is done, so that no SM waits for the slowest one
-    const long long t_begin = n_static * blockIdx.x / gridDim.x, t_end = n_static * (blockIdx.x + 1) / gridDim.x;
+    const long long t_begin = n_tiles * blockIdx.x / gridDim.x, t_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
     const long long chunk0 = t_begin / CB_PER_BLOCK;
     const long long stride = nwarps;
     long long tile = t_begin + warp;
@@ -349,30 +346,6 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     auto do_tile = [&](const uint32_t (&w)[4 * Q], long long t) {
         if constexpr (RQ) scan_tile_rq<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, packed, (uint32_t *)flags, chunk_counts, q, qn, nflag);
         else scan_tile<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
-    };
-    auto drain_pool = [&]() {
-        if constexpr (!RQ) {
-            constexpr int G = 4;                              // tiles per grab
-            if (n_static >= n_tiles) return;
-            uint32_t wa[4 * Q], wb[4 * Q];
-            for (;;) {
-                unsigned g = 0;
-                if (lane == 0) g = atomicAdd(pool_counter, 1u);
-                g = __shfl_sync(FULL, g, 0);
-                const long long t0 = n_static + (long long)g * G;
-                if (t0 >= n_tiles) break;
-                const int cnt = (int)(n_tiles - t0 < G ? n_tiles - t0 : G);
-                load_tile<Q>(wa, packed, t0, lane);
-                for (int k = 0; k < cnt; k++) {
-                    if (k + 1 < cnt) load_tile<Q>(wb, packed, t0 + k + 1, lane);
-                    scan_tile<W, KP, Q>(wa, t0 + k, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts, false);
-                    if (k + 1 < cnt) {
-#pragma unroll
-                        for (int i = 0; i < 4 * Q; i++) wa[i] = wb[i];
-                    }
-                }
-            }
-        }
     };
     if constexpr (PF) {
         uint32_t wa[4 * Q], wb[4 * Q];
@@ -389,7 +362,6 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
             do_tile(wb, t2);
             tile = t3;
         }
-        drain_pool();
     } else {
         stage_filter(filt, g_filter, nb);
         __syncthreads();
@@ -398,7 +370,6 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
             load_tile<Q>(w, packed, tile, lane);
             do_tile(w, tile);
         }
-        drain_pool();
     }
     if constexpr (RQ) {
         rq_drain<W, KP, Q>(q, qn, lane, 1, packed, nprobe, filt, fmul, nb, (uint32_t *)flags, chunk_counts);
@@ -411,7 +382,7 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     }
 }
 
-static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1, g_scan_pool_shift = 4;
+static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1;
 // tuning knobs.  Scan variant (mode 0/3): register double buffer under an 85-register cap, up to 768
 // threads = 24 warps per SM (a 512-thread / 128-register variant and a 1024-thread variant without
 // prefetch measured the same and were dropped to keep the build short).
@@ -427,9 +398,6 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     // reads happens inside the scan (refine queue, see refine_pass) and the survivors go straight to k_extend;
     // an index whose filter is saturated (long anchor) still takes the k_verify route
     if (mode == 11) { g_middle = 11; return AF_OK; }
-    // modes 20..28: the share of the tiles the scan's warps take from a common pool once their CTA's own range is
-    // done is 2^-(mode - 20) (20: none, all tiles statically assigned; default 24: a sixteenth)
-    if (mode >= 20 && mode <= 28) { g_scan_pool_shift = mode - 20; return AF_OK; }
     // modes 9 / 10: k_verify_smem (9, default: membership from a half-size filter in shared memory) or
     // k_verify (10: membership from the L2-resident bitmap)
     if (mode == 9 || mode == 10) { g_verify_smem = mode == 9; return AF_OK; }
@@ -454,16 +422,8 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
     int nwarps = g_scan_threads / 32;
     long long want = (n_tiles + nwarps - 1) / nwarps;
     int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
-    // the dynamically scheduled tail needs a zeroed counter: the spare word behind the scan's chunk counts
-    long long n_static = n_tiles;
-    uint32_t *pool = nullptr;
-    if (!RQ && chunk_counts && g_scan_pool_shift > 0 && grid == d->num_sms && n_tiles >= 64ll * grid * nwarps) {
-        n_static = n_tiles - (n_tiles >> g_scan_pool_shift);
-        pool = chunk_counts + (n_tiles + CB_PER_BLOCK - 1) / CB_PER_BLOCK;
-    }
     k_seed_scan<W, KP, MAXT, PF, RQ><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
-                                                                         d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts, counts,
-                                                                         n_static, pool);
+                                                                         d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts, counts);
     g_launches++;
     AF_CUDA(cudaGetLastError());
     return AF_OK;
