@@ -78,6 +78,7 @@ SIGNATURES = {
                                      P(c_i64)]),
     "af_fastq_record": (ctypes.c_int, [c_vp, c_i64, P(c_vp), P(c_i32), P(c_vp), P(c_vp), P(c_i32)]),
     "af_workspace_bytes": (ctypes.c_size_t, [c_i64, c_i64]),
+    "af_workspace_bytes_len": (ctypes.c_size_t, [c_i64, c_i64, c_i32]),
     "af_anchor_batch": (ctypes.c_int, [c_vp, P(Batch), c_vp, ctypes.c_size_t, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "af_seed_scan": (ctypes.c_int, [c_vp, P(Batch), c_vp, c_vp]),
     "af_debug_scan_pair": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, P(c_i32), P(c_i32)]),

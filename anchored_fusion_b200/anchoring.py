@@ -168,14 +168,14 @@ class Anchorer:
         self._pipe_key = None
 
     # -- device-resident path -----------------------------------------------------------
-    def _workspace(self, n_pairs, cand_cap, hits_cap, slot=0):
-        key = (n_pairs, cand_cap, hits_cap)
+    def _workspace(self, n_pairs, cand_cap, hits_cap, slot=0, max_read_len=256):
+        key = (n_pairs, cand_cap, hits_cap, max_read_len)
         cur = self._ws.get(slot) if isinstance(self._ws, dict) else None
         if cur is None or cur[0] != key:
             torch = self.torch
             if not isinstance(self._ws, dict):
                 self._ws = {}
-            nbytes = lib().af_workspace_bytes(n_pairs, cand_cap)
+            nbytes = lib().af_workspace_bytes_len(n_pairs, cand_cap, max_read_len)
             # counts (8 x int32 = 2 rows) and the hit records share one tensor, so that the multi-GPU
             # gather can ship (count, first records) as one contiguous slice with no packing kernel
             hc = torch.zeros((2 + max(hits_cap, 1), 4), dtype=torch.int32, device=self.dev)
@@ -203,7 +203,7 @@ class Anchorer:
         n = batch.n_pairs
         cand_cap = int(cand_cap or 2 * max(n, 1))
         hits_cap = int(hits_cap or cand_cap)
-        ws, hits, counts, side = self._workspace(n, cand_cap, hits_cap, slot)
+        ws, hits, counts, side = self._workspace(n, cand_cap, hits_cap, slot, batch.max_read_len)
         st = stream if stream is not None else (side if side is not None else torch.cuda.current_stream(self.dev))
         cb = batch.c_struct()
         if exchange is not None:

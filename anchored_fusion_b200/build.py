@@ -6,13 +6,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libafb200.so")
-SOURCES = ["af_host.cpp", "af_fastq.cpp", "af_kernels.cu", "af_pipeline.cu", "af_exchange.cu"]
+SOURCES = ["af_host.cpp", "af_fastq.cpp", "af_kernels.cu", "af_tail.cu", "af_pipeline.cu", "af_exchange.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-cudart", "static"]
 
 
 OBJDIR = os.path.join(HERE, "build")
-COMMON_DEPS = [os.path.join(CSRC, "af_common.h"), os.path.join(CSRC, "af_inflate.h"), os.path.join(HERE, "..", "include", "anchored_fusion.h"), os.path.abspath(__file__)]
+COMMON_DEPS = [os.path.join(CSRC, "af_common.h"), os.path.join(CSRC, "af_device.cuh"), os.path.join(CSRC, "af_inflate.h"), os.path.join(HERE, "..", "include", "anchored_fusion.h"), os.path.abspath(__file__)]
 
 
 def _newer(target, deps):

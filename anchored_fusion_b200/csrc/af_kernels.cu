@@ -23,8 +23,8 @@
 #include <cstring>
 
 #include "af_common.h"
+#include "af_device.cuh"
 
-#define FULL 0xFFFFFFFFu
 #ifndef AF_SCAN_BOUND
 #define AF_SCAN_BOUND 768   // __launch_bounds__ of the seed scan (register cap 65536 / bound); launched with <= 768 threads
 #endif
@@ -35,7 +35,6 @@ extern "C" int64_t af_kernel_launches(void) { return (int64_t)g_launches.load();
 // ---- optional per-stage timing with CUDA events on the launching stream (bench.py) ---------
 #include <mutex>
 #include <vector>
-enum { ST_SCAN = 0, ST_COMPACT1 = 1, ST_VERIFY = 2, ST_EXTEND = 3, ST_COMPACT2 = 4, ST_N = 5 };
 struct ProfSpan { cudaEvent_t a, b; int stage; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_prof;
@@ -53,6 +52,9 @@ static void prof_span(cudaEvent_t a, cudaStream_t st, int stage) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back({a, b, stage});
 }
+void af_note_launches(int n) { g_launches += n; }
+void af_prof_mark(cudaEvent_t *ev, cudaStream_t st) { prof_mark(ev, st); }
+void af_prof_span(cudaEvent_t a, cudaStream_t st, int stage) { prof_span(a, st, stage); }
 extern "C" void af_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto &p : g_prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -74,124 +76,10 @@ extern "C" int af_profile_end(double *ms_out, int64_t *calls_out) {
     return AF_OK;
 }
 
-#define AF_CUDA(call)                                                                         \
-    do {                                                                                      \
-        cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess) {                                                              \
-            af_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-            return AF_ERR_CUDA;                                                               \
-        }                                                                                     \
-    } while (0)
-
-struct af_dev_index {
-    int device;
-    af_params_t P;
-    int32_t kp, stride, G;
-    uint32_t fmul, nb, tmask;
-    uint32_t *d_filter;  // nb words
-    uint32_t fmul2, nb2;
-    uint32_t *d_filter2; // nb2 words: the half-size filter k_verify stages
-    uint2 *d_table;      // tmask+1 entries {key, value}
-    uint32_t *d_member;  // 4^kp-bit exact membership bitmap (L2 resident)
-    uint8_t *d_anchor;   // G base codes
-    uint32_t *d_apk[2];  // 2-bit packed anchor: forward / reverse complement
-    int anchor_has_n;
-    int pad_byte;
-    int num_sms;
-    bool saturated;      // many filter buckets overflowed (long anchor): flagged reads take the exact k_verify route
-};
-
 // ------------------------------------------------------------------------------------------
 // seed scan
 // ------------------------------------------------------------------------------------------
 static const int CB_THREADS = 256, CB_ITEMS = 8, CB_PER_BLOCK = CB_THREADS * CB_ITEMS;   // compaction chunk
-
-// opt a kernel in to all the shared memory an SM offers a CTA (227 KB) minus what it declares statically;
-// *max_dynamic receives the dynamic part it may then be launched with
-template <class K>
-static int allow_full_smem(K kernel, size_t *max_dynamic) {
-    cudaFuncAttributes a;
-    AF_CUDA(cudaFuncGetAttributes(&a, kernel));
-    const size_t dyn = 227 * 1024 - a.sharedSizeBytes;
-    AF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    if (max_dynamic) *max_dynamic = dyn;
-    return AF_OK;
-}
-
-__device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-// One 16-byte quad of a scattered read (verify).  Without the hint L2 fills a whole 128-byte line per
-// quad (ncu: 129 MB of DRAM reads for 35 MB of sectors asked for); with it 68 MB.
-__device__ __forceinline__ uint4 ld_gather_v4(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-// Stage the anchor filter into shared memory: 128-bit loads, several in flight per thread (a
-// one-word-per-iteration loop spends ~20 us of pure L2 latency here; ncu, round 1).
-// The same with the TMA engine: one thread posts bulk copies global -> shared (cp.async.bulk, SASS
-// UBLKCP) against an mbarrier, every thread waits for the barrier's phase.  No registers, no LSU
-// instructions, and the copy runs while the warps' first tile loads are in flight.  Ends with the
-// filter visible to all threads of the CTA.  Measured: the scan takes the same 0.187 ms per 10 M pairs
-// either way (the ~200 KB per CTA come from L2 in a few microseconds in both forms); kept because it
-// leaves the load/store pipe and 16 registers per thread to the tile loads already in flight.
-// AF_STAGE_TMA=0 builds the load/store loop instead.
-#ifndef AF_STAGE_TMA
-#define AF_STAGE_TMA 1
-#endif
-__device__ __forceinline__ void stage_filter_tma(uint32_t *filt, const uint32_t *__restrict__ g_filter, uint32_t nb) {
-    __shared__ __align__(8) unsigned long long mbar;
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
-    const uint32_t bytes = nb * 4u;                                // nb is a multiple of 32: 128-byte granules
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(filt);
-        const uint32_t CH = 32u << 10;
-        for (uint32_t off = 0; off < bytes; off += CH) {
-            const uint32_t n = bytes - off < CH ? bytes - off : CH;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + off), "l"((const char *)g_filter + off), "r"(n), "r"(bar) : "memory");
-        }
-    }
-    uint32_t done = 0;
-    while (!done)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(0u) : "memory");
-}
-
-__device__ __forceinline__ void stage_filter_ldst(uint32_t *filt, const uint32_t *__restrict__ g_filter, uint32_t nb) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(g_filter);
-    uint4 *dst = reinterpret_cast<uint4 *>(filt);
-    const uint32_t n4 = nb >> 2, step = blockDim.x;              // nb is a multiple of 32
-    uint32_t i = threadIdx.x;
-    for (; i + 3 * step < n4; i += 4 * step) {
-        const uint4 a = src[i], b = src[i + step], c = src[i + 2 * step], d = src[i + 3 * step];
-        dst[i] = a; dst[i + step] = b; dst[i + 2 * step] = c; dst[i + 3 * step] = d;
-    }
-    for (; i < n4; i += step) dst[i] = src[i];
-}
-
-__device__ __forceinline__ void stage_filter(uint32_t *filt, const uint32_t *__restrict__ g_filter, uint32_t nb) {
-#if AF_STAGE_TMA
-    stage_filter_tma(filt, g_filter, nb);
-#else
-    stage_filter_ldst(filt, g_filter, nb);
-#endif
-}
 
 template <int Q>
 __device__ __forceinline__ void load_tile(uint32_t (&w)[4 * Q], const uint4 *__restrict__ packed, long long tile, int lane) {
@@ -317,6 +205,88 @@ __device__ __forceinline__ void scan_tile_rq(const uint32_t (&w)[4 * Q], long lo
     }
 }
 
+// ---- candidate emission (EMIT = true) ---------------------------------------------------------
+// A flagged lane still holds its read in registers: it is stored as one record of the candidate stream
+// (af_emit, af_device.cuh) instead of being re-gathered from HBM later.  The warp owns the chunk it fills
+// (no atomics per record); a chunk is taken from the pool with one atomic per 32 records.
+struct EmitState { uint32_t cur, end, reg, reg_end, nflag; };
+
+__device__ __forceinline__ void emit_pad(EmitState &S, const af_emit &E, int rq, int lane) {
+    const uint32_t n = S.end - S.cur;                       // < 32 unused slots of the open chunk
+    if ((uint32_t)lane < n) E.recs[(size_t)(S.cur + lane) * (rq * 4)] = AF_REC_INVALID;
+    S.cur = S.end;
+}
+
+// One chunk from the pool, listed in region `reg`'s directory (lane 0 only).  AF_REC_INVALID when the pool is empty.
+__device__ __forceinline__ uint32_t emit_grab(uint32_t reg, const af_emit &E) {
+    uint32_t c = atomicAdd(E.pool, 1u);
+    if (c < E.pool_chunks) {
+        const uint32_t k = atomicAdd(&E.dir_count[reg], 1u);
+        if (k < AF_DIR_CAP) E.dir[(size_t)reg * AF_DIR_CAP + k] = c;
+        else c = AF_REC_INVALID;                             // cannot happen (AF_DIR_CAP covers a fully flagged region)
+    }
+    if (c >= E.pool_chunks) { atomicOr(&E.counts[AF_CNT_STATUS], AF_STATUS_CAND_OVERFLOW); c = AF_REC_INVALID; }
+    return c;
+}
+
+// A record = one header quad {read_id, 0, 0, 0} + the Q quads of the read's PAIR exactly as the tile load left
+// them in registers (aligned register quads: no repacking; the tail picks the mate's words by read_id & 1).
+template <int Q>
+__device__ __forceinline__ void emit_store(uint32_t at, uint32_t rid, const uint32_t (&w)[4 * Q], const af_emit &E) {
+    if (at == AF_REC_INVALID) return;
+    uint4 *dst = reinterpret_cast<uint4 *>(E.recs) + (size_t)at * (Q + 1);
+    dst[0] = make_uint4(rid, 0u, 0u, 0u);
+#pragma unroll
+    for (int q = 0; q < Q; q++) dst[1 + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+template <int W, int KP, int Q>
+__device__ __forceinline__ void scan_tile_emit(const uint32_t (&w)[4 * Q], long long tile, long long n_tiles, long long n_pairs,
+                                               int lane, int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
+                                               const af_emit &E, EmitState &S) {
+    uint32_t a1 = af_scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
+    uint32_t a2 = af_scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
+    const uint32_t vm = tile_valid_mask(tile, n_pairs);
+    const uint32_t b1 = __ballot_sync(FULL, a1 != 0) & vm, b2 = __ballot_sync(FULL, a2 != 0) & vm;
+    if (b1 | b2) {                                           // ~70 % of the tiles hold a flagged read (1.2 on average)
+        if (E.m > 1) {                                       // the warp's tiles ascend: step to the region of this tile
+            while ((uint32_t)tile >= S.reg_end) {
+                emit_pad(S, E, Q + 1, lane);
+                S.reg++;
+                S.reg_end = (uint32_t)(n_tiles * (long long)(S.reg + 1) / ((long long)gridDim.x * E.m));
+            }
+        }
+        const int n1 = __popc(b1), n = n1 + __popc(b2), room = (int)(S.end - S.cur);
+        uint32_t nb0 = AF_REC_INVALID, nb1 = AF_REC_INVALID;
+        if (n > room) {                                      // once per 32 records: one or (n > 32 + room) two new chunks
+            uint32_t c0 = AF_REC_INVALID, c1 = AF_REC_INVALID;
+            if (lane == 0) {
+                c0 = emit_grab(S.reg, E);
+                if (n - room > AF_CHUNK) c1 = emit_grab(S.reg, E);
+            }
+            c0 = __shfl_sync(FULL, c0, 0); c1 = __shfl_sync(FULL, c1, 0);
+            if (c0 != AF_REC_INVALID) nb0 = c0 * AF_CHUNK;
+            if (c1 != AF_REC_INVALID) nb1 = c1 * AF_CHUNK;
+        }
+        auto slot = [&](int k) -> uint32_t {
+            if (k < room) return S.cur + (uint32_t)k;
+            k -= room;
+            if (k < AF_CHUNK) return nb0 == AF_REC_INVALID ? AF_REC_INVALID : nb0 + (uint32_t)k;
+            return nb1 == AF_REC_INVALID ? AF_REC_INVALID : nb1 + (uint32_t)(k - AF_CHUNK);
+        };
+        const uint32_t lt = (1u << lane) - 1u, rid = (uint32_t)(tile * 32 + lane) * 2u;
+        if ((b1 >> lane) & 1u) emit_store<Q>(slot(__popc(b1 & lt)), rid, w, E);
+        if ((b2 >> lane) & 1u) emit_store<Q>(slot(n1 + __popc(b2 & lt)), rid + 1u, w, E);
+        if (n > room) {
+            const bool two = n - room > AF_CHUNK;
+            const uint32_t last = two ? nb1 : nb0;
+            if (last != AF_REC_INVALID) { S.cur = last + (uint32_t)(n - room - (two ? AF_CHUNK : 0)); S.end = last + AF_CHUNK; }
+            else S.cur = S.end = 0;                          // pool exhausted (status set): the rest is dropped
+        } else S.cur += (uint32_t)n;
+        S.nflag += (uint32_t)n;
+    }
+}
+
 // Persistent kernel, one CTA per SM: the anchor filter is staged into shared memory once, then
 // the CTA's warps walk its contiguous range of tiles (32 pairs per tile, one pair per lane, all
 // of it in registers).
@@ -325,11 +295,13 @@ __device__ __forceinline__ void scan_tile_rq(const uint32_t (&w)[4 * Q], long lo
 // PF = false (<= 1024 threads, 64 registers): latency is hidden by occupancy alone.
 // RQ = true: flags[] receives the REFINED flag words (see refine_pass), chunk_counts their per-chunk
 // counts and counts[AF_CNT_FLAGGED] the number of reads that passed the plain filter.
-template <int W, int KP, int MAXT, bool PF, bool RQ>
+// EMIT = true: no flag words at all -- every flagged read goes into the candidate stream (emit_reads) that
+// k_tail consumes; counts[AF_CNT_FLAGGED] receives their number.
+template <int W, int KP, int MAXT, bool PF, bool RQ, bool EMIT = false>
 __global__ void __launch_bounds__(MAXT, 1)
 k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pairs, int nprobe,
             const uint32_t *__restrict__ g_filter, uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags,
-            uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ counts) {
+            uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ counts, const af_emit E) {
     extern __shared__ __align__(128) uint32_t filt[];
     __shared__ uint32_t cc_local[SCAN_LOCAL_CHUNKS];
     __shared__ uint32_t rq[RQ ? (MAXT / 32) * RQ_CAP : 1];
@@ -343,8 +315,13 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     uint32_t *q = rq + (RQ ? warp * RQ_CAP : 0);
     int qn = 0;
     uint32_t nflag = 0;
+    EmitState S;
+    S.cur = S.end = 0; S.nflag = 0;
+    S.reg = EMIT ? blockIdx.x * (uint32_t)E.m : 0u;
+    S.reg_end = EMIT ? (uint32_t)(n_tiles * (long long)(S.reg + 1) / ((long long)gridDim.x * E.m)) : 0u;
     auto do_tile = [&](const uint32_t (&w)[4 * Q], long long t) {
-        if constexpr (RQ) scan_tile_rq<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, packed, (uint32_t *)flags, chunk_counts, q, qn, nflag);
+        if constexpr (EMIT) scan_tile_emit<W, KP, Q>(w, t, n_tiles, n_pairs, lane, nprobe, filt, fmul, nb, E, S);
+        else if constexpr (RQ) scan_tile_rq<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, packed, (uint32_t *)flags, chunk_counts, q, qn, nflag);
         else scan_tile<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
     };
     if constexpr (PF) {
@@ -371,7 +348,12 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
             do_tile(w, tile);
         }
     }
-    if constexpr (RQ) {
+    if constexpr (EMIT) {
+        emit_pad(S, E, Q + 1, lane);
+        if (lane == 0 && S.nflag) atomicAdd(&cc_local[0], S.nflag);
+        __syncthreads();
+        if (threadIdx.x == 0 && cc_local[0]) atomicAdd(&counts[AF_CNT_FLAGGED], cc_local[0]);
+    } else if constexpr (RQ) {
         rq_drain<W, KP, Q>(q, qn, lane, 1, packed, nprobe, filt, fmul, nb, (uint32_t *)flags, chunk_counts);
         if (lane == 0 && nflag) atomicAdd(&cc_local[0], nflag);
         __syncthreads();
@@ -382,7 +364,8 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     }
 }
 
-static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1;
+static long long *g_tail_dbg = nullptr;   // af_debug_tail_timing
+static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1, g_stream = 0;
 // tuning knobs.  Scan variant (mode 0/3): register double buffer under an 85-register cap, up to 768
 // threads = 24 warps per SM (a 512-thread / 128-register variant and a 1024-thread variant without
 // prefetch measured the same and were dropped to keep the build short).
@@ -401,7 +384,10 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     // modes 9 / 10: k_verify_smem (9, default: membership from a half-size filter in shared memory) or
     // k_verify (10: membership from the L2-resident bitmap)
     if (mode == 9 || mode == 10) { g_verify_smem = mode == 9; return AF_OK; }
-    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off), 7/8/11 or 9/10"); return AF_ERR_ARG; }
+    // modes 12 / 13: the candidate-stream path (12, default: k_seed_scan<EMIT> + k_tail, 2 kernels) or the
+    // six-kernel path (13: scan -> flag compaction -> verify -> selection -> extend -> hit compaction)
+    if (mode == 12 || mode == 13) { g_stream = mode == 12; return AF_OK; }
+    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off), 7/8/11, 9/10 or 12/13"); return AF_ERR_ARG; }
     const int maxt = 768;
     if (threads_per_block == 0) threads_per_block = maxt;
     if (threads_per_block < 64 || threads_per_block > maxt || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..%d, multiple of 32", maxt); return AF_ERR_ARG; }
@@ -409,21 +395,25 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     return AF_OK;
 }
 
-template <int W, int KP, int MAXT, bool PF, bool RQ>
+static int scan_grid(const af_dev_index *d, long long n_tiles) {
+    const int nwarps = g_scan_threads / 32;
+    const long long want = (n_tiles + nwarps - 1) / nwarps;
+    return (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
+}
+
+template <int W, int KP, int MAXT, bool PF, bool RQ, bool EMIT>
 static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
-                       uint32_t *chunk_counts, uint32_t *counts, cudaStream_t st) {
+                       uint32_t *chunk_counts, uint32_t *counts, const af_emit &E, cudaStream_t st) {
     size_t smem = (size_t)d->nb * 4;
     static bool attr_set[64] = {false};  // per device
     if (!attr_set[d->device & 63]) {
-        int rc = allow_full_smem(k_seed_scan<W, KP, MAXT, PF, RQ>, nullptr);  // the filter + a few static words (chunk counters, mbarrier, refine queues)
+        int rc = allow_full_smem(k_seed_scan<W, KP, MAXT, PF, RQ, EMIT>, nullptr);  // the filter + a few static words (chunk counters, mbarrier, refine queues)
         if (rc) return rc;
         attr_set[d->device & 63] = true;
     }
-    int nwarps = g_scan_threads / 32;
-    long long want = (n_tiles + nwarps - 1) / nwarps;
-    int grid = (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
-    k_seed_scan<W, KP, MAXT, PF, RQ><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
-                                                                         d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts, counts);
+    const int grid = scan_grid(d, n_tiles);
+    k_seed_scan<W, KP, MAXT, PF, RQ, EMIT><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
+                                                                               d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts, counts, E);
     g_launches++;
     AF_CUDA(cudaGetLastError());
     return AF_OK;
@@ -431,15 +421,16 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
 
 template <int W, int KP>
 static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
-                            uint32_t *cc, uint32_t *counts, bool rq, cudaStream_t st) {
-    if (rq) return launch_scan<W, KP, AF_SCAN_BOUND, true, true>(d, b, n_tiles, nprobe, flags, cc, counts, st);
-    return launch_scan<W, KP, AF_SCAN_BOUND, true, false>(d, b, n_tiles, nprobe, flags, cc, counts, st);
+                            uint32_t *cc, uint32_t *counts, bool rq, const af_emit *emit, cudaStream_t st) {
+    if (emit) return launch_scan<W, KP, AF_SCAN_BOUND, true, false, true>(d, b, n_tiles, nprobe, flags, cc, counts, *emit, st);
+    if (rq) return launch_scan<W, KP, AF_SCAN_BOUND, true, true, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st);
+    return launch_scan<W, KP, AF_SCAN_BOUND, true, false, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st);
 }
 
-#define AF_SCAN_CASE(WW)                                                                                 \
-    case WW:                                                                                             \
-        return kp == 12 ? launch_scan_mode<WW, 12>(d, b, n_tiles, nprobe, flags, cc, counts, rq, st)     \
-                        : launch_scan_mode<WW, 13>(d, b, n_tiles, nprobe, flags, cc, counts, rq, st);
+#define AF_SCAN_CASE(WW)                                                                                       \
+    case WW:                                                                                                   \
+        return kp == 12 ? launch_scan_mode<WW, 12>(d, b, n_tiles, nprobe, flags, cc, counts, rq, emit, st)     \
+                        : launch_scan_mode<WW, 13>(d, b, n_tiles, nprobe, flags, cc, counts, rq, emit, st);
 
 static int batch_check(const af_dev_index *d, const af_batch_t *b, af_layout_t *lay) {
     if (!d || !b) { af_set_error("null index or batch"); return AF_ERR_ARG; }
@@ -453,7 +444,7 @@ static int batch_check(const af_dev_index *d, const af_batch_t *b, af_layout_t *
 }
 
 static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *flags, uint32_t *cc, uint32_t *counts, bool rq,
-                          cudaStream_t st) {
+                          const af_emit *emit, cudaStream_t st) {
     af_layout_t lay;
     int rc = batch_check(d, b, &lay);
     if (rc) return rc;
@@ -475,7 +466,7 @@ static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *
 
 extern "C" int af_seed_scan(const af_dev_index_t *d, const af_batch_t *batch, uint32_t *d_flags, void *stream) {
     AF_CUDA(cudaSetDevice(d ? d->device : 0));
-    return seed_scan_impl(d, batch, d_flags, nullptr, nullptr, false, (cudaStream_t)stream);
+    return seed_scan_impl(d, batch, d_flags, nullptr, nullptr, false, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -662,30 +653,6 @@ k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cap, const uint32_t *__r
 // diagonal holds >= k consecutive matches: exactly the SEEDED predicate of the spec, so
 // k_extend only ever sees reads it has to extend.
 // ------------------------------------------------------------------------------------------
-struct ReadRef {
-    const uint32_t *packed;   // tile-interleaved words
-    size_t base;              // word index of word 0 of this read's pair in its quad 0
-    int wofs;                 // mate * W
-    const uint32_t *nm;       // N-mask words of this read or nullptr
-    int L;
-    __device__ __forceinline__ uint32_t word(int t) const {
-        const int wi = wofs + t;
-        return packed[base + (size_t)(wi >> 2) * 128 + (wi & 3)];
-    }
-    __device__ __forceinline__ uint32_t base_at(int i) const { return (word(i >> 4) >> (2 * (i & 15))) & 3u; }
-    __device__ __forceinline__ bool is_n(int i) const { return nm && ((nm[i >> 5] >> (i & 31)) & 1u); }
-};
-
-__device__ __forceinline__ bool diag_match(const ReadRef &r, int s, int i, int d, const uint8_t *__restrict__ anchor, int G) {
-    const int ap = i + d;
-    if (i < 0 || i >= r.L || ap < 0 || ap >= G) return false;
-    const int fi = s ? r.L - 1 - i : i;
-    if (r.is_n(fi)) return false;
-    uint32_t b = r.base_at(fi);
-    if (s) b = 3u - b;
-    return anchor[ap] == b;
-}
-
 template <int KP>
 __global__ void __launch_bounds__(256)
 k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, const uint16_t *__restrict__ lens,
@@ -762,13 +729,6 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
     }
 }
 
-
-// 32 bases (64 bits) of a 2-bit packed sequence starting at base `pos` (pos >= 0)
-__device__ __forceinline__ unsigned long long packed_window(const uint32_t *__restrict__ a, int pos) {
-    const int wi = pos >> 4, sh = 2 * (pos & 15);
-    const uint32_t w0 = a[wi], w1 = a[wi + 1], w2 = a[wi + 2];
-    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
-}
 
 // ------------------------------------------------------------------------------------------
 // verify, shared-memory variant (default).  k_verify above spends its time in L1TEX: ~36 sector
@@ -1147,120 +1107,6 @@ k_scan_verify(const uint4 *__restrict__ packed, long long n_tiles, long long n_p
 // ------------------------------------------------------------------------------------------
 // extend: one warp per seeded read
 // ------------------------------------------------------------------------------------------
-struct ExtParams {
-    int k, A, B, clip5, clip3, T, X;
-};
-
-#define NEG_INF (-(1 << 29))
-
-// number of set mask bits in positions [0, x), x in [0, 256]; lane t holds word t (mw) and the
-// count of set bits in words < t (cp); lanes >= 8 hold mw = 0, cp = total.
-__device__ __forceinline__ int mask_cum(uint32_t mw, uint32_t cp, int x) {
-    int wi = x >> 5;
-    uint32_t wv = __shfl_sync(FULL, mw, wi), cv = __shfl_sync(FULL, cp, wi);
-    return (int)cv + __popc(wv & ((1u << (x & 31)) - 1u));
-}
-
-// One direction of the ungapped X-drop extension over mask positions start, start+dir, ...
-// (n steps).  Lane = step within a 32-step chunk; scores come from popcounts of the match
-// mask, the running maximum from a warp prefix-max scan.  Mirrors `extend` in the oracle.
-__device__ __forceinline__ void extend_dir(uint32_t mw, uint32_t cp, int start, int dir, int n, int qlen, int h0,
-                                           const ExtParams &P, int lane, int &mx_out, int &off_out, int &g_out) {
-    int mx = h0, off = 0, g = -1;
-    const int base_cum = dir > 0 ? mask_cum(mw, cp, start) : mask_cum(mw, cp, start + 1);
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane;
-        const bool valid = j < n;
-        const int jj = valid ? j : 0, pos = start + dir * jj;
-        const int c = mask_cum(mw, cp, dir > 0 ? pos + 1 : pos);
-        const int ones = dir > 0 ? c - base_cum : base_cum - c;
-        int Pj = h0 + P.A * (jj + 1) - (P.A + P.B) * ((jj + 1) - ones);
-        if (!valid) Pj = NEG_INF;
-        const bool dead = valid && Pj <= 0;
-        int pm = Pj;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pm, o); if (lane >= o) pm = max(pm, t); }
-        const int Mj = max(pm, mx);
-        const bool xd = valid && (Mj - Pj > P.X);
-        const uint32_t bd = __ballot_sync(FULL, dead), bx = __ballot_sync(FULL, xd);
-        int endlane = min(32, n - j0);
-        bool stop = false;
-        if (bd) { endlane = min(endlane, __ffs(bd) - 1); stop = true; }
-        if (bx) { endlane = min(endlane, __ffs(bx)); stop = true; }   // the x-drop step itself is processed
-        const bool processed = lane < endlane;
-        int cm = processed ? Pj : NEG_INF;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) cm = max(cm, __shfl_xor_sync(FULL, cm, o));
-        if (cm > mx) {
-            const uint32_t be = __ballot_sync(FULL, processed && Pj == cm);
-            mx = cm;
-            off = j0 + __ffs(be);
-        }
-        if (n == qlen) {
-            const int gl = qlen - 1 - j0;
-            if (gl >= 0 && gl < endlane) g = __shfl_sync(FULL, Pj, gl);
-        }
-        if (stop) break;
-    }
-    mx_out = mx; off_out = off; g_out = g;
-}
-
-// Evaluate diagonal (s, d) of the read held by the warp.  Returns the score or -1 if the
-// diagonal holds no run of k matches.  rw: lane t < W holds packed word t of the read;
-// nw: lane t < 8 holds N-mask word t.
-__device__ __forceinline__ int eval_diag(int s, int d, int L, uint32_t rw, uint32_t nw, bool has_n,
-                                         const uint8_t *__restrict__ anchor, int G, const ExtParams &P, int lane,
-                                         int &qb_out, int &qe_out) {
-    // 256-bit match mask, 32 positions per ballot
-    uint32_t mw = 0;
-    const int nchunks = (L + 31) >> 5;
-    for (int c = 0; c < nchunks; c++) {
-        const int i = c * 32 + lane;
-        const int fi = min(max(s ? L - 1 - i : i, 0), AF_MAX_READ_LEN - 1);   // position in the stored read
-        uint32_t word = __shfl_sync(FULL, rw, fi >> 4);
-        uint32_t base = (word >> (2 * (fi & 15))) & 3u;
-        if (s) base = 3u - base;
-        bool isn = false;
-        if (has_n) { uint32_t nword = __shfl_sync(FULL, nw, fi >> 5); isn = (nword >> (fi & 31)) & 1u; }
-        const int ap = i + d;
-        bool m = false;
-        if (i < L && ap >= 0 && ap < G && !isn) m = anchor[ap] == base;
-        const uint32_t bal = __ballot_sync(FULL, m);
-        if (lane == c) mw = bal;
-    }
-    uint32_t pc = __popc(mw), cp = pc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL, cp, o); if (lane >= o) cp += t; }
-    cp -= pc;  // exclusive: set bits in words before this lane's word
-
-    // leftmost run of k matches
-    const uint32_t kmask = P.k >= 32 ? FULL : ((1u << P.k) - 1u);
-    int qb0 = -1;
-    for (int c = 0; c < nchunks && qb0 < 0; c++) {
-        uint32_t w0 = __shfl_sync(FULL, mw, c), w1 = __shfl_sync(FULL, mw, c + 1);
-        // bits i .. i+31 of the mask, i = c*32 + lane; a run of k <= 32 fits
-        uint32_t win = __funnelshift_r(w0, w1, lane);
-        uint32_t b = __ballot_sync(FULL, (win & kmask) == kmask);
-        if (b) qb0 = c * 32 + __ffs(b) - 1;
-    }
-    if (qb0 < 0 || qb0 + P.k > L) return -1;
-
-    int sc = P.k * P.A, qb = 0, qe = L, mx, off, g;
-    if (qb0 > 0) {
-        const int n = min(qb0, qb0 + d);
-        extend_dir(mw, cp, qb0 - 1, -1, n, qb0, sc, P, lane, mx, off, g);
-        if (g <= 0 || g <= mx - P.clip5) { qb = qb0 - off; sc = mx; } else { qb = 0; sc = g; }
-    }
-    const int qe0 = qb0 + P.k;
-    if (qe0 < L) {
-        const int n = min(L - qe0, G - (qe0 + d));
-        extend_dir(mw, cp, qe0, +1, n, L - qe0, sc, P, lane, mx, off, g);
-        if (g <= 0 || g <= mx - P.clip3) { qe = qe0 + off; sc = mx; } else { qe = L; sc = g; }
-    }
-    qb_out = qb; qe_out = qe;
-    return sc;
-}
-
 __global__ void __launch_bounds__(256)
 k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, const uint16_t *__restrict__ lens,
          const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
@@ -1361,6 +1207,10 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
     }
 }
 
+// debug hook (tools/tail_timing.py): a device buffer of num_sms x 8 int64 that k_tail fills with the phase
+// boundaries (cycles since CTA start) of each CTA's first region, or NULL to switch it off; not part of the ABI header
+extern "C" void af_debug_tail_timing(long long *d_buf) { g_tail_dbg = d_buf; }
+
 template <int W, int KP>
 static int launch_fused(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
                         uint32_t *cc, uint32_t *counts, cudaStream_t st) {
@@ -1408,9 +1258,11 @@ static int fused_impl(const af_dev_index *d, const af_batch_t *b, const af_layou
 // ------------------------------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct WsLayout { size_t flags, cc, cand, keep, cand2, slots, total, cc_bytes; uint32_t nch1, nch2; };
+struct WsLayout { size_t flags, cc, cand, keep, cand2, slots, total, cc_bytes; uint32_t nch1, nch2;
+                  // candidate-stream path (k_seed_scan<EMIT> + k_tail); shares the bytes behind `cc` with the lists of the six-kernel path
+                  size_t ctl, ctl_bytes, dir, chunk_hits, recs; uint32_t r_max, pool_chunks; int rq; };
 
-static WsLayout ws_layout(long long n_pairs, long long cand_cap) {
+static WsLayout ws_layout(long long n_pairs, long long cand_cap, int max_read_len) {
     WsLayout w;
     long long n_tiles = (n_pairs + 31) / 32;
     w.nch1 = (uint32_t)((n_tiles + CB_PER_BLOCK - 1) / CB_PER_BLOCK);
@@ -1420,17 +1272,33 @@ static WsLayout ws_layout(long long n_pairs, long long cand_cap) {
     w.cc = o;                                            // chunk counts of the three compactions, zeroed per call
     w.cc_bytes = align256(((size_t)w.nch1 + 2 * (size_t)w.nch2 + 3) * 4);
     o += w.cc_bytes;
+    const size_t u0 = o;
     w.cand = o; o += align256((size_t)cand_cap * 4);
     w.keep = o; o += align256((size_t)cand_cap);
     w.cand2 = o; o += align256((size_t)cand_cap * 4);
     w.slots = o; o += align256((size_t)cand_cap * 16);
-    w.total = o;
+    const size_t classic_end = o;
+    // candidate stream: R <= n_tiles / AF_REG_TILES + 1 + #SMs regions (R = scan grid x regions per CTA); every
+    // (scan warp, region) pair may leave one chunk partly filled
+    o = u0;
+    w.r_max = (uint32_t)(n_tiles / AF_REG_TILES + 1 + 256);
+    w.pool_chunks = (uint32_t)((cand_cap + AF_CHUNK - 1) / AF_CHUNK + 24ll * w.r_max + 1);
+    w.rq = af_rec_quads((max_read_len + 15) / 16);
+    w.ctl = o; w.ctl_bytes = align256((16 + 2 * (size_t)w.r_max) * 4); o += w.ctl_bytes;   // [0] pool counter, [16..) dir_count[R], region_state[R]: zeroed per call
+    w.dir = o; o += align256((size_t)w.r_max * AF_DIR_CAP * 4);
+    w.chunk_hits = o; o += align256((size_t)w.pool_chunks * 4);
+    w.recs = o; o += align256((size_t)w.pool_chunks * AF_CHUNK * w.rq * 16);
+    w.total = o > classic_end ? o : classic_end;
     return w;
 }
 
+extern "C" size_t af_workspace_bytes_len(int64_t n_pairs, int64_t cand_cap, int32_t max_read_len) {
+    if (n_pairs < 0 || cand_cap < 0 || max_read_len < 1 || max_read_len > AF_MAX_READ_LEN) return 0;
+    return ws_layout(n_pairs, cand_cap, max_read_len).total + 256;
+}
+
 extern "C" size_t af_workspace_bytes(int64_t n_pairs, int64_t cand_cap) {
-    if (n_pairs < 0 || cand_cap < 0) return 0;
-    return ws_layout(n_pairs, cand_cap).total + 256;
+    return af_workspace_bytes_len(n_pairs, cand_cap, AF_MAX_READ_LEN);
 }
 
 static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void *workspace, size_t workspace_bytes,
@@ -1443,17 +1311,50 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
         af_set_error("af_anchor_batch: bad buffers or capacities");
         return AF_ERR_ARG;
     }
-    if (workspace_bytes < af_workspace_bytes(b->n_pairs, cand_cap)) { af_set_error("af_anchor_batch: workspace too small"); return AF_ERR_CAPACITY; }
+    if (workspace_bytes < af_workspace_bytes_len(b->n_pairs, cand_cap, b->max_read_len)) { af_set_error("af_anchor_batch: workspace too small"); return AF_ERR_CAPACITY; }
     AF_CUDA(cudaSetDevice(d->device));
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    WsLayout w = ws_layout(b->n_pairs, cand_cap);
+    WsLayout w = ws_layout(b->n_pairs, cand_cap, b->max_read_len);
     uint32_t *flags = (uint32_t *)(ws + w.flags), *cand = (uint32_t *)(ws + w.cand), *cand2 = (uint32_t *)(ws + w.cand2);
     uint32_t *cc1 = (uint32_t *)(ws + w.cc), *cc2 = cc1 + w.nch1 + 1, *cc3 = cc2 + w.nch2 + 1;
     uint8_t *keep = (uint8_t *)(ws + w.keep);
     uint4 *slots = (uint4 *)(ws + w.slots);
     AF_CUDA(cudaMemsetAsync(d_counts, 0, AF_N_COUNTS * sizeof(uint32_t), st));
     if (lay.n_tiles == 0) return AF_OK;
+    if (g_stream && !g_fused && g_middle == 7 && !d->saturated) {
+        // candidate-stream path: the scan emits the flagged reads, k_tail does the rest -- 2 kernels
+        const int grid = scan_grid(d, lay.n_tiles);
+        const int m = (int)((lay.n_tiles + (long long)grid * AF_REG_TILES - 1) / ((long long)grid * AF_REG_TILES));
+        const uint32_t R = (uint32_t)grid * (uint32_t)m;
+        if (R > w.r_max) { af_set_error("af_anchor_batch: %u regions, workspace laid out for %u", R, w.r_max); return AF_ERR_ARG; }
+        uint32_t *ctl = (uint32_t *)(ws + w.ctl);
+        AF_CUDA(cudaMemsetAsync(ctl, 0, w.ctl_bytes, st));
+        af_emit E;
+        E.recs = (uint32_t *)(ws + w.recs); E.pool = ctl; E.pool_chunks = w.pool_chunks;
+        E.dir_count = ctl + 16; E.dir = (uint32_t *)(ws + w.dir); E.counts = d_counts; E.m = m;
+        cudaEvent_t ev;
+        prof_mark(&ev, st);
+        rc = seed_scan_impl(d, b, nullptr, nullptr, d_counts, false, &E, st);
+        if (rc) return rc;
+        prof_span(ev, st, ST_SCAN);
+        prof_mark(&ev, st);
+        af_tail_args a;
+        a.recs = E.recs; a.rq = w.rq; a.dir_count = E.dir_count; a.dir = E.dir; a.n_regions = R; a.n_tiles = lay.n_tiles;
+        a.chunk_hits = (uint32_t *)(ws + w.chunk_hits); a.region_state = ctl + 16 + w.r_max;
+        a.packed = (const uint32_t *)b->packed; a.W = lay.words_per_read; a.Q = lay.quads_per_pair; a.uniform_len = b->uniform_len;
+        a.lens = b->lens; a.nread_ids = b->nread_ids; a.nmask = b->nmask; a.n_nreads = (int)b->n_nreads;
+        a.g_filter = d->d_filter2; a.fmul = d->fmul2; a.nb = d->nb2; a.table = d->d_table; a.tmask = d->tmask;
+        a.anchor = d->d_anchor; a.apk0p = d->d_apkp[0]; a.apk1p = d->d_apkp[1]; a.apn0p = d->d_apn[0]; a.apn1p = d->d_apn[1]; a.apk_words = d->apk_words; a.anchor_has_n = d->anchor_has_n; a.G = d->G;
+        a.anchor_in_smem = 0;
+        a.P = {d->P.k, d->P.A, d->P.B, d->P.clip5, d->P.clip3, d->P.T, d->P.X};
+        a.hits = (uint4 *)d_hits; a.hits_cap = (uint32_t)hits_cap; a.cand_cap = (uint32_t)cand_cap; a.counts = d_counts;
+        a.dbg = g_tail_dbg;
+        rc = af_tail_launch(d, a, sink, st);
+        if (rc) return rc;
+        prof_span(ev, st, ST_VERIFY);
+        return AF_OK;
+    }
     AF_CUDA(cudaMemsetAsync(cc1, 0, w.cc_bytes, st));
     const int scatter_grid = d->num_sms * 4;
     const int sg2 = (int)(w.nch2 < (uint32_t)scatter_grid ? w.nch2 : scatter_grid);
@@ -1473,7 +1374,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
         g_launches -= 2;                                    // this path has 4 kernels, the code below counts 5 more
     } else {
     const bool rq = g_middle == 11 && !d->saturated;
-    rc = seed_scan_impl(d, b, flags, cc1, d_counts, rq, st);
+    rc = seed_scan_impl(d, b, flags, cc1, d_counts, rq, nullptr, st);
     if (rc) return rc;
     prof_span(ev, st, ST_SCAN);
     prof_mark(&ev, st);
@@ -1589,9 +1490,30 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     cudaError_t e = cudaMalloc(&d->d_filter, idx->filter.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_filter2, idx->filter2.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(d->d_filter2, idx->filter2.data(), idx->filter2.size() * 4, cudaMemcpyHostToDevice);
+    d->d_apkp[0] = d->d_apkp[1] = nullptr;
+    d->d_apn[0] = d->d_apn[1] = nullptr;
+    if (idx->anchor_has_n) {                                // N bitmasks for k_tail's word-parallel match masks
+        const size_t nw = ((size_t)idx->G + 31) / 32 + 8 + 10;
+        std::vector<uint32_t> bits[2];
+        bits[0].assign(nw, 0u); bits[1].assign(nw, 0u);
+        for (int i = 0; i < idx->G; i++)
+            if (idx->codes[(size_t)i] > 3) {
+                const int f = i + 256, r = idx->G - 1 - i + 256;
+                bits[0][(size_t)f >> 5] |= 1u << (f & 31);
+                bits[1][(size_t)r >> 5] |= 1u << (r & 31);
+            }
+        for (int o = 0; o < 2; o++) {
+            if (e == cudaSuccess) e = cudaMalloc(&d->d_apn[o], nw * 4);
+            if (e == cudaSuccess) e = cudaMemcpy(d->d_apn[o], bits[o].data(), nw * 4, cudaMemcpyHostToDevice);
+        }
+    }
+    d->apk_words = (int)idx->apk[0].size() + 16;
     for (int o = 0; o < 2; o++) {
         if (e == cudaSuccess) e = cudaMalloc(&d->d_apk[o], idx->apk[o].size() * 4);
         if (e == cudaSuccess) e = cudaMemcpy(d->d_apk[o], idx->apk[o].data(), idx->apk[o].size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&d->d_apkp[o], (size_t)d->apk_words * 4);
+        if (e == cudaSuccess) e = cudaMemset(d->d_apkp[o], 0, 16 * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(d->d_apkp[o] + 16, idx->apk[o].data(), idx->apk[o].size() * 4, cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess) e = cudaMalloc(&d->d_member, idx->member.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(d->d_member, idx->member.data(), idx->member.size() * 4, cudaMemcpyHostToDevice);
@@ -1602,7 +1524,7 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     if (e == cudaSuccess) e = cudaMemcpy(d->d_anchor, idx->codes.data(), idx->codes.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         af_set_error("af_index_upload: %s", cudaGetErrorString(e));
-        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]); cudaFree(d->d_filter2);
+        cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]); cudaFree(d->d_apkp[0]); cudaFree(d->d_apkp[1]); cudaFree(d->d_apn[0]); cudaFree(d->d_apn[1]); cudaFree(d->d_filter2);
         delete d;
         return AF_ERR_CUDA;
     }
@@ -1615,7 +1537,7 @@ extern "C" int af_dev_index_device(const af_dev_index_t *d) { return d ? d->devi
 extern "C" void af_dev_index_free(af_dev_index_t *d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]); cudaFree(d->d_filter2);
+    cudaFree(d->d_filter); cudaFree(d->d_table); cudaFree(d->d_anchor); cudaFree(d->d_member); cudaFree(d->d_apk[0]); cudaFree(d->d_apk[1]); cudaFree(d->d_apkp[0]); cudaFree(d->d_apkp[1]); cudaFree(d->d_apn[0]); cudaFree(d->d_apn[1]); cudaFree(d->d_filter2);
     delete d;
 }
 

@@ -84,7 +84,7 @@ extern "C" int af_pipeline_create(const af_dev_index_t *d, int64_t slot_pairs, i
     p->cand_cap = 2 * slot_pairs;      // every read may be flagged: nothing is ever dropped
     p->hits_cap = 2 * slot_pairs;
     p->ncap = 2 * slot_pairs;
-    p->ws_bytes = af_workspace_bytes(slot_pairs, p->cand_cap);
+    p->ws_bytes = af_workspace_bytes_len(slot_pairs, p->cand_cap, max_read_len);
     p->slots.resize((size_t)n_slots);
     p->launches0 = af_kernel_launches();
     cudaError_t e = cudaSetDevice(p->device);

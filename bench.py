@@ -577,9 +577,12 @@ def main():
                             "region (same steps, one stream)" % stage_calls[0],
                 "serial_ms_per_step": serial_ms_per_step,
                 "whole_step_frac": alg_bytes(args.read_len) * n / (ms_per_step * 1e-3) / 1e9 / peak,
-                "stage_ms_per_step": {"seed_scan": stage_ms[0] / args.steps, "flag_compaction": stage_ms[1] / args.steps,
-                                      "verify": stage_ms[2] / args.steps, "extend": stage_ms[3] / args.steps,
-                                      "hit_compaction": stage_ms[4] / args.steps}}
+                "stage_ms_per_step": ({"seed_scan": stage_ms[0] / args.steps, "flag_compaction": stage_ms[1] / args.steps,
+                                       "verify": stage_ms[2] / args.steps, "extend": stage_ms[3] / args.steps,
+                                       "hit_compaction": stage_ms[4] / args.steps} if stage_calls[3] else
+                                      {"seed_scan_emit": stage_ms[0] / args.steps,
+                                       "tail_verify_extend_place": stage_ms[2] / args.steps}),
+                "kernels_per_step": 6 if stage_calls[3] else 2}
 
     # end to end through the host-buffer C-ABI call: pinned host batch -> H2D -> kernels -> D2H hits
     e2e = None

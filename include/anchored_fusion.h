@@ -181,7 +181,10 @@ int af_fastq_file_starts(const af_fastq_t *fq, int64_t *first_pair_out, int32_t 
 int64_t af_fastq_batch_first_pair(const af_fastq_t *fq);
 
 /* ---- the hot path on one GPU: replaces `bwa mem -M | samtools view -F 772` -------------- */
+/* bytes af_anchor_batch needs for a batch of n_pairs pairs of reads up to max_read_len bases with room for
+ * cand_cap flagged reads; af_workspace_bytes assumes AF_MAX_READ_LEN (always sufficient) */
 size_t af_workspace_bytes(int64_t n_pairs, int64_t cand_cap);
+size_t af_workspace_bytes_len(int64_t n_pairs, int64_t cand_cap, int32_t max_read_len);
 /* seed scan -> compaction -> verify -> compaction -> extend -> compaction: 6 kernels, all on `stream`,
  * no host sync.  counts[AF_CNT_FLAGGED] reads passed the scan's filter, counts[AF_CNT_SEEDED] were handed
  * to the extension (with the default verify stage: they hold a true >= k-base exact match),

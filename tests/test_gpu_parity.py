@@ -271,7 +271,7 @@ def test_pipeline_equals_resident_path_and_counts_launches(af):
     before = lib().af_kernel_launches()
     hits2, _ = eng.anchor_host(host, slot_pairs=65_536, n_slots=3)
     assert hits_equal(hits, hits2)
-    assert lib().af_kernel_launches() - before == 6 * ((n + 65_535) // 65_536)
+    assert lib().af_kernel_launches() - before in (6 * ((n + 65_535) // 65_536), 2 * ((n + 65_535) // 65_536))   # six-kernel path / candidate-stream path (scan + k_tail)
 
 
 def test_fused_scan_verify_kernel_gives_the_same_records(af, bundled):
