@@ -312,6 +312,150 @@ __device__ __forceinline__ int eval_diag(int s, int d, int L, uint32_t rw, uint3
     return eval_from_mask(mw, d, L, G, P, lane, qb_out, qe_out);
 }
 
+static const int APK_PAD_WORDS = 16;                    // zero words in front of the padded packed anchor (256 bases)
+static const int APN_PAD_WORDS = 8;                     // ... and in front of the anchor's N bitmask (256 bases)
+
+// 32 bases (64 bits) of the padded 2-bit packed anchor starting at base pos >= -256
+__device__ __forceinline__ unsigned long long apk_window(const uint32_t *ap, int pos) {
+    const int p = pos + 16 * APK_PAD_WORDS, wi = p >> 4, sh = 2 * (p & 15);
+    const uint32_t w0 = ap[wi], w1 = ap[wi + 1], w2 = ap[wi + 2];
+    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+// bits 0, 2, 4 .. 30 of x -> bits 0 .. 15
+__device__ __forceinline__ uint32_t even_bits(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+
+// ---- extension, one warp per read, walking MISMATCHES instead of bases -------------------------------
+// k_extend steps through a diagonal 32 bases at a time with warp prefix scans (~120 warp instructions per 32
+// bases); with ~120 reads to extend per SM and region that instruction stream, not latency, was the limit
+// (measured: 11 k cycles per read at 8 warps per scheduler).  Here
+//   * the 256-bit match mask is 8 XORs of 64-bit windows (lane c < 8: read words against the 2-bit packed anchor,
+//     forward or reverse complement) instead of 256 base tests;
+//   * the leftmost run of k matches comes from AND-ing shifted copies of the mask words (eval_from_mask's search);
+//   * the X-drop extension walks the mismatches of the mask: between two mismatches the score only rises, so the
+//     maximum moves only at the end of a match run and every stop condition (score <= 0, max - score > X) can only
+//     fire on a mismatch.  A 150-base read with two substitutions takes three steps of ~12 instructions.
+// A one-thread-per-read version of the same was tried and rejected: ~3 000 dependent instructions per read at
+// ~8 cycles each, 90 k cycles for the phase (tools/tail_timing.py, AF_TAIL_PROF).
+// Same results as oracle/af_oracle.c::extend / diag_eval, step for step (spec v1).
+
+// The 256-bit match mask of diagonal (s, d), word-parallel; lane c < 8 returns mask word c (oriented read
+// positions [32c, 32c+32)), lanes >= 8 return 0.  apn*: the anchor's N bitmasks or nullptr.
+__device__ __forceinline__ uint32_t diag_mask_wp(int s, int d, int L, uint32_t rw, uint32_t nwv, bool has_n,
+                                                const uint32_t *apk0p, const uint32_t *apk1p, const uint32_t *apn0p,
+                                                const uint32_t *apn1p, int G, int lane) {
+    const int c = lane & 7;
+    const int dd = s ? G - L - d : d;                       // forward read base j lies on strand-s anchor base j + dd
+    const uint32_t *ap = s ? apk1p : apk0p, *an = s ? apn1p : apn0p;
+    const uint32_t r0 = __shfl_sync(FULL, rw, 2 * c), r1 = __shfl_sync(FULL, rw, 2 * c + 1);
+    const int lo = max(0, -dd), hi = min(L, G - dd);        // read bases that face an anchor base: [lo, hi)
+    const int b0 = max(lo - 32 * c, 0), b1 = min(hi - 32 * c, 32);
+    uint32_t mf = 0;
+    if (b1 > b0) {                                          // (then 32c + dd lies in (-32, G): inside the padded arrays)
+        const unsigned long long x = ((unsigned long long)r0 | ((unsigned long long)r1 << 32)) ^ apk_window(ap, 32 * c + dd);
+        const unsigned long long ne = x | (x >> 1);         // even bits: 1 = bases differ
+        const uint32_t eq = ~(even_bits((uint32_t)ne) | (even_bits((uint32_t)(ne >> 32)) << 16));
+        mf = eq & ((b1 - b0 >= 32 ? FULL : ((1u << (b1 - b0)) - 1u)) << b0);
+        if (an) {                                           // the packed anchor holds A where the anchor has N
+            const int pn = 32 * c + dd + 32 * APN_PAD_WORDS;
+            mf &= ~__funnelshift_r(an[pn >> 5], an[(pn >> 5) + 1], pn & 31);
+        }
+    }
+    if (has_n) mf &= ~__shfl_sync(FULL, nwv, c);
+    if (!s) return lane < 8 ? mf : 0u;
+    // oriented position i = L - 1 - j: mask(i) = Rev(i + 256 - L) with Rev = the 256-bit mask bit-reversed;
+    // Rev word t = brev(forward word 7 - t), which lane 7 - t holds
+    const uint32_t rev = __brev(mf);
+    const int sh = 256 - L, w0 = c + (sh >> 5);
+    const uint32_t lo_w = __shfl_sync(FULL, rev, (7 - w0) & 7), hi_w = __shfl_sync(FULL, rev, (6 - w0) & 7);
+    const uint32_t m = __funnelshift_r(w0 < 8 ? lo_w : 0u, w0 + 1 < 8 ? hi_w : 0u, sh & 31);
+    return lane < 8 ? m : 0u;
+}
+
+// first position in [pos, limit) whose bit is 0 in the mask spread over lanes 0..7 (lanes >= 8 hold 0), or limit
+__device__ __forceinline__ int dm_next_zero(uint32_t mw, int pos, int limit, int lane) {
+    const int wp = pos >> 5;
+    uint32_t z = ~mw;
+    if (lane < wp) z = 0u; else if (lane == wp) z &= FULL << (pos & 31);
+    const uint32_t who = __ballot_sync(FULL, z != 0);       // never empty: lanes >= 8 hold all-zero words
+    const int c = __ffs(who) - 1;
+    return min(c * 32 + __ffs(__shfl_sync(FULL, z, c)) - 1, limit);
+}
+// last position in (limit, pos] whose bit is 0, or limit (limit >= -1, pos <= 255)
+__device__ __forceinline__ int dm_prev_zero(uint32_t mw, int pos, int limit, int lane) {
+    if (pos <= limit) return limit;
+    const int wp = pos >> 5;
+    uint32_t z = ~mw;
+    if (lane > wp) z = 0u; else if (lane == wp) z &= FULL >> (31 - (pos & 31));
+    const uint32_t who = __ballot_sync(FULL, z != 0);
+    if (!who) return limit;
+    const int c = 31 - __clz(who);
+    return max(c * 32 + 31 - __clz(__shfl_sync(FULL, z, c)), limit);
+}
+
+// One direction of the ungapped X-drop extension over mask positions start, start + dir, ... (n steps), from
+// score h0 (> 0); qlen = read bases left on this side.  oracle/af_oracle.c::extend, mismatch by mismatch;
+// warp-uniform.
+__device__ __forceinline__ void walk_dir(uint32_t mw, int start, int dir, int n, int qlen, int h0, const ExtParams &P,
+                                         int lane, int &mx_out, int &off_out, int &g_out) {
+    int cur = h0, mx = h0, off = 0, g = -1, j = 0;
+    for (;;) {
+        const int jz = dir > 0 ? dm_next_zero(mw, start + j, start + n, lane) - start
+                               : start - dm_prev_zero(mw, start - j, start - n, lane);   // step of the next mismatch, n if none
+        if (jz > j) {                                       // a run of matches: steps j .. jz-1
+            cur += P.A * (jz - j);
+            if (cur > mx) { mx = cur; off = jz; }
+            if (jz == qlen) g = cur;                         // the run ends on the read's last base
+        }
+        if (jz >= n) break;
+        cur -= P.B;                                          // step jz: mismatch
+        if (cur <= 0) break;
+        if (jz + 1 == qlen) g = cur;
+        if (mx - cur > P.X) break;
+        j = jz + 1;
+    }
+    mx_out = mx; off_out = off; g_out = g;
+}
+
+// Score of diagonal d given its match mask (lane c < 8 holds word c, lanes >= 8 hold 0): eval_from_mask with
+// walk_dir in place of extend_dir.  Returns the score or -1 if the mask holds no run of k.
+__device__ __forceinline__ int eval_mask_walk(uint32_t mw, int d, int L, int G, const ExtParams &P, int lane, int &qb_out, int &qe_out) {
+    const uint32_t nx = __shfl_down_sync(FULL, mw, 1);
+    const unsigned long long v = (unsigned long long)mw | ((unsigned long long)(lane < 31 ? nx : 0u) << 32);
+    unsigned long long acc = ~0ull, p = v;
+    for (int kk = P.k, off = 0, len = 1; kk; kk >>= 1, len <<= 1) {
+        if (kk & 1) { acc &= p >> off; off += len; }
+        p &= p >> len;
+    }
+    const uint32_t starts = (uint32_t)acc;
+    const uint32_t who = __ballot_sync(FULL, starts != 0);
+    if (!who) return -1;
+    const int c0 = __ffs(who) - 1;
+    const int qb0 = c0 * 32 + __ffs(__shfl_sync(FULL, starts, c0)) - 1;
+    if (qb0 + P.k > L) return -1;
+    int sc = P.k * P.A, qb = 0, qe = L, mx, off, g;
+    if (qb0 > 0) {
+        const int n = min(qb0, qb0 + d);
+        walk_dir(mw, qb0 - 1, -1, n, qb0, sc, P, lane, mx, off, g);
+        if (g <= 0 || g <= mx - P.clip5) { qb = qb0 - off; sc = mx; } else { qb = 0; sc = g; }
+    }
+    const int qe0 = qb0 + P.k;
+    if (qe0 < L) {
+        const int n = min(L - qe0, G - (qe0 + d));
+        walk_dir(mw, qe0, +1, n, L - qe0, sc, P, lane, mx, off, g);
+        if (g <= 0 || g <= mx - P.clip3) { qe = qe0 + off; sc = mx; } else { qe = L; sc = g; }
+    }
+    qb_out = qb; qe_out = qe;
+    return sc;
+}
+
 // ---- k_tail (af_tail.cu): verify + extend + ordered placement of the candidate stream, one kernel ----
 struct af_tail_args {
     // candidate stream

@@ -20,6 +20,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "af_common.h"
@@ -365,7 +366,10 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
 }
 
 static long long *g_tail_dbg = nullptr;   // af_debug_tail_timing
-static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1, g_stream = 0;
+static int env_flag(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }
+static int g_scan_threads = 768, g_fused = 0, g_middle = 7, g_verify_smem = 1;
+static int g_walk = 1;                             // k_extend evaluates diagonals with eval_mask_walk (1) or eval_diag (0); af_seed_scan_config(0, 14 / 15)
+static int g_stream = env_flag("AF_STREAM", 0);   // 1: candidate-stream path (k_seed_scan<EMIT> + k_tail); also af_seed_scan_config(0, 12 / 13)
 // tuning knobs.  Scan variant (mode 0/3): register double buffer under an 85-register cap, up to 768
 // threads = 24 warps per SM (a 512-thread / 128-register variant and a 1024-thread variant without
 // prefetch measured the same and were dropped to keep the build short).
@@ -387,7 +391,9 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     // modes 12 / 13: the candidate-stream path (12, default: k_seed_scan<EMIT> + k_tail, 2 kernels) or the
     // six-kernel path (13: scan -> flag compaction -> verify -> selection -> extend -> hit compaction)
     if (mode == 12 || mode == 13) { g_stream = mode == 12; return AF_OK; }
-    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off), 7/8/11, 9/10 or 12/13"); return AF_ERR_ARG; }
+    // modes 14 / 15: k_extend's diagonal evaluation -- 14 (default) word-parallel mask + mismatch walk, 15 the round-1 code
+    if (mode == 14 || mode == 15) { g_walk = mode == 14; return AF_OK; }
+    if (mode != 0 && mode != 3) { af_set_error("af_seed_scan_config: mode must be 0/3 (scan variant), 4/5 (fused on/off), 7/8/11, 9/10, 12/13 or 14/15"); return AF_ERR_ARG; }
     const int maxt = 768;
     if (threads_per_block == 0) threads_per_block = maxt;
     if (threads_per_block < 64 || threads_per_block > maxt || threads_per_block % 32) { af_set_error("af_seed_scan_config: threads must be 64..%d, multiple of 32", maxt); return AF_ERR_ARG; }
@@ -1112,7 +1118,9 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
          const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
          const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts, uint32_t cand_cap,
          const uint2 *__restrict__ table, uint32_t tmask, const uint8_t *__restrict__ anchor, int G, int KP, int S,
-         ExtParams P, uint4 *__restrict__ slots, uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ next_read) {
+         ExtParams P, uint4 *__restrict__ slots, uint32_t *__restrict__ chunk_counts, uint32_t *__restrict__ next_read,
+         const uint32_t *__restrict__ apk0p, const uint32_t *__restrict__ apk1p, const uint32_t *__restrict__ apn0p,
+         const uint32_t *__restrict__ apn1p, int walk) {
     const int lane = threadIdx.x & 31;
     const uint32_t ncand = min(counts[AF_CNT_SEEDED], cand_cap);
     const uint32_t kpmask = (1u << (2 * KP)) - 1u;
@@ -1187,7 +1195,10 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
                     const uint32_t dk = __shfl_sync(FULL, dkey, src);
                     const int s = dk >> 31, d = (int)(dk & 0x7FFFFFFFu) - 1024;
                     int qb, qe;
-                    const int sc = eval_diag(s, d, L, rw, nwv, has_n, anchor, G, P, lane, qb, qe);
+                    // walk != 0 (default): word-parallel match mask + an extension that steps from mismatch to mismatch
+                    // (eval_mask_walk); 0: base-by-base mask and 32-step warp scans (eval_diag), kept for A/B runs
+                    const int sc = walk ? eval_mask_walk(diag_mask_wp(s, d, L, rw, nwv, has_n, apk0p, apk1p, apn0p, apn1p, G, lane), d, L, G, P, lane, qb, qe)
+                                        : eval_diag(s, d, L, rw, nwv, has_n, anchor, G, P, lane, qb, qe);
                     if (sc > best_sc || (sc == best_sc && sc >= 0 && dk < best_key)) { best_sc = sc; best_qb = qb; best_qe = qe; best_key = dk; }
                 }
                 if (found) next_match();
@@ -1435,7 +1446,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     k_extend<<<ext_blocks, 256, 0, st>>>((const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair,
                                          b->uniform_len, b->lens, b->nread_ids, b->nmask, (int)b->n_nreads, cand2,
                                          d_counts, (uint32_t)cand_cap, d->d_table, d->tmask, d->d_anchor, d->G, d->kp,
-                                         d->stride, P, slots, cc3, d_counts + AF_CNT_SCRATCH);
+                                         d->stride, P, slots, cc3, d_counts + AF_CNT_SCRATCH, d->d_apkp[0], d->d_apkp[1], d->d_apn[0], d->d_apn[1], g_walk);
     prof_span(ev, st, ST_EXTEND);
     prof_mark(&ev, st);
     if (sink) k_hit_scatter<true><<<sg2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, cc3, (uint4 *)d_hits, (uint32_t)hits_cap, d_counts, *sink);

@@ -38,261 +38,69 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 __device__ __forceinline__ void st_relaxed_gpu(uint32_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-#ifndef AF_TAIL_EXP
-#define AF_TAIL_EXP 0
-#endif
-#ifndef AF_TAIL_PROF
-#define AF_TAIL_PROF 0                                  // 1: thread_extend counts cycles per part into g_prof_* (tools/tail_timing.py)
-#endif
-#if AF_TAIL_PROF
-#define PROF_T0 const long long prof_t0_ = clock64();
-#define PROF_ADD(x) x += clock64() - prof_t0_;
-#else
-#define PROF_T0
-#define PROF_ADD(x)
-#endif
-struct ExtProf { long long collect, eval, n_eval, n_load, mask, run, ext, n_iter, t_start, t_consume; };
-
-static const int APK_PAD_WORDS = 16;                    // zero words in front of the padded packed anchor (256 bases)
-static const int APN_PAD_WORDS = 8;                     // ... and in front of the anchor's N bitmask (256 bases)
-
-// 32 bases (64 bits) of the padded 2-bit packed anchor starting at base pos >= -256
-__device__ __forceinline__ unsigned long long apk_window(const uint32_t *ap, int pos) {
-    const int p = pos + 16 * APK_PAD_WORDS, wi = p >> 4, sh = 2 * (p & 15);
-    const uint32_t w0 = ap[wi], w1 = ap[wi + 1], w2 = ap[wi + 2];
-    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
-}
-
-// bits 0, 2, 4 .. 30 of x -> bits 0 .. 15
-__device__ __forceinline__ uint32_t even_bits(uint32_t x) {
-    x &= 0x55555555u;
-    x = (x | (x >> 1)) & 0x33333333u;
-    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
-    x = (x | (x >> 4)) & 0x00FF00FFu;
-    x = (x | (x >> 8)) & 0x0000FFFFu;
-    return x;
-}
-
-// ---- extension, one THREAD per read ------------------------------------------------------------
-// k_extend gives a read a whole warp; most of its instructions do the same thing in 32 lanes, and with ~120
-// reads to extend per SM and region the warp-level instruction stream -- not latency -- was the limit
-// (measured: 11 k cycles per read, 42 k cycles for the phase).  Here a lane owns a read:
-//   * the 256-bit match mask of a diagonal is 8 XORs of 64-bit windows (read words from shared memory against
-//     the 2-bit packed anchor, forward or reverse complement) instead of 256 base tests;
-//   * the leftmost run of k matches comes from AND-ing shifted copies of the mask words;
-//   * the X-drop extension walks the MISMATCHES of the mask, not the bases: between two mismatches the score
-//     only rises, so the maximum moves only at the end of a match run and every stop condition (score <= 0,
-//     max - score > X) can only fire on a mismatch.  A 150-base read with two substitutions takes three steps.
-// Same results as oracle/af_oracle.c::extend / diag_eval, step for step (spec v1).
-
-// first position j in [pos, limit) whose mask bit is 0, or limit
-__device__ __forceinline__ int mask_next_zero(const uint32_t *m, int pos, int limit) {
-    while (pos < limit) {
-        const int wi = pos >> 5;
-        const uint32_t z = ~m[wi] & (FULL << (pos & 31));
-        if (z) return min(wi * 32 + __ffs(z) - 1, limit);
-        pos = (wi + 1) * 32;
-    }
-    return limit;
-}
-// last position j in (limit, pos] whose mask bit is 0, or limit (limit >= -1)
-__device__ __forceinline__ int mask_prev_zero(const uint32_t *m, int pos, int limit) {
-    while (pos > limit) {
-        const int wi = pos >> 5;
-        const uint32_t z = ~m[wi] & (FULL >> (31 - (pos & 31)));
-        if (z) return max(wi * 32 + 31 - __clz(z), limit);
-        pos = wi * 32 - 1;
-    }
-    return limit;
-}
-
-// One direction of the ungapped X-drop extension over mask positions start, start + dir, ... (n steps), from
-// score h0 (> 0); qlen = read bases left on this side.  oracle/af_oracle.c::extend, mismatch by mismatch.
-__device__ __forceinline__ void thread_extend_dir(const uint32_t *m, int start, int dir, int n, int qlen, int h0,
-                                                  const ExtParams &P, int &mx_out, int &off_out, int &g_out) {
-    int cur = h0, mx = h0, off = 0, g = -1, j = 0;
-    for (;;) {
-        const int jz = dir > 0 ? mask_next_zero(m, start + j, start + n) - start
-                               : start - mask_prev_zero(m, start - j, start - n);   // step of the next mismatch, n if none
-        if (jz > j) {                                       // a run of matches: steps j .. jz-1
-            cur += P.A * (jz - j);
-            if (cur > mx) { mx = cur; off = jz; }
-            if (jz == qlen) g = cur;                         // the run ends on the read's last base
-        }
-        if (jz >= n) break;
-        cur -= P.B;                                          // step jz: mismatch
-        if (cur <= 0) break;
-        if (jz + 1 == qlen) g = cur;
-        if (mx - cur > P.X) break;
-        j = jz + 1;
-    }
-    mx_out = mx; off_out = off; g_out = g;
-}
-
-// Evaluate diagonal (s, d) of the read whose words sit in shared memory at sw[t * VT].  Returns the score or -1 if
-// the diagonal holds no run of k matches.  nm: the read's N-mask words (forward coordinates) or nullptr.
-__device__ __forceinline__ int thread_eval_diag(int s, int d, int L, const uint32_t *sw, int VT, const uint32_t *nm,
-                                                const uint32_t *apk0p, const uint32_t *apk1p, const uint32_t *apn0p,
-                                                const uint32_t *apn1p, int G, const ExtParams &P, int &qb_out, int &qe_out, ExtProf &pf) {
-    const int nw = (L + 31) >> 5;
-    long long tp0 = AF_TAIL_PROF ? clock64() : 0;
-    const int dd = s ? G - L - d : d;                       // forward read base j lies on strand-s anchor base j + dd
-    const uint32_t *ap = s ? apk1p : apk0p, *an = s ? apn1p : apn0p;   // an: 1 bit per anchor base that is N, or nullptr
-    const int lo = max(0, -dd), hi = min(L, G - dd);        // read bases that face an anchor base: [lo, hi)
-    uint32_t mf[9], mo[9];
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        uint32_t w = 0;
-        const int b0 = max(lo - 32 * c, 0), b1 = min(hi - 32 * c, 32);
-        if (c < nw && b1 > b0) {                            // (then 32c + dd lies in (-32, G): inside the padded array)
-            const unsigned long long x = ((unsigned long long)sw[2 * c * VT] | ((unsigned long long)sw[(2 * c + 1) * VT] << 32)) ^
-                                         apk_window(ap, 32 * c + dd);
-            const unsigned long long ne = x | (x >> 1);     // even bits: 1 = bases differ
-            const uint32_t eq = ~(even_bits((uint32_t)ne) | (even_bits((uint32_t)(ne >> 32)) << 16));
-            w = eq & ((b1 - b0 >= 32 ? FULL : ((1u << (b1 - b0)) - 1u)) << b0);
-            if (nm) w &= ~nm[c];
-            if (an) {                                       // the packed anchor holds A where the anchor has N
-                const int pn = 32 * c + dd + 32 * APN_PAD_WORDS;
-                w &= ~__funnelshift_r(an[pn >> 5], an[(pn >> 5) + 1], pn & 31);
-            }
-        }
-        mf[c] = w;
-    }
-    mf[8] = 0;
-    const uint32_t *m = mf;
-    if (s) {
-        // oriented position i = L - 1 - j: mask(i) = Rev(i + 256 - L), Rev = the 256-bit mask bit-reversed
-        // (Rev word t = brev(forward word 7 - t))
-        const int sh = 256 - L, ws = sh >> 5, bs = sh & 31;
-        for (int c = 0; c < 8; c++) {
-            const int w0 = c + ws;
-            const uint32_t a0 = w0 < 8 ? __brev(mf[7 - w0]) : 0u, a1 = w0 + 1 < 8 ? __brev(mf[6 - w0]) : 0u;
-            mo[c] = __funnelshift_r(a0, a1, bs);
-        }
-        mo[8] = 0;
-        m = mo;
-    }
-    if (AF_TAIL_PROF) { const long long t = clock64(); pf.mask += t - tp0; tp0 = t; }
-    // leftmost run of k <= 32 matches: starts b < 32 of word c with bits b .. b+k-1 set in (word c, word c+1)
-    int qb0 = -1;
-    for (int c = 0; c < nw && qb0 < 0; c++) {
-        const unsigned long long v = (unsigned long long)m[c] | ((unsigned long long)m[c + 1] << 32);
-        unsigned long long acc = ~0ull, p = v;
-        for (int kk = P.k, off = 0, len = 1; kk; kk >>= 1, len <<= 1) {
-            if (kk & 1) { acc &= p >> off; off += len; }
-            p &= p >> len;
-        }
-        const uint32_t starts = (uint32_t)acc;
-        if (starts) qb0 = c * 32 + __ffs(starts) - 1;
-    }
-    if (AF_TAIL_PROF) { const long long t = clock64(); pf.run += t - tp0; tp0 = t; }
-    if (qb0 < 0 || qb0 + P.k > L) return -1;
-    int sc = P.k * P.A, qb = 0, qe = L, mx, off, g;
-    if (qb0 > 0) {
-        const int n = min(qb0, qb0 + d);
-        thread_extend_dir(m, qb0 - 1, -1, n, qb0, sc, P, mx, off, g);
-        if (g <= 0 || g <= mx - P.clip5) { qb = qb0 - off; sc = mx; } else { qb = 0; sc = g; }
-    }
-    const int qe0 = qb0 + P.k;
-    if (qe0 < L) {
-        const int n = min(L - qe0, G - (qe0 + d));
-        thread_extend_dir(m, qe0, +1, n, L - qe0, sc, P, mx, off, g);
-        if (g <= 0 || g <= mx - P.clip3) { qe = qe0 + off; sc = mx; } else { qe = L; sc = g; }
-    }
-    if (AF_TAIL_PROF) pf.ext += clock64() - tp0;
-    qb_out = qb; qe_out = qe;
-    return sc;
-}
-
-// All of k_extend for one read, by one thread: exact table lookups for every sample, each distinct diagonal
-// evaluated, best = score desc, strand 0 first, smaller d.  Returns true and the record if it scores >= T.
-// The lanes of a warp work on different reads, so the code is arranged for convergence: diagonals are first
-// COLLECTED (table walks, cheap, divergent) into a short list and then evaluated in one loop with a single call
-// site, so that all lanes run thread_eval_diag together (inlining it into the table walk made every lane run it
-// alone: 100 k cycles per read instead of 10 k, measured).
-__device__ __forceinline__ bool thread_extend(bool active, uint32_t rid, int L, const uint32_t *sw, int VT, const uint32_t *nm,
-                                              const uint2 *__restrict__ table, uint32_t tmask, const uint32_t *apk0p,
-                                              const uint32_t *apk1p, const uint32_t *apn0p, const uint32_t *apn1p, int G,
-                                              int KP, int S, const ExtParams &P, uint4 &out, ExtProf &pf) {
-    // Called by ALL 32 lanes of a warp (`active` = this lane has a read).  Every loop below runs a warp-uniform
-    // number of times (__any_sync), lanes that are done are predicated off: left to itself the compiler let the
-    // lanes drift apart in the table-walk state machine and each lane ended up running it alone (75 k cycles per
-    // read, measured with AF_TAIL_PROF).
+// The whole warp extends one candidate (k_extend's lookup + de-duplication, the evaluation above).  rw: lane
+// t < W holds packed word t; nwv: lane t < 8 holds N-mask word t.  Returns true (warp-uniform) and the record if
+// the best diagonal scores >= T.
+__device__ __forceinline__ bool tail_extend(uint32_t rid, int L, uint32_t rw, uint32_t nwv, bool has_n,
+                                            const uint2 *__restrict__ table, uint32_t tmask, const uint32_t *apk0p,
+                                            const uint32_t *apk1p, const uint32_t *apn0p, const uint32_t *apn1p, int G,
+                                            int KP, int S, const ExtParams &P, int lane, uint4 &out) {
     const uint32_t kpmask = (1u << (2 * KP)) - 1u;
-    constexpr int CAP = 8;
     int best_sc = -1, best_qb = 0, best_qe = 0;
-    uint32_t best_key = 0xFFFFFFFFu, seen0 = 0xFFFFFFFFu, seen1 = 0xFFFFFFFFu;   // the last two diagonals evaluated
-    uint32_t dl[CAP];
-    int nd = 0, j = 0, p = 0;
-    const int nprobe = active && L >= KP ? (L - KP) / S + 1 : 0;
-    uint32_t key = 0, sl = 0;
-    uint2 e0 = make_uint2(AF_T_EMPTY, 0), e1 = e0;
-    bool walking = false;
-    for (;;) {
-        long long tp0 = AF_TAIL_PROF ? clock64() : 0;
-        for (;;) {                                           // collect: walk the table for sample after sample
-            const bool want = nd < CAP && (walking || j < nprobe);
-            if (!__any_sync(FULL, want)) break;
-            if (AF_TAIL_PROF) pf.n_iter++;
-            const long long ti0 = AF_TAIL_PROF ? clock64() : 0;
-            const bool was_walking = walking;
-            if (want) {
-                if (!walking) {
-                    p = j * S;
-                    bool skip = false;
-                    if (nm) {                                // a k'-mer that overlaps an N is no seed material
-                        const uint32_t nn = __funnelshift_r(nm[p >> 5], (p >> 5) + 1 < AF_NMASK_WORDS ? nm[(p >> 5) + 1] : 0u, p & 31);
-                        skip = (nn & ((1u << KP) - 1u)) != 0;
-                    }
-                    if (skip) j++;
-                    else {
-                        const int o = 2 * p;
-                        key = __funnelshift_r(sw[(o >> 5) * VT], sw[((o >> 5) + 1) * VT], o & 31) & kpmask;
-                        sl = af_table_hash(key, tmask);
-                        e0 = table[sl]; e1 = table[(sl + 1) & tmask];   // the usual walk is {match, empty}: both loads in flight
-                        walking = true;
-                        if (AF_TAIL_PROF) pf.n_load += 2;
-                    }
-                } else {
-                    const uint2 e = e0;
-                    if (e.x == AF_T_EMPTY) { walking = false; j++; }
-                    else {
-                        sl = (sl + 1) & tmask;
-                        e0 = e1;
-                        if (e0.x != AF_T_EMPTY) e1 = table[(sl + 1) & tmask];
-                        if (e.x == key) {
-                            const int s = e.y >> 31, jpos = (int)(e.y & 0x7FFFFFFFu);
-                            const int d = jpos - (s ? L - p - KP : p);
-                            const uint32_t dk = ((uint32_t)s << 31) | (uint32_t)(d + 1024);
-                            bool known = dk == seen0 || dk == seen1;
-                            for (int t = 0; t < nd; t++) known |= dl[t] == dk;
-                            if (!known) dl[nd++] = dk;
-                        }
-                    }
-                }
-            }
-            if (AF_TAIL_PROF) { if (was_walking) pf.t_consume += clock64() - ti0; else pf.t_start += clock64() - ti0; }
+    uint32_t best_key = 0xFFFFFFFFu;
+    const int nprobe = L >= KP ? (L - KP) / S + 1 : 0;
+    for (int p0 = 0; p0 < nprobe; p0 += 32) {
+        const int pi = p0 + lane, p = pi * S;
+        bool active = pi < nprobe;
+        const int o = 2 * (active ? p : 0), wi = o >> 5;
+        uint32_t w0 = __shfl_sync(FULL, rw, wi), w1 = __shfl_sync(FULL, rw, min(wi + 1, 31));
+        const uint32_t key = __funnelshift_r(w0, w1, o & 31) & kpmask;
+        if (has_n) {
+            const int q = active ? p : 0;
+            uint32_t n0 = __shfl_sync(FULL, nwv, q >> 5), n1 = __shfl_sync(FULL, nwv, min((q >> 5) + 1, 31));
+            if (__funnelshift_r(n0, n1, q & 31) & ((1u << KP) - 1u)) active = false;  // k'-mer overlaps an N
         }
-        if (AF_TAIL_PROF) { const long long t = clock64(); pf.collect += t - tp0; tp0 = t; }
-        if (!__any_sync(FULL, nd > 0)) break;
-        for (int t = 0; __any_sync(FULL, t < nd); t++) {     // evaluate: one call site, all lanes together
-            if (t < nd) {
-                const uint32_t dk = dl[t];
+        uint32_t slot = af_table_hash(key, tmask), val = 0;
+        bool found = false;
+        auto next_match = [&]() {                            // advance to this lane's next table entry with the same key
+            found = false;
+            while (active) {
+                uint2 e = table[slot];
+                slot = (slot + 1) & tmask;
+                if (e.x == AF_T_EMPTY) { active = false; break; }
+                if (e.x == key) { found = true; val = e.y; break; }
+            }
+        };
+        next_match();
+        uint32_t fm;
+        while ((fm = __ballot_sync(FULL, found)) != 0) {
+            uint32_t dkey = 0;
+            bool leader = false;
+            if (found) {
+                const int s = val >> 31, j = (int)(val & 0x7FFFFFFFu);
+                const int d = j - (s ? L - p - KP : p);
+                dkey = ((uint32_t)s << 31) | (uint32_t)(d + 1024);
+                uint32_t grp = __match_any_sync(fm, dkey);
+                leader = (__ffs(grp) - 1) == lane;
+            }
+            uint32_t leaders = __ballot_sync(FULL, leader);
+            while (leaders) {
+                const int src = __ffs(leaders) - 1;
+                leaders &= leaders - 1;
+                const uint32_t dk = __shfl_sync(FULL, dkey, src);
                 const int s = dk >> 31, d = (int)(dk & 0x7FFFFFFFu) - 1024;
                 int qb, qe;
-                const int sc = thread_eval_diag(s, d, L, sw, VT, nm, apk0p, apk1p, apn0p, apn1p, G, P, qb, qe, pf);
-                if (AF_TAIL_PROF) pf.n_eval++;
+                const int sc = eval_mask_walk(diag_mask_wp(s, d, L, rw, nwv, has_n, apk0p, apk1p, apn0p, apn1p, G, lane), d, L, G, P, lane, qb, qe);
                 if (sc > best_sc || (sc == best_sc && sc >= 0 && dk < best_key)) { best_sc = sc; best_qb = qb; best_qe = qe; best_key = dk; }
-                seen1 = seen0; seen0 = dk;
             }
-            __syncwarp();
+            if (found) next_match();
         }
-        if (AF_TAIL_PROF) pf.eval += clock64() - tp0;
-        nd = 0;
     }
     if (best_sc < P.T) return false;
     const int s = best_key >> 31, d = (int)(best_key & 0x7FFFFFFFu) - 1024;
@@ -379,7 +187,7 @@ template <int KP>
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
 k_tail(const af_tail_args a, const af_sink sink, const int has_sink) {
     extern __shared__ __align__(128) uint32_t tsm[];
-    __shared__ uint32_t s_next, s_base, s_seeded, s_qn, s_tmp[33];
+    __shared__ uint32_t s_next, s_done, s_base, s_seeded, s_qn, s_qhead, s_tmp[33];
     constexpr int VT = TAIL_THREADS;
     uint32_t *filt = tsm;                                  // nb words: half-size anchor filter
     uint32_t *swb = filt + a.nb;                           // (W + 3) x VT: word t of thread i's candidate at swb[t * VT + i]
@@ -431,77 +239,82 @@ k_tail(const af_tail_args a, const af_sink sink, const int has_sink) {
         const uint32_t rid0 = (uint32_t)(t0 * 64);
         const int nwords = (int)(t1 - t0) * 2;
         for (int i = tid; i < min(nwords + 4, REG_WORDS); i += VT) bitmap[i] = 0;
-        if (tid == 0) { s_next = 0; s_qn = 0; }
         const uint32_t ndir = min(a.dir_count[r], AF_DIR_CAP);
         const uint32_t *dir = a.dir + (size_t)r * AF_DIR_CAP;
         __syncthreads();
         // ---- phase 1, in rounds of at most qcap / 32 chunks so that the queue always has room ---------
+        // One work loop per round: a warp extends a queued candidate if there is one, else pre-filters the next
+        // chunk (a lane = a candidate; survivors are queued), else waits for the last chunks to be finished by
+        // their warps.  No barrier between filtering and extending, and the extension -- the part whose cost
+        // varies from read to read -- is balanced over all warps from the first queued candidate on.
         for (uint32_t k0 = 0; k0 < ndir; k0 += a.qcap / AF_CHUNK) {
-            const uint32_t kend = min(k0 + a.qcap / AF_CHUNK, ndir);
-            // 1a: a lane = a candidate; shared-memory pre-filter; survivors are queued
+            const uint32_t nch = min(a.qcap / AF_CHUNK, ndir - k0);
+            for (uint32_t i = tid; i < nch * AF_CHUNK; i += VT) queue[i] = AF_REC_INVALID;
+            if (tid == 0) { s_next = 0; s_done = 0; s_qn = 0; s_qhead = 0; }
+            __syncthreads();
             for (;;) {
-                uint32_t k = 0;
-                if (lane == 0) k = k0 + atomicAdd(&s_next, 1u);
-                k = __shfl_sync(FULL, k, 0);
-                if (k >= kend) break;
-                const uint32_t chunk = dir[k], ri = chunk * AF_CHUNK + lane;
-                if (lane == 0) a.chunk_hits[chunk] = 0;
-                const uint4 *rp = recs4 + (size_t)ri * a.rq;
-                const uint32_t rid = rp[0].x;
-                bool seeded = false;
-                if (rid != AF_REC_INVALID) {
-                    load_words(rp, rid);
-                    seeded = tail_prefilter<KP>(sw, VT, a.uniform_len > 0 ? a.uniform_len : (int)a.lens[rid], nmask_of(rid), filt, a.fmul, a.nb, a.P.k);
+                uint32_t what = 0, arg = 0;                  // 1 = extend queue entry `arg`, 2 = filter chunk `arg`, 3 = all done
+                if (lane == 0) {
+                    for (;;) {                               // take a queue entry if one is reserved and not yet taken
+                        const uint32_t h = ld_vol(&s_qhead);
+                        if (h >= ld_vol(&s_qn)) break;
+                        if (atomicCAS(&s_qhead, h, h + 1) == h) { what = 1; arg = h; break; }
+                    }
+                    if (!what && ld_vol(&s_next) < nch) {
+                        const uint32_t k = atomicAdd(&s_next, 1u);
+                        if (k < nch) { what = 2; arg = k; }
+                    }
+                    if (!what && ld_vol(&s_done) >= nch && ld_vol(&s_qhead) >= ld_vol(&s_qn)) what = 3;
                 }
-                __syncwarp();
-                const uint32_t todo = __ballot_sync(FULL, seeded);
-                if (todo) {
-                    uint32_t pos = 0;
-                    if (lane == 0) pos = atomicAdd(&s_qn, (uint32_t)__popc(todo));
-                    pos = __shfl_sync(FULL, pos, 0);
-                    if (seeded) queue[pos + __popc(todo & ((1u << lane) - 1u))] = ri;
-                }
-                __syncwarp();
-            }
-            __syncthreads();
-            if (r == blockIdx.x && k0 == 0) c_p1a = clock64();
-            // 1b: the queued candidates, one THREAD each, dense lanes
-            const uint32_t qn = s_qn;
-            n_seeded += tid == 0 ? qn : 0u;
-            for (uint32_t i0 = (uint32_t)warp * 32; i0 < qn; i0 += VT) {   // whole warps: thread_extend's loops are warp-uniform
-                const uint32_t i = i0 + lane;
-                const bool have = i < qn && (!AF_TAIL_EXP || lane == 0);
-                uint32_t ri = 0, rid = 0;
-                int L = 0;
-                const uint32_t *nm = nullptr;
-                if (have) {
-                    ri = queue[i];
+                what = __shfl_sync(FULL, what, 0);
+                arg = __shfl_sync(FULL, arg, 0);
+                if (what == 3) break;
+                if (what == 0) { __nanosleep(200); continue; }
+                if (what == 2) {
+                    const uint32_t chunk = dir[k0 + arg], ri = chunk * AF_CHUNK + lane;
+                    if (lane == 0) a.chunk_hits[chunk] = 0;
                     const uint4 *rp = recs4 + (size_t)ri * a.rq;
-                    rid = rp[0].x;
-                    load_words(rp, rid);
-                    L = a.uniform_len > 0 ? a.uniform_len : (int)a.lens[rid];
-                    nm = nmask_of(rid);
+                    const uint32_t rid = rp[0].x;
+                    bool seeded = false;
+                    if (rid != AF_REC_INVALID) {
+                        load_words(rp, rid);
+                        seeded = tail_prefilter<KP>(sw, VT, a.uniform_len > 0 ? a.uniform_len : (int)a.lens[rid], nmask_of(rid), filt, a.fmul, a.nb, a.P.k);
+                    }
+                    __syncwarp();
+                    const uint32_t todo = __ballot_sync(FULL, seeded);
+                    if (todo) {
+                        uint32_t pos = 0;
+                        if (lane == 0) pos = atomicAdd(&s_qn, (uint32_t)__popc(todo));
+                        pos = __shfl_sync(FULL, pos, 0);
+                        if (seeded) st_vol(&queue[pos + __popc(todo & ((1u << lane) - 1u))], ri);
+                        n_seeded += lane == 0 ? __popc(todo) : 0;
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(&s_done, 1u);   // after its entries are in the queue
+                    continue;
                 }
-                __syncwarp();
+                // what == 1: the whole warp extends queued candidate `arg`
+                uint32_t ri;
+                while ((ri = ld_vol(&queue[arg])) == AF_REC_INVALID) { }   // reserved a moment ago, about to be written
+                const uint32_t *rec = a.recs + (size_t)ri * (a.rq * 4);
+                const uint32_t rid = rec[0];
+                const uint32_t rw = lane < a.W ? rec[4 + (rid & 1u) * a.W + lane] : 0u;
+                const int L = a.uniform_len > 0 ? a.uniform_len : (int)a.lens[rid];
+                const uint32_t *nm = nmask_of(rid);
+                const uint32_t nwv = nm && lane < AF_NMASK_WORDS ? nm[lane] : 0u;
                 uint4 out;
-                ExtProf pf = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                const long long tq0 = AF_TAIL_PROF ? clock64() : 0;
-                const bool anchored = thread_extend(have, rid, L, sw, VT, nm, a.table, a.tmask, apk0p, apk1p, a.apn0p, a.apn1p, a.G, KP, 20 - KP, a.P, out, pf);
-                if (AF_TAIL_PROF && a.dbg && have && i < 64 && r == blockIdx.x) {
-                    long long *o = a.dbg + 8 * 148 + ((size_t)blockIdx.x * 64 + i) * 8;
-                    o[0] = clock64() - tq0; o[1] = pf.collect; o[2] = pf.eval; o[3] = pf.n_eval; o[4] = pf.n_load; o[5] = pf.n_iter; o[6] = pf.t_start; o[7] = pf.t_consume;
-                }
-                if (have && anchored) {
-                    // the anchored read's record replaces the header quad of its own candidate record; its bit goes
-                    // into the region's hit bitmap and into its chunk's hit mask
-                    reinterpret_cast<uint4 *>(a.recs)[(size_t)ri * a.rq] = out;
-                    const uint32_t bit = rid - rid0;
-                    atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
-                    atomicOr(&a.chunk_hits[ri / AF_CHUNK], 1u << (ri % AF_CHUNK));
+                if (tail_extend(rid, L, rw, nwv, nm != nullptr, a.table, a.tmask, apk0p, apk1p, a.apn0p, a.apn1p, a.G, KP, 20 - KP, a.P, lane, out)) {
+                    if (lane == 0) {
+                        // the anchored read's record replaces the header quad of its own candidate record; its bit goes
+                        // into the region's hit bitmap and into its chunk's hit mask
+                        reinterpret_cast<uint4 *>(a.recs)[(size_t)ri * a.rq] = out;
+                        const uint32_t bit = rid - rid0;
+                        atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+                        atomicOr(&a.chunk_hits[ri / AF_CHUNK], 1u << (ri % AF_CHUNK));
+                    }
                 }
             }
-            __syncthreads();
-            if (tid == 0) { s_next = 0; s_qn = 0; }
             __syncthreads();
         }
         if (r == blockIdx.x) c_p1b = clock64();
@@ -590,7 +403,7 @@ k_tail(const af_tail_args a, const af_sink sink, const int has_sink) {
         o[0] = c_staged - c_start; o[1] = c_p1a - c_start; o[2] = c_p1b - c_start; o[3] = c_look - c_start; o[4] = clock64() - c_start;
         o[5] = n_seeded;
     }
-    if (tid == 0 && n_seeded) atomicAdd(&s_seeded, n_seeded);
+    if (lane == 0 && n_seeded) atomicAdd(&s_seeded, n_seeded);
     if (over) atomicOr(&a.counts[AF_CNT_STATUS], AF_STATUS_HIT_OVERFLOW);
     __syncthreads();
     if (tid == 0 && s_seeded) atomicAdd(&a.counts[AF_CNT_SEEDED], s_seeded);
