@@ -34,6 +34,12 @@ class Batch(ctypes.Structure):
                 ("lens", c_vp), ("nread_ids", c_vp), ("nmask", c_vp), ("n_nreads", c_i64)]
 
 
+class GenomeStats(ctypes.Structure):
+    """af_genome_stats_t"""
+    _fields_ = [("genome_bases", c_i64), ("n_candidates", c_i64), ("n_seeds", c_i64), ("n_passes", c_i32), ("n_retries", c_i32),
+                ("scan_ms", ctypes.c_double), ("total_ms", ctypes.c_double), ("host_index_ms", ctypes.c_double)]
+
+
 class Synth(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("ref_len", c_i64), ("anchor_start", c_i64), ("anchor_len", c_i32),
                 ("read_len", c_i32), ("frag_mean", c_i32), ("frag_sd", c_i32), ("sub_ppm", c_u32),
@@ -42,6 +48,9 @@ class Synth(ctypes.Structure):
 
 HIT_DTYPE = np.dtype([("read_id", "<u4"), ("pos", "<i4"), ("clip_l", "<u2"), ("m_len", "<u2"),
                       ("clip_r", "<u2"), ("score_strand", "<u2")])
+GENOME_HIT_DTYPE = np.dtype([("pos", "<i8"), ("read_id", "<u4"), ("clip_l", "<u2"), ("m_len", "<u2"), ("clip_r", "<u2"),
+                             ("score_strand", "<u2"), ("reserved", "<u4")])
+GENOME_SEP = 256
 CNT_FLAGGED, CNT_HITS, CNT_STATUS, CNT_SEEDED, N_COUNTS = 0, 1, 2, 3, 8
 NMASK_WORDS = 8
 MAX_READ_LEN = 256
@@ -101,6 +110,14 @@ SIGNATURES = {
     "af_exchange_read": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i64, P(c_i64), P(ctypes.c_uint32), P(ctypes.c_uint32)]),
     "af_host_alloc": (c_vp, [ctypes.c_size_t]),
     "af_host_free": (None, [c_vp]),
+    "af_genome_from_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, P(c_vp)]),
+    "af_genome_from_contigs": (ctypes.c_int, [P(ctypes.c_char_p), P(ctypes.c_char_p), P(c_i64), c_i32, ctypes.c_int, P(c_vp)]),
+    "af_genome_synth": (ctypes.c_int, [ctypes.c_uint64, c_i64, ctypes.c_int, P(c_vp)]),
+    "af_genome_free": (None, [c_vp]),
+    "af_genome_length": (c_i64, [c_vp]),
+    "af_genome_n_contigs": (c_i32, [c_vp]),
+    "af_genome_contig": (ctypes.c_int, [c_vp, c_i32, P(ctypes.c_char_p), P(c_i64), P(c_i64)]),
+    "af_genome_align": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, P(Params), c_i32, c_vp, P(c_i64), P(GenomeStats)]),
     "af_synth_anchor": (ctypes.c_int, [P(Synth), c_vp]),
     "af_synth_pairs_host": (ctypes.c_int, [P(Synth), c_i64, c_i64, c_vp, c_vp]),
     "af_synth_pairs_device": (ctypes.c_int, [P(Synth), c_i64, c_i64, c_i32, c_vp, c_vp]),

@@ -231,6 +231,11 @@ struct af_index {
     int32_t n_keys, n_entries, n_overflow, pad_byte;
 };
 
+// shared-memory filter over `keys` (distinct k'-mers) with nbk buckets: tries the first n_muls multipliers and keeps
+// the one with the fewest false positives on 2^log2_probes pseudo-random keys (af_host.cpp)
+void af_filter_pick(const std::vector<uint32_t> &keys, uint32_t kmask, uint32_t nbk, int n_muls, int log2_probes,
+                    uint32_t &mul_out, std::vector<uint32_t> &filt_out, int32_t *ov_out);
+
 static inline uint8_t af_code_of(char c) {
     switch (c) {
         case 'A': case 'a': return 0;

@@ -47,6 +47,31 @@ static int build_filter(const std::vector<uint32_t> &keys, uint32_t fmul, uint32
     return overflow;
 }
 
+// The filter hash is one multiply; how often foreign k'-mers collide with stored ones depends on
+// the multiplier (the colliding key differences form a lattice).  Try a few and keep the one
+// with the lowest measured false-positive rate on pseudo-random probe keys.
+void af_filter_pick(const std::vector<uint32_t> &keys, uint32_t kmask, uint32_t nbk, int n_muls, int log2_probes,
+                    uint32_t &mul_out, std::vector<uint32_t> &filt_out, int32_t *ov_out) {
+    static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du,
+                                    0xFD7046C5u, 0xB55A4F09u, 0x8DA6B343u, 0xD8163841u, 0xCB1AB31Fu, 0x9C06FAF5u,
+                                    0x2545F491u, 0x6C8E9CF5u, 0xE7037ED1u, 0xA3B19535u};
+    std::vector<uint32_t> cand;
+    long best = -1;
+    for (int mi = 0; mi < n_muls && mi < 16; mi++) {
+        const uint32_t m = muls[mi];
+        int ov = build_filter(keys, m, nbk, cand);
+        long fp = 0;
+        uint32_t x = 0x12345678u;
+        for (int t = 0; t < (1 << log2_probes); t++) {
+            x = af_mix32(x + 0x9E3779B9u);
+            uint32_t b, fp3;
+            af_filter_hash(x & kmask, m, nbk, b, fp3);
+            fp += af_filter_test(cand[b], fp3) != 0;
+        }
+        if (best < 0 || fp < best) { best = fp; mul_out = m; filt_out = cand; if (ov_out) *ov_out = ov; }
+    }
+}
+
 extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t *params, int32_t kp,
                               af_index_t **out) {
     if (!anchor || !out || len <= 0 || len >= (1ll << 28)) { af_set_error("af_index_build: bad anchor"); return AF_ERR_ARG; }
@@ -128,27 +153,8 @@ extern "C" int af_index_build(const char *anchor, int64_t len, const af_params_t
     uint32_t nb = (uint32_t)std::min<uint64_t>(AF_MAX_BUCKETS, std::max<uint64_t>(AF_MIN_BUCKETS, want));
     nb = (nb + 31u) & ~31u;
     idx->nb = nb;
-    // The filter hash is one multiply; how often foreign k'-mers collide with stored ones depends on
-    // the multiplier (the colliding key differences form a lattice).  Try a few and keep the one
-    // with the lowest measured false-positive rate on pseudo-random probe keys.
-    static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du,
-                                    0xFD7046C5u, 0xB55A4F09u, 0x8DA6B343u, 0xD8163841u, 0xCB1AB31Fu, 0x9C06FAF5u,
-                                    0x2545F491u, 0x6C8E9CF5u, 0xE7037ED1u, 0xA3B19535u};
-    std::vector<uint32_t> cand;
     auto pick = [&](uint32_t nbk, uint32_t &mul_out, std::vector<uint32_t> &filt_out, int32_t *ov_out) {
-        long best = -1;
-        for (uint32_t m : muls) {
-            int ov = build_filter(keys, m, nbk, cand);
-            long fp = 0;
-            uint32_t x = 0x12345678u;
-            for (int t = 0; t < (1 << 18); t++) {
-                x = af_mix32(x + 0x9E3779B9u);
-                uint32_t b, fp3;
-                af_filter_hash(x & kmask, m, nbk, b, fp3);
-                fp += af_filter_test(cand[b], fp3) != 0;
-            }
-            if (best < 0 || fp < best) { best = fp; mul_out = m; filt_out = cand; if (ov_out) *ov_out = ov; }
-        }
+        af_filter_pick(keys, kmask, nbk, 16, 18, mul_out, filt_out, ov_out);
     };
     pick(nb, idx->fmul, idx->filter, &idx->n_overflow);
     idx->nb2 = ((nb / 2) + 31u) & ~31u;

@@ -268,6 +268,50 @@ int af_anchor_batch_exchange(const af_dev_index_t *d, const af_batch_t *batch, v
 int af_exchange_read(const af_exchange_t *ex, int32_t src_rank, int32_t slot, af_hit_t *h_out, int64_t cap,
                      int64_t *n_out, uint32_t *status_out, uint32_t *n_batches_out);
 
+/* ---- genome pass of the contiguity filter ----------------------------------- *
+ * Replaces `bwa mem -M -t T <genome> <w>_del_tmp.fa` inside del_too_many_reads (functions.py:716): the 2-op
+ * anchored reads are aligned to the whole GENOME under the same anchoring spec (k = 19 exact seed, ungapped
+ * X-drop extension, one primary record per read).  No genome index exists: the genome lives 2 bit/base in HBM
+ * (human: 0.8 GB + 0.4 GB N bitmap) and every pass STREAMS it once past a shared-memory filter holding the
+ * k'-mers of ~90 reads (both orientations); hits are verified against an exact table, every seeded diagonal is
+ * extended by one warp, the best record per read is kept.
+ * The genome is one sequence: [256 N] contig 0 [256 N] contig 1 ... [>= 256 N]; positions in records are 1-based
+ * in that sequence, af_genome_contig gives the contigs' starts. */
+typedef struct af_genome af_genome_t;
+typedef struct {
+    int64_t pos;           /* 1-based leftmost aligned base in the concatenated genome */
+    uint32_t read_id;      /* index of the read in the call */
+    uint16_t clip_l, m_len, clip_r;
+    uint16_t score_strand; /* score*2 + strand; strand 1 == the read's reverse complement lies on the genome */
+    uint32_t reserved;
+} af_genome_hit_t;
+typedef struct {
+    int64_t genome_bases;  /* bases streamed per pass */
+    int64_t n_candidates;  /* genome samples that passed the filter, all passes */
+    int64_t n_seeds;       /* (read, strand, diagonal) runs of >= k matches handed to the extension */
+    int32_t n_passes;
+    int32_t n_retries;     /* passes repeated with larger buffers */
+    double scan_ms;        /* device time of the genome scans (CUDA events), all passes */
+    double total_ms;       /* device time of the whole call */
+    double host_index_ms;  /* host time spent building the per-pass filters and tables */
+} af_genome_stats_t;
+#define AF_GENOME_SEP 256
+/* FASTA (plain or gzip); contig name = header up to the first blank */
+int af_genome_from_fasta(const char *path, int device, af_genome_t **out);
+/* n contigs given as ASCII strings (ACGT any case; anything else is N) */
+int af_genome_from_contigs(const char *const *names, const char *const *seqs, const int64_t *lens, int32_t n, int device,
+                           af_genome_t **out);
+/* measurement input: one contig "synth" whose base x is af_synth's random reference base f(seed, x), generated on the device */
+int af_genome_synth(uint64_t seed, int64_t len, int device, af_genome_t **out);
+void af_genome_free(af_genome_t *g);
+int64_t af_genome_length(const af_genome_t *g); /* separators included */
+int32_t af_genome_n_contigs(const af_genome_t *g);
+int af_genome_contig(const af_genome_t *g, int32_t i, const char **name, int64_t *start /* 0-based in the concatenation */, int64_t *len);
+/* reads: concatenated ASCII, offs[i]..offs[i+1] delimit read i (<= AF_MAX_READ_LEN bases each).  hits_out holds up to
+ * n_reads records, ordered by read_id; reads without a record are unaligned.  reads_per_pass = 0 picks the default. */
+int af_genome_align(af_genome_t *g, const char *reads, const int64_t *offs, int64_t n_reads, const af_params_t *params,
+                    int32_t reads_per_pass, af_genome_hit_t *hits_out, int64_t *n_hits_out, af_genome_stats_t *stats);
+
 /* ---- seeded synthetic reads (measurement) --------------------------------- */
 typedef struct {
     uint64_t seed;

@@ -35,6 +35,8 @@ def test_struct_sizes_match_the_header():
     assert ctypes.sizeof(_lib.Batch) == 56
     assert ctypes.sizeof(_lib.Synth) == 56
     assert ctypes.sizeof(_lib.IndexInfo) == 44
+    assert _lib.GENOME_HIT_DTYPE.itemsize == 24          # af_genome_hit_t
+    assert ctypes.sizeof(_lib.GenomeStats) == 56         # af_genome_stats_t
 
 
 def test_no_cpu_fallback_device_entry_points_fail_loudly_without_a_gpu():
@@ -50,6 +52,11 @@ def test_no_cpu_fallback_device_entry_points_fail_loudly_without_a_gpu():
     from anchored_fusion_b200.dist import HitExchange
     with pytest.raises(af.AnchoredFusionError):
         HitExchange(0, 1, 1, 64, 0)              # the hit exchange lives in device memory: no GPU, no exchange
+    from anchored_fusion_b200.genome import Genome
+    with pytest.raises(af.AnchoredFusionError):
+        Genome.from_contigs([("c", "ACGT" * 100)])    # the genome pass streams a genome resident in HBM: no GPU, no genome
+    with pytest.raises(af.AnchoredFusionError):
+        Genome.synthetic(1, 100000)
 
 
 def test_only_the_seed_length_the_kernels_are_built_for_is_accepted():
