@@ -98,6 +98,31 @@ def write_split_points(stats, gene, path):
     return groups
 
 
+def contiguity_stage(out_dir_name, gene, args):
+    """del_too_many_reads (Anchored_Fusion.py:202-203) when --file_ref_seq names a genome FASTA: the 2-op anchored
+    reads are re-aligned to the genome on the GPU (genome.py; the reference runs `bwa mem` on the genome here) and
+    the survivors go to `<w>_anchored_reads.sam` -- the file the reference's Find_fine_block / contact_reads read
+    next, and whose existence makes the reference skip its own del_too_many_reads.  Also writes the split-point
+    table of the survivors.  Returns the number of surviving reads, or None when there is no genome."""
+    ref = getattr(args, 'file_ref_seq', '')
+    if not ref or not os.path.isfile(ref):
+        return None
+    from .functions import contact_reads, del_too_many_reads
+    out_sam = out_dir_name + '_anchored_reads.sam'
+    if not os.path.exists(out_sam):
+        part = out_sam + '.partial'
+        from .stage import resolve_device
+        del_too_many_reads(out_dir_name + '_anchored_reads.bam', part, out_dir_name, ref, args.thread, device=resolve_device(args.gpu_number))
+        os.replace(part, out_sam)
+    groups = contact_reads(out_sam, out_dir_name, ref, args.thread)
+    with open(out_dir_name + '_split_points_filtered.txt', 'w') as o:
+        o.write('gene\tsplit_point\ttype\tsupport\tseq_left\tseq_right\n')
+        for g in sorted(groups, key=lambda g: (-g.cnt, g.breakpoint)):
+            o.write('%s\t%d\t%s\t%d\t%s\t%s\n' % (gene, g.breakpoint, g.type_, g.cnt, g.seq_left, g.seq_right))
+    with open(out_sam) as fh:
+        return sum(1 for _ in fh)
+
+
 def run_gene_sample(file_anchored_seq, gene, fastq1, fastq2, out_dir_name, args, gene_anchorer=None):
     done = out_dir_name + '_anchored_reads.bam'
     if os.path.exists(done) and os.path.exists(out_dir_name + '_realign_reads.bam'):
@@ -109,6 +134,9 @@ def run_gene_sample(file_anchored_seq, gene, fastq1, fastq2, out_dir_name, args,
     if stats is None:               # a rank other than 0 of a torchrun job: rank 0 writes the files
         return None
     groups = write_split_points(stats, gene, out_dir_name + '_split_points.txt')
+    kept = contiguity_stage(out_dir_name, gene, args)
+    if kept is not None:
+        print('[anchoring] %s: %d 2-op reads survive the genome-contiguity filter' % (gene, kept))
     dt = time.time() - t0
     print('[anchoring] %s: %d pairs, %d anchored reads, %d half-anchored pairs, %d split-point groups, %.2f s (%.0f pairs/s)'
           % (gene, stats['pairs'], stats['anchored'], stats['half_anchored_pairs'], len(groups), dt, stats['pairs'] / max(dt, 1e-9)))
@@ -162,6 +190,7 @@ def main_bulk(argv=None):
         if all_stats is not None:
             for (g, _), stats in zip(todo, all_stats):
                 groups = write_split_points(stats, g, work_prefix(g) + '_split_points.txt')
+                contiguity_stage(work_prefix(g), g, args)
                 print('[anchoring] %s: %d pairs, %d anchored reads, %d half-anchored pairs, %d split-point groups'
                       % (g, stats['pairs'], stats['anchored'], stats['half_anchored_pairs'], len(groups)))
             print('[anchoring] %d genes in one pass over the reads, %.2f s' % (len(todo), time.time() - t0))
@@ -229,6 +258,7 @@ def main_singlecell(argv=None):
         def on_cell(cell, cell_stats):
             for gene, st in zip(gene_names, cell_stats):
                 write_split_points(st, gene, prefix_of(gene, cell) + '_split_points.txt')
+                contiguity_stage(prefix_of(gene, cell), gene, args)
 
         res = anchor_cells(gas, mine, prefix_of, thread=args.thread, on_cell=on_cell)
         n_pairs, n_cells = res['pairs'], res['cells']

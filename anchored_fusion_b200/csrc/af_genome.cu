@@ -659,7 +659,7 @@ extern "C" int af_genome_align(af_genome_t *g, const char *reads, const int64_t 
     std::condition_variable cv;
     int next_build = 0, consumed = 0;
     bool stop = false;
-    const int n_workers = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 8, n_pass}));
+    const int n_workers = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, n_pass}));
     std::vector<std::thread> workers;
     for (int t = 0; t < n_workers; t++)
         workers.emplace_back([&]() {

@@ -253,3 +253,51 @@ def test_del_too_many_reads_with_the_gpu_genome_pass(toy, tmp_path):
     assert 0 < len(got) < len(recs)                           # some reads are explained by the genome, some are not
     assert not os.path.exists(str(tmp_path / "w") + "_del_tmp.fa")
     g.close()
+
+
+def test_bulk_cli_runs_the_contiguity_stage_when_given_a_genome(bundled, tmp_path):
+    """--file_ref_seq <genome FASTA>: the CLI goes on to del_too_many_reads (Anchored_Fusion.py:202-203) with the GPU
+    genome pass and leaves <w>_anchored_reads.sam, the file the reference's next stages read."""
+    from anchored_fusion_b200.bam import read_bam, sam_line
+    from anchored_fusion_b200.cli import main_bulk
+    from anchored_fusion_b200.functions import contiguity_filter, two_op_records
+    from anchored_fusion_b200.genome import Genome
+    d = str(tmp_path)
+    fa = os.path.join(d, "target_gene.fasta")
+    with open(fa, "w") as fh:
+        fh.write(bundled["header"] + "\n" + bundled["anchor"] + "\n")
+    p1, p2 = os.path.join(d, "s_1.fastq"), os.path.join(d, "s_2.fastq")
+    q = bundled["qual_char"] * bundled["read_len"]
+    with open(p1, "w") as f1, open(p2, "w") as f2:
+        for i in range(len(bundled["seqs1"])):
+            f1.write("@%s\n%s\n+\n%s\n" % (bundled["names1"][i], bundled["seqs1"][i], q))
+            f2.write("@%s\n%s\n+\n%s\n" % (bundled["names2"][i], bundled["seqs2"][i], q))
+    # toy genome: the gene itself, and a contig that holds every third junction-spanning read in full (those reads
+    # are explained by the genome without a junction and must go), in random flanks
+    rng = np.random.default_rng(1)
+    hits = bundled["oracle_hits"]
+    clipped = [h for h in hits if int(h["clip_l"]) >= 20 or int(h["clip_r"]) >= 20]
+    whole = []
+    for h in clipped[::3]:
+        rid = int(h["read_id"])
+        whole.append((bundled["seqs1"], bundled["seqs2"])[rid & 1][rid >> 1])
+    contigs = [("chrG", _rand_seq(rng, 5000) + bundled["anchor"] + _rand_seq(rng, 5000)),
+               ("chrJ", _rand_seq(rng, 300).join(whole) + _rand_seq(rng, 300))]
+    gfa = os.path.join(d, "genome.fa")
+    with open(gfa, "w") as fh:
+        for n, s in contigs:
+            fh.write(">%s\n" % n + "".join(s[i:i + 80] + "\n" for i in range(0, len(s), 80)))
+    out = os.path.join(d, "out")
+    assert main_bulk(["--file_anchored_cds", fa, "--fastq1", p1, "--fastq2", p2, "--out_folder", out, "--file_ref_seq", gfa,
+                      "--not_filter_false_positive", "--thread", "4"]) == 0
+    w = os.path.join(out, "BCR_fusion", "work_dir", "BCR_fusion")
+    got = open(w + "_anchored_reads.sam").read().splitlines(keepends=True)
+    recs = list(two_op_records([sam_line(r) for r in read_bam(w + "_anchored_reads.bam")[2]]))
+    g = Genome.from_contigs(contigs)
+    ora = _oracle_hits(_concat(contigs), [s for _, s in recs])
+    want = contiguity_filter(g.sam_lines([t for t, _ in recs], [s for _, s in recs], ora))
+    assert got == want
+    assert 0 < len(got) < len(recs) and len(recs) - len(got) >= len(whole) // 2
+    assert all(len(l.split("\t")) == 11 for l in got)
+    assert os.path.exists(w + "_split_points_filtered.txt")
+    g.close()
