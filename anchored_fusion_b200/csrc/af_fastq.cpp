@@ -37,6 +37,7 @@
 
 #include "af_common.h"
 #include "af_inflate.h"
+#include "af_crc32.h"
 
 struct SeqRef { const char *p; int32_t len; };
 struct PackSide {
@@ -304,7 +305,7 @@ struct Side {
             index_slice(*sp, *sl);
             if (with_crc_member) {
                 CrcPiece c;
-                c.crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)sp->text + sl->b, (uInt)(sl->e - sl->b));
+                c.crc = af_crc32((const uint8_t *)sp->text + sl->b, sl->e - sl->b);
                 c.len = sl->e - sl->b; c.member_end = member_end; c.want_crc = want_crc; c.want_size = want_size;
                 sl->crc.push_back(c);
             }
@@ -349,7 +350,7 @@ struct Side {
                     if (rc < 0) { if (e.empty()) e = rc == afz::ERR_TRUNCATED ? "gzip stream is truncated" : "corrupt deflate data"; break; }
                     const uint8_t *t = inf.byte_pos();
                     if (end - t < 8) { e = "gzip stream is truncated (no trailer)"; break; }
-                    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)sp->text + member_start, (uInt)(out_len - member_start));
+                    const uint32_t crc = af_crc32((const uint8_t *)sp->text + member_start, out_len - member_start);
                     if (crc != rd32(t) || (uint32_t)(out_len - member_start) != rd32(t + 4)) { e = "gzip CRC or length check failed"; break; }
                     p = t + 8;
                 }
@@ -459,7 +460,7 @@ struct Side {
                         uint8_t *start = o;
                         const int rc = inf.run(start, &o, start + b.isize + 1, start + b.isize);
                         if (rc != afz::OK_DONE || (size_t)(o - start) != b.isize) { sp->fail("corrupt BGZF block"); o = start + b.isize; continue; }
-                        if (b.isize && (uint32_t)crc32(crc32(0L, Z_NULL, 0), start, b.isize) != rd32(bp + b.size - 8)) sp->fail("BGZF block CRC check failed");
+                        if (b.isize && af_crc32(start, b.isize) != rd32(bp + b.size - 8)) sp->fail("BGZF block CRC check failed");
                     }
                     index_slice(*sp, *sl);
                     sp->latch.done();
@@ -993,3 +994,6 @@ extern "C" int af_fastq_file_starts(const af_fastq_t *fq, int64_t *first_pair_ou
 
 // pairs handed out before the current batch (global index of the current batch's first pair)
 extern "C" int64_t af_fastq_batch_first_pair(const af_fastq_t *fq) { return fq ? fq->pairs_done : 0; }
+
+// test hook: the reader's CRC-32 (carry-less multiplication where the CPU has it) of a host buffer
+extern "C" uint32_t af_debug_crc32(const void *buf, int64_t len) { return buf && len > 0 ? af_crc32((const uint8_t *)buf, (size_t)len) : af_crc32((const uint8_t *)"", 0); }

@@ -175,6 +175,9 @@ int af_fastq_record(const af_fastq_t *fq, int64_t read_id, const char **name, in
  * needed) when text_cap is too small; text may be NULL to size the buffer. */
 int af_fastq_records(const af_fastq_t *fq, const int64_t *read_ids, int64_t n, char *text, int64_t text_cap,
                      int64_t *offs, int64_t *text_used);
+/* test hook: the CRC-32 the reader checks every inflated BGZF block / gzip member with (PCLMULQDQ folding where the
+ * CPU has it, zlib otherwise); equals zlib's crc32(0, buf, len) */
+uint32_t af_debug_crc32(const void *buf, int64_t len);
 /* index (over the whole run) of the first pair of every input file started so far; returns the count */
 int af_fastq_file_starts(const af_fastq_t *fq, int64_t *first_pair_out, int32_t cap);
 /* index (over the whole run) of the current batch's first pair */

@@ -419,3 +419,17 @@ def test_inflater_equals_zlib_on_many_streams(tmp_path):
         _, recs = _read_all(rd)
         rd.close()
         assert [r[1] for r in recs[0::2]] == seqs and [r[2] for r in recs[0::2]] == quals, k
+
+
+def test_reader_crc32_equals_zlib_on_every_length_and_alignment():
+    """af_crc32.h (PCLMULQDQ folding, zlib below 64 bytes and on CPUs without it) against zlib.crc32."""
+    import zlib
+    from anchored_fusion_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(9)
+    sizes = list(range(0, 200)) + [255, 256, 257, 1023, 4096, 4097, 65535, 65536, 65537, (1 << 20) + 5]
+    for n in sizes:
+        for off in (0, 1, 3, 15):
+            raw = rng.integers(0, 256, n + off, dtype=np.uint8)
+            view = raw[off:]
+            assert L.af_debug_crc32(view.ctypes.data, n) == zlib.crc32(view.tobytes()), (n, off)
