@@ -13,6 +13,7 @@ buffers) and the GPU pipeline; only the anchored reads and the mates of half-anc
 ever materialised as text.
 """
 import ctypes
+import os
 import sys
 
 import numpy as np
@@ -202,7 +203,13 @@ def host_threads(thread):
         t = int(thread)
     except (TypeError, ValueError):
         t = 0
-    return t if t > 0 else 0
+    if t > 0:
+        return t
+    # one process per GPU (torchrun): the ranks of a node share its cores instead of each starting one worker per core
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or "1")
+    if local_world > 1:
+        return max(2, (os.cpu_count() or 1) // local_world)
+    return 0
 
 
 class AnchoredRead:
