@@ -10,4 +10,5 @@ from ._lib import HIT_DTYPE, AnchoredFusionError, lib  # noqa: F401
 lib()  # load now: a missing CUDA library must not go unnoticed
 
 from .anchoring import (Anchorer, AnchorIndex, PackedBatch, default_params, layout, pack_pairs,  # noqa: E402,F401
-                        synth_anchor, synth_pairs_device, synth_pairs_host, synth_spec, unpack_read)
+                        synth_anchor, synth_pairs_device, synth_pairs_host, synth_spec, unpack_read, wire_bytes,
+                        wire_from_packed, wire_to_packed)

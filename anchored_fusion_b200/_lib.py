@@ -100,6 +100,11 @@ SIGNATURES = {
     "af_pipeline_free": (None, [c_vp]),
     "af_pipeline_run": (ctypes.c_int, [c_vp, P(Batch), c_vp, c_i64, P(c_i64), P(c_i64)]),
     "af_pipeline_run_multi": (ctypes.c_int, [c_vp, c_i32, c_vp, P(Batch), c_vp, c_vp, c_vp, c_vp]),
+    "af_wire_bytes": (c_i64, [c_i32, c_i64]),
+    "af_wire_from_packed": (ctypes.c_int, [c_vp, c_i32, c_i64, c_vp]),
+    "af_wire_to_packed": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i32, c_vp]),
+    "af_wire_expand_device": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp]),
+    "af_pipeline_run_wire": (ctypes.c_int, [c_vp, P(Batch), c_i32, c_vp, c_i64, P(c_i64), P(c_i64)]),
     "af_pipeline_launches": (c_i64, [c_vp]),
     "af_pipeline_h2d_bytes": (c_i64, [c_vp]),
     "af_exchange_create": (ctypes.c_int, [ctypes.c_int, c_i32, c_i32, c_i32, c_i64, P(c_vp)]),

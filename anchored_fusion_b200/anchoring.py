@@ -138,6 +138,28 @@ def pack_pairs(seqs1, seqs2, max_read_len=None, pad_byte=0xE4, out=None):
                        nids[:k].copy() if k else None, nmask[:k].copy() if k else None)
 
 
+def wire_bytes(max_read_len, n_pairs):
+    return lib().af_wire_bytes(max_read_len, n_pairs)
+
+
+def wire_from_packed(packed, max_read_len, n_pairs, out=None):
+    """Packed tiles (uint32 array, host) -> wire format (4 * max_read_len bits per pair, include/anchored_fusion.h)."""
+    packed = np.ascontiguousarray(packed).view(np.uint32)
+    nbytes = wire_bytes(max_read_len, n_pairs)
+    wire = out if out is not None else np.zeros(nbytes // 4, dtype=np.uint32)
+    assert wire.nbytes >= nbytes
+    check(lib().af_wire_from_packed(packed.ctypes.data, max_read_len, n_pairs, wire.ctypes.data))
+    return wire
+
+
+def wire_to_packed(wire, max_read_len, n_pairs, pad_byte):
+    """Host twin of the device expansion: wire format -> packed tiles."""
+    wire = np.ascontiguousarray(wire).view(np.uint32)
+    packed = np.zeros(layout(max_read_len, n_pairs).packed_bytes // 4, dtype=np.uint32)
+    check(lib().af_wire_to_packed(wire.ctypes.data, max_read_len, n_pairs, pad_byte, packed.ctypes.data))
+    return packed
+
+
 def unpack_read(batch, read_id, length=None):
     """codes 0..3 of one read of a HOST batch (test helper)."""
     length = batch.read_len(read_id) if length is None else length
@@ -254,15 +276,19 @@ class Anchorer:
             _lib._lib.af_pipeline_free(self._pipe)
         self._pipe, self._pipe_key = None, None
 
-    def anchor_host(self, batch, slot_pairs=1 << 20, n_slots=3, hits_out=None):
+    def anchor_host(self, batch, slot_pairs=1 << 20, n_slots=3, hits_out=None, wire=False):
         """Anchor a HOST batch (numpy / pinned arrays): H2D copies, kernels and the D2H of the
-        hit list all happen inside this call.  Returns (hits ndarray, stats)."""
+        hit list all happen inside this call.  Returns (hits ndarray, stats).  wire=True: batch.packed holds
+        the wire format (`wire_from_packed`), 4 L bits per pair instead of whole tiles; it is expanded on the GPU."""
         pipe = self.pipeline(batch.max_read_len, slot_pairs, n_slots)
         cap = 2 * max(batch.n_pairs, 1) if hits_out is None else len(hits_out)
         out = hits_out if hits_out is not None else np.zeros(cap, dtype=HIT_DTYPE)
         nh, nf = ctypes.c_int64(0), ctypes.c_int64(0)
         cb = batch.c_struct()
-        check(lib().af_pipeline_run(pipe, ctypes.byref(cb), out.ctypes.data, cap, ctypes.byref(nh), ctypes.byref(nf)))
+        if wire:
+            check(lib().af_pipeline_run_wire(pipe, ctypes.byref(cb), self.index.pad_byte, out.ctypes.data, cap, ctypes.byref(nh), ctypes.byref(nf)))
+        else:
+            check(lib().af_pipeline_run(pipe, ctypes.byref(cb), out.ctypes.data, cap, ctypes.byref(nh), ctypes.byref(nf)))
         return out[: nh.value], {"flagged": nf.value, "hits": nh.value}
 
     def __del__(self):

@@ -208,6 +208,72 @@ extern "C" int af_layout(int32_t max_read_len, int64_t n_pairs, af_layout_t *out
     return AF_OK;
 }
 
+// ---- wire format (include/anchored_fusion.h): a pair's 4 L bits back to back, word-interleaved per tile ----------
+static inline int wire_words(int32_t L) { return (4 * L + 31) / 32; }
+static inline uint32_t pad_word(int32_t pad_byte) {
+    uint32_t padw = 0;
+    for (int i = 0; i < 16; i++) padw |= (uint32_t)((pad_byte >> (2 * (i & 3))) & 3) << (2 * i);
+    return padw;
+}
+extern "C" int64_t af_wire_bytes(int32_t max_read_len, int64_t n_pairs) {
+    if (max_read_len <= 0 || max_read_len > AF_MAX_READ_LEN || n_pairs < 0) return -1;
+    return ((n_pairs + AF_TILE_PAIRS - 1) / AF_TILE_PAIRS) * (int64_t)wire_words(max_read_len) * 128;
+}
+extern "C" int af_wire_from_packed(const void *packed, int32_t L, int64_t n_pairs, void *wire_out) {
+    af_layout_t lay;
+    int rc = af_layout(L, n_pairs, &lay);
+    if (rc) return rc;
+    if ((!packed || !wire_out) && lay.n_tiles) { af_set_error("af_wire_from_packed: null"); return AF_ERR_ARG; }
+    const int W = lay.words_per_read, Q = lay.quads_per_pair, NW = wire_words(L);
+    const uint32_t *in = (const uint32_t *)packed;
+    uint32_t *out = (uint32_t *)wire_out;
+    for (int64_t tile = 0; tile < lay.n_tiles; tile++)
+        for (int lane = 0; lane < 32; lane++) {
+            const uint32_t *pb = in + (tile * Q * 32 + lane) * 4;
+            uint32_t o[33];
+            memset(o, 0, sizeof(o));
+            int bit = 0;
+            for (int m = 0; m < 2; m++)
+                for (int t = 0; t < W; t++) {
+                    const int wi = m * W + t, nb = std::min(32, 2 * L - 32 * t);
+                    uint32_t v = pb[(wi >> 2) * 128 + (wi & 3)];
+                    if (nb < 32) v &= (1u << nb) - 1u;
+                    const int a = bit >> 5, sh = bit & 31;
+                    o[a] |= v << sh;
+                    if (sh && sh + nb > 32) o[a + 1] |= v >> (32 - sh);
+                    bit += nb;
+                }
+            for (int j = 0; j < NW; j++) out[(tile * NW + j) * 32 + lane] = o[j];
+        }
+    return AF_OK;
+}
+extern "C" int af_wire_to_packed(const void *wire, int32_t L, int64_t n_pairs, int32_t pad_byte, void *packed_out) {
+    af_layout_t lay;
+    int rc = af_layout(L, n_pairs, &lay);
+    if (rc) return rc;
+    if ((!wire || !packed_out) && lay.n_tiles) { af_set_error("af_wire_to_packed: null"); return AF_ERR_ARG; }
+    const int W = lay.words_per_read, Q = lay.quads_per_pair, NW = wire_words(L);
+    const uint32_t padw = pad_word(pad_byte);
+    const uint32_t *in = (const uint32_t *)wire;
+    uint32_t *out = (uint32_t *)packed_out;
+    for (int64_t tile = 0; tile < lay.n_tiles; tile++)
+        for (int lane = 0; lane < 32; lane++) {
+            uint32_t *pb = out + (tile * Q * 32 + lane) * 4;
+            for (int wi = 0; wi < 4 * Q; wi++) {
+                uint32_t word = 0;
+                if (wi < 2 * W) {
+                    const int m = wi >= W, t = wi - m * W, nb = std::min(32, 2 * L - 32 * t), bit = m * 2 * L + 32 * t;
+                    const int a = bit >> 5, sh = bit & 31;
+                    const uint32_t lo = in[(tile * NW + a) * 32 + lane], hi = a + 1 < NW ? in[(tile * NW + a + 1) * 32 + lane] : 0u;
+                    const uint32_t v = af_funnel_r(lo, hi, sh), mask = nb >= 32 ? 0xFFFFFFFFu : (1u << nb) - 1u;
+                    word = (v & mask) | (padw & ~mask);
+                }
+                pb[(wi >> 2) * 128 + (wi & 3)] = word;
+            }
+        }
+    return AF_OK;
+}
+
 struct SeqRef { const char *p; int32_t len; };
 
 // One mate's words of every pair of a batch (mate 0 also writes the zero words that pad a pair to

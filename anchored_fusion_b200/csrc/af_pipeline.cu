@@ -24,12 +24,70 @@
     } while (0)
 
 
+// ---- wire format -> tiles, on the device (include/anchored_fusion.h, "Wire format") -----------------------------
+// One thread per pair: word j of the pair's bit stream sits at wire[(tile * NW + j) * 32 + lane] (coalesced), every
+// tile word is two neighbouring stream words funnel-shifted; bases past max_read_len in a mate's last word get the
+// pad pattern back, the words that pad a pair to whole quads are zero.  Writes one 128-bit quad per store, 512
+// contiguous bytes per warp.  Reads 76 and writes 80 bytes per 2 x 150 bp pair: ~0.25 ms per 10 M pairs, behind a
+// 14 ms copy.
+__global__ void __launch_bounds__(256)
+k_wire_expand(const uint32_t *__restrict__ wire, long long n_tiles, int L, int W, int Q, int NW, uint32_t padw, uint4 *__restrict__ packed) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x, tile = p >> 5;
+    if (tile >= n_tiles) return;
+    const int lane = (int)(p & 31);
+    const uint32_t *src = wire + tile * NW * 32 + lane;
+    for (int q = 0; q < Q; q++) {
+        uint32_t o[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int wi = 4 * q + c;
+            uint32_t word = 0u;
+            if (wi < 2 * W) {
+                const int m = wi >= W, t = wi - m * W, nb = min(32, 2 * L - 32 * t), bit = m * 2 * L + 32 * t;
+                const int a = bit >> 5, sh = bit & 31;
+                const uint32_t lo = __ldg(src + a * 32), hi = a + 1 < NW ? __ldg(src + (a + 1) * 32) : 0u;
+                const uint32_t v = __funnelshift_r(lo, hi, sh), mask = nb >= 32 ? 0xFFFFFFFFu : (1u << nb) - 1u;
+                word = (v & mask) | (padw & ~mask);
+            }
+            o[c] = word;
+        }
+        packed[(tile * Q + q) * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+static uint32_t pad_word_of(int32_t pad_byte) {
+    uint32_t padw = 0;
+    for (int i = 0; i < 16; i++) padw |= (uint32_t)((pad_byte >> (2 * (i & 3))) & 3) << (2 * i);
+    return padw;
+}
+
+static long long g_wire_launches = 0;
+
+static int wire_expand_launch(const void *d_wire, int32_t L, int64_t n_pairs, int32_t pad_byte, void *d_packed, cudaStream_t st) {
+    af_layout_t lay;
+    int rc = af_layout(L, n_pairs, &lay);
+    if (rc) return rc;
+    if (lay.n_tiles == 0) return AF_OK;
+    const long long threads = lay.n_tiles * 32;
+    k_wire_expand<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const uint32_t *)d_wire, lay.n_tiles, L, lay.words_per_read,
+                                                                     lay.quads_per_pair, (4 * L + 31) / 32, pad_word_of(pad_byte), (uint4 *)d_packed);
+    g_wire_launches++;
+    AF_CUDA(cudaGetLastError());
+    return AF_OK;
+}
+
+extern "C" int af_wire_expand_device(const void *d_wire, int32_t max_read_len, int64_t n_pairs, int32_t pad_byte, void *d_packed, void *stream) {
+    if ((!d_wire || !d_packed) && n_pairs > 0) { af_set_error("af_wire_expand_device: null"); return AF_ERR_ARG; }
+    return wire_expand_launch(d_wire, max_read_len, n_pairs, pad_byte, d_packed, (cudaStream_t)stream);
+}
+
 static const int MAX_GENES = 64;     // anchor indexes one pipeline can scan a resident chunk for
 
 struct Slot {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     void *d_packed = nullptr, *d_ws = nullptr;
+    void *d_wire = nullptr;         // wire-format staging of the chunk (af_pipeline_run_wire), allocated on first use
     uint16_t *d_lens = nullptr;
     uint32_t *d_nids = nullptr, *d_nmask = nullptr;
     std::vector<uint32_t *> d_counts;   // per anchor index
@@ -49,7 +107,7 @@ struct af_pipeline {
     int32_t max_read_len = 0;
     size_t ws_bytes = 0;
     std::vector<Slot> slots;
-    long long launches0 = 0;
+    long long launches0 = 0, wire_launches0 = 0;
     long long h2d_bytes = 0;        // bytes copied host -> device so far (tiles, lengths, N lists)
 };
 
@@ -59,7 +117,7 @@ extern "C" void af_pipeline_free(af_pipeline_t *p) {
     cudaSetDevice(p->device);
     for (Slot &s : p->slots) {
         if (s.st) cudaStreamSynchronize(s.st);
-        cudaFree(s.d_packed); cudaFree(s.d_ws); cudaFree(s.d_lens); cudaFree(s.d_nids); cudaFree(s.d_nmask);
+        cudaFree(s.d_packed); cudaFree(s.d_wire); cudaFree(s.d_ws); cudaFree(s.d_lens); cudaFree(s.d_nids); cudaFree(s.d_nmask);
         for (uint32_t *c : s.d_counts) cudaFree(c);
         for (af_hit_t *h : s.d_hits) cudaFree(h);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_nids); cudaFreeHost(s.h_hits);
@@ -87,6 +145,7 @@ extern "C" int af_pipeline_create(const af_dev_index_t *d, int64_t slot_pairs, i
     p->ws_bytes = af_workspace_bytes_len(slot_pairs, p->cand_cap, max_read_len);
     p->slots.resize((size_t)n_slots);
     p->launches0 = af_kernel_launches();
+    p->wire_launches0 = g_wire_launches;
     cudaError_t e = cudaSetDevice(p->device);
     for (Slot &s : p->slots) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
@@ -112,7 +171,7 @@ extern "C" int af_pipeline_create(const af_dev_index_t *d, int64_t slot_pairs, i
     return AF_OK;
 }
 
-extern "C" int64_t af_pipeline_launches(const af_pipeline_t *p) { return p ? af_kernel_launches() - p->launches0 : 0; }
+extern "C" int64_t af_pipeline_launches(const af_pipeline_t *p) { return p ? af_kernel_launches() - p->launches0 + (g_wire_launches - p->wire_launches0) : 0; }
 extern "C" int64_t af_pipeline_h2d_bytes(const af_pipeline_t *p) { return p ? p->h2d_bytes : 0; }
 
 // wait for a slot, append its hits (rebased to batch read ids) to each anchor index's list
@@ -149,7 +208,18 @@ static void drain_all(af_pipeline *p) {
 }
 
 static int pipeline_run_impl(af_pipeline_t *p, int n_genes, const af_dev_index_t *const *idx, const af_batch_t *hb,
-                             af_hit_t *const *h_hits, const int64_t *hits_cap, int64_t *n_hits_out, int64_t *n_flagged_out);
+                             af_hit_t *const *h_hits, const int64_t *hits_cap, int64_t *n_hits_out, int64_t *n_flagged_out,
+                             bool wire = false, int32_t pad_byte = 0);
+
+extern "C" int af_pipeline_run_wire(af_pipeline_t *p, const af_batch_t *hb, int32_t pad_byte, af_hit_t *h_hits, int64_t hits_cap,
+                                    int64_t *n_hits_out, int64_t *n_flagged_out) {
+    if (!p || !n_hits_out) { af_set_error("af_pipeline_run_wire: null argument"); return AF_ERR_ARG; }
+    int64_t nf = 0;
+    const int rc = pipeline_run_impl(p, 1, &p->d, hb, &h_hits, &hits_cap, n_hits_out, &nf, true, pad_byte);
+    if (rc != AF_OK) drain_all(p);
+    else if (n_flagged_out) *n_flagged_out = nf;
+    return rc;
+}
 
 extern "C" int af_pipeline_run(af_pipeline_t *p, const af_batch_t *hb, af_hit_t *h_hits, int64_t hits_cap,
                                int64_t *n_hits_out, int64_t *n_flagged_out) {
@@ -180,7 +250,8 @@ extern "C" int af_pipeline_run_multi(af_pipeline_t *p, int32_t n_indexes, const 
 }
 
 static int pipeline_run_impl(af_pipeline_t *p, int n_genes, const af_dev_index_t *const *idx, const af_batch_t *hb,
-                             af_hit_t *const *h_hits, const int64_t *hits_cap, int64_t *n_hits_out, int64_t *n_flagged_out) {
+                             af_hit_t *const *h_hits, const int64_t *hits_cap, int64_t *n_hits_out, int64_t *n_flagged_out,
+                             bool wire, int32_t pad_byte) {
     if (!p || !hb || !n_hits_out) { af_set_error("af_pipeline_run: null argument"); return AF_ERR_ARG; }
     for (int g = 0; g < n_genes; g++) if (hits_cap[g] > 0 && !h_hits[g]) { af_set_error("af_pipeline_run: null hit buffer"); return AF_ERR_ARG; }
     if (hb->max_read_len != p->max_read_len) { af_set_error("af_pipeline_run: batch max_read_len %d, pipeline built for %d", hb->max_read_len, p->max_read_len); return AF_ERR_ARG; }
@@ -210,9 +281,19 @@ static int pipeline_run_impl(af_pipeline_t *p, int n_genes, const af_dev_index_t
         const int64_t tiles = (n + 31) / 32;
         s.first_pair = first;
         s.n_pairs = n;
-        AF_CUDA(cudaMemcpyAsync(s.d_packed, (const char *)hb->packed + (size_t)(first / 32) * tile_bytes,
-                                (size_t)tiles * tile_bytes, cudaMemcpyHostToDevice, s.st));
-        p->h2d_bytes += (long long)((size_t)tiles * tile_bytes);
+        if (wire) {                                  // 4 L bits per pair cross the link; the tiles are rebuilt here
+            const size_t wtile = (size_t)((4 * hb->max_read_len + 31) / 32) * 128;
+            if (!s.d_wire) AF_CUDA(cudaMalloc(&s.d_wire, (size_t)(p->slot_pairs / 32) * wtile));
+            AF_CUDA(cudaMemcpyAsync(s.d_wire, (const char *)hb->packed + (size_t)(first / 32) * wtile, (size_t)tiles * wtile,
+                                    cudaMemcpyHostToDevice, s.st));
+            p->h2d_bytes += (long long)((size_t)tiles * wtile);
+            rc = wire_expand_launch(s.d_wire, hb->max_read_len, n, pad_byte, s.d_packed, s.st);
+            if (rc) return rc;
+        } else {
+            AF_CUDA(cudaMemcpyAsync(s.d_packed, (const char *)hb->packed + (size_t)(first / 32) * tile_bytes,
+                                    (size_t)tiles * tile_bytes, cudaMemcpyHostToDevice, s.st));
+            p->h2d_bytes += (long long)((size_t)tiles * tile_bytes);
+        }
         af_batch_t db;
         db.packed = s.d_packed;
         db.n_pairs = n;

@@ -166,7 +166,7 @@ def fastq_rates(args, index, eng):
         for key, fmt, ext, level in (("bgzf", oracle.FASTQ_BGZF, ".fastq.gz", 1), ("gzip", oracle.FASTQ_GZIP, ".fastq.gz", 1),
                                      ("plain", oracle.FASTQ_PLAIN, ".fastq", 0)):
             p1, p2 = os.path.join(d, key + "_1" + ext), os.path.join(d, key + "_2" + ext)
-            oracle.synth_fastq(spec, 0, n, [p1], [p2], fmt, level, threads=2)
+            oracle.synth_fastq(spec, 0, n, [p1], [p2], fmt, level, threads=max(2, min(8, os.cpu_count() or 2)))
             scan_fastq_pair(index, p1, p2, engine=eng, batch_pairs=1 << 19, threads=args.threads)      # warm-up: staging, page cache
             best = None
             for _ in range(2):
@@ -303,6 +303,8 @@ def main():
     ap.add_argument("--graphs", type=int, default=0, help="1: replay one CUDA graph per slot in the throughput region")
     ap.add_argument("--cand-cap", type=int, default=0, help="candidate capacity per batch (default 2 x pairs: every read)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="iterations of the host-buffer end-to-end region (0: --steps, at most 50)")
+    ap.add_argument("--e2e-format", choices=["wire", "tiles"], default="wire",
+                    help="host buffers of the end-to-end region: the wire format (76 B per 2x150 pair, expanded on the GPU) or whole tiles (80 B)")
     ap.add_argument("--cpu-pairs", type=int, default=10_000_000, help="bounded sample for cpu_baseline")
     ap.add_argument("--ref-pairs", type=int, default=10_000_000, help="pairs per step of the reference arm")
     ap.add_argument("--parity-pairs", type=int, default=1_000_000, help="pairs per rank compared with the oracle after the clock (0: skip)")
@@ -312,7 +314,7 @@ def main():
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N > 1: how the ranks' hit lists reach every rank -- p2p: the hit-compaction kernel stores them "
                          "into every GPU's log over NVLink peer memory; nccl: one all-gather per step")
-    ap.add_argument("--fastq-pairs", type=int, default=1_000_000, help="pairs of the FASTQ end-to-end samples (0: skip)")
+    ap.add_argument("--fastq-pairs", type=int, default=4_000_000, help="pairs of the FASTQ end-to-end samples (0: skip)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -592,22 +594,40 @@ def main():
         hptr = L.af_host_alloc(lay.packed_bytes)
         host_packed = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint32)), (lay.packed_bytes // 4,))
         host_packed[:] = batch.packed.cpu().numpy().view(np.uint32)
-        hb = af.PackedBatch(host_packed, n, args.read_len, args.read_len)
+        wire = args.e2e_format == "wire"
+        h2d_bytes = int(lay.packed_bytes)
+        wptr = None
+        if wire:
+            # the library's wire format: 4 L bits per pair (76 bytes for 2 x 150 bp) instead of whole tiles (80); the
+            # conversion is input preparation, outside the clock -- a packer would write this format directly
+            h2d_bytes = int(af.wire_bytes(args.read_len, n))
+            wptr = L.af_host_alloc(h2d_bytes)
+            host_wire = np.ctypeslib.as_array(ctypes.cast(wptr, ctypes.POINTER(ctypes.c_uint32)), (h2d_bytes // 4,))
+            af.wire_from_packed(host_packed, args.read_len, n, out=host_wire)
+            src_words = host_wire
+        else:
+            src_words = host_packed
+        hb = af.PackedBatch(src_words, n, args.read_len, args.read_len)
         hits_out = np.zeros(max(1 << 20, n // 16), dtype=af.HIT_DTYPE)
         for _ in range(3):
-            eng.anchor_host(hb, hits_out=hits_out)              # warm-up (allocates the slots)
+            eng.anchor_host(hb, hits_out=hits_out, wire=wire)              # warm-up (allocates the slots)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            h, st = eng.anchor_host(hb, hits_out=hits_out)
+            h, st = eng.anchor_host(hb, hits_out=hits_out, wire=wire)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / e2e_steps
+        if args.parity_pairs and wire:                          # the wire path delivers what the resident path delivers
+            ref_hits, _ = eng.anchor(batch)
+            if not (len(ref_hits) == len(h) and ref_hits.tobytes() == np.ascontiguousarray(h).tobytes()):
+                print("bench: the wire-format pipeline and the resident path disagree", file=sys.stderr)
+                sys.exit(3)
         # the ceiling the fabric in front of the GPUs sets for this: the same tiles through cudaMemcpyAsync alone,
         # all ranks copying at once
         h2d_stream = torch.cuda.Stream(device=dev)
-        pinned_view = torch.empty(host_packed.shape, dtype=torch.int32, pin_memory=True)
-        pinned_view.numpy()[:] = host_packed.view(np.int32)
-        dst = torch.empty_like(batch.packed)
+        pinned_view = torch.empty(src_words.shape, dtype=torch.int32, pin_memory=True)
+        pinned_view.numpy()[:] = src_words.view(np.int32)
+        dst = torch.empty(src_words.shape, dtype=torch.int32, device=dev)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(h2d_stream):
             dst.copy_(pinned_view, non_blocking=True)
@@ -623,18 +643,23 @@ def main():
             t = torch.tensor([dt, copy_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt, copy_ms = float(t[0].item()), float(t[1].item())
-        e2e = {"value": world * n / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(lay.packed_bytes),
+        e2e = {"value": world * n / dt, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": int(len(h) * 16 + 32 * ((n + (1 << 20) - 1) >> 20)), "ms_per_step": dt * 1e3,
                "steps": e2e_steps,
-               "path": "af_pipeline_run: pinned host tiles -> cudaMemcpyAsync -> kernels -> hit list on host",
+               "path": ("af_pipeline_run_wire: pinned host batch in wire format (4 L bits per pair) -> cudaMemcpyAsync -> expansion "
+                        "into tiles on the GPU -> kernels -> hit list on host") if wire else
+                       "af_pipeline_run: pinned host tiles -> cudaMemcpyAsync -> kernels -> hit list on host",
+               "format": args.e2e_format,
                "h2d_only_ceiling": {"ms_per_step": copy_ms, "pairs_per_s": world * n / (copy_ms * 1e-3),
-                                    "gb_per_s_all_ranks": world * lay.packed_bytes / (copy_ms * 1e-3) / 1e9,
-                                    "what": "the same %d MB of tiles per rank through cudaMemcpyAsync alone, all %d rank(s) at once, max over ranks"
-                                            % (lay.packed_bytes // 1_000_000, world)},
+                                    "gb_per_s_all_ranks": world * h2d_bytes / (copy_ms * 1e-3) / 1e9,
+                                    "what": "the same %d MB per rank through cudaMemcpyAsync alone, all %d rank(s) at once, max over ranks"
+                                            % (h2d_bytes // 1_000_000, world)},
                "host_cpus_rank0": ("%d CPUs local to the GPU (NVML affinity)" % len(cpus)) if cpus else "unbound"}
         del dst, pinned_view
         eng.close_pipeline()
         L.af_host_free(hptr)
+        if wptr:
+            L.af_host_free(wptr)
 
     # third rate: FASTQ files on disk -> reader -> packer -> pipeline -> records
     fastq = None

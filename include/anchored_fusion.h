@@ -229,6 +229,21 @@ int af_pipeline_run(af_pipeline_t *p, const af_batch_t *host_batch, af_hit_t *h_
 int af_pipeline_run_multi(af_pipeline_t *p, int32_t n_indexes, const af_dev_index_t *const *indexes,
                           const af_batch_t *host_batch, af_hit_t *const *h_hits, const int64_t *hits_cap,
                           int64_t *n_hits_out, int64_t *n_flagged_out);
+/* Wire format: the same batch without the padding of the tile layout -- per pair 4 * max_read_len bits (mate 1's
+ * bases then mate 2's, 2 bit/base) rounded up to whole 32-bit words, e.g. 19 words = 76 bytes for 2 x 150 bp where a
+ * tile spends 80; word w of pair (tile*32 + lane) at ((tile * NW + w) * 32 + lane) * 4 bytes.  It is what crosses PCIe
+ * in af_pipeline_run_wire: each chunk is expanded into tiles on the device (k_wire_expand) before the kernels run, so
+ * the host->device traffic is the algorithmic 76 bytes per pair.  Lengths and N lists travel as in af_batch_t. */
+int64_t af_wire_bytes(int32_t max_read_len, int64_t n_pairs);
+/* host conversions (whole tiles: the pad lanes of the last tile are carried along); to_packed is the host twin of the
+ * device expansion and restores the pad pattern past max_read_len */
+int af_wire_from_packed(const void *packed, int32_t max_read_len, int64_t n_pairs, void *wire_out);
+int af_wire_to_packed(const void *wire, int32_t max_read_len, int64_t n_pairs, int32_t pad_byte, void *packed_out);
+/* device expansion alone (both pointers in device memory), stream-ordered */
+int af_wire_expand_device(const void *d_wire, int32_t max_read_len, int64_t n_pairs, int32_t pad_byte, void *d_packed, void *stream);
+/* af_pipeline_run with host_batch->packed in wire format; pad_byte = the index's pad pattern (af_index_info) */
+int af_pipeline_run_wire(af_pipeline_t *p, const af_batch_t *host_batch, int32_t pad_byte, af_hit_t *h_hits, int64_t hits_cap,
+                         int64_t *n_hits_out, int64_t *n_flagged_out);
 int64_t af_pipeline_launches(const af_pipeline_t *p); /* kernels launched so far */
 int64_t af_pipeline_h2d_bytes(const af_pipeline_t *p); /* bytes copied host -> device so far */
 void *af_host_alloc(size_t bytes);                    /* cudaHostAlloc (pinned) */

@@ -112,11 +112,96 @@ static int write_one(const af_synth_t *s, int64_t first_pair, int64_t n, int mat
     return (fclose(fh) == 0 && ok) ? 0 : -1;
 }
 
+// One large file written by many threads: the pair range is cut into chunks, every chunk's text is generated and
+// compressed on its own (BGZF blocks are independent anyway; for a single gzip member every chunk is a raw deflate
+// stream closed with a sync flush -- an empty stored block on a byte boundary -- and the last one with Z_FINISH, which
+// concatenate into ONE valid deflate stream, the way pigz writes them), then the pieces are written in order.
+static int write_one_chunked(const af_synth_t *s, int64_t first_pair, int64_t n, int mate, const char *path, int format, int level, int threads) {
+    const int64_t CH = 1 << 16;
+    const int64_t n_chunks = std::max<int64_t>(1, (n + CH - 1) / CH);
+    std::vector<std::string> pieces((size_t)n_chunks);
+    std::vector<uint32_t> crcs((size_t)n_chunks, 0);
+    std::vector<size_t> lens((size_t)n_chunks, 0);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1) reduction(+ : bad)
+    for (int64_t c = 0; c < n_chunks; c++) {
+        std::string t;
+        const int64_t p0 = c * CH, cnt = std::min<int64_t>(CH, n - p0);
+        fastq_text(s, first_pair + p0, cnt > 0 ? cnt : 0, mate, t);
+        std::string &out = pieces[(size_t)c];
+        if (format == 0) { out.swap(t); continue; }
+        if (format == 2) {                                   // BGZF blocks of this chunk (no EOF block)
+            std::vector<unsigned char> comp(70000);
+            for (size_t i = 0; i < t.size(); i += 0xFF00) {
+                const size_t m = std::min<size_t>(0xFF00, t.size() - i);
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad++; break; }
+                zs.next_in = (Bytef *)t.data() + i; zs.avail_in = (uInt)m;
+                zs.next_out = comp.data(); zs.avail_out = (uInt)comp.size();
+                deflate(&zs, Z_FINISH);
+                const unsigned clen = (unsigned)zs.total_out, bsize = clen + 25;
+                deflateEnd(&zs);
+                const unsigned char hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (unsigned char)(bsize & 255), (unsigned char)(bsize >> 8)};
+                const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)t.data() + i, (uInt)m), isz = (uint32_t)m;
+                unsigned char tail[8];
+                for (int k = 0; k < 4; k++) { tail[k] = (unsigned char)(crc >> (8 * k)); tail[4 + k] = (unsigned char)(isz >> (8 * k)); }
+                out.append((const char *)hdr, 18); out.append((const char *)comp.data(), clen); out.append((const char *)tail, 8);
+            }
+            continue;
+        }
+        // format 1: a piece of one raw deflate stream
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad++; continue; }
+        out.resize(deflateBound(&zs, (uLong)t.size()) + 64);
+        zs.next_in = (Bytef *)t.data(); zs.avail_in = (uInt)t.size();
+        zs.next_out = (Bytef *)&out[0]; zs.avail_out = (uInt)out.size();
+        const int rc = deflate(&zs, c + 1 == n_chunks ? Z_FINISH : Z_SYNC_FLUSH);
+        if ((c + 1 == n_chunks && rc != Z_STREAM_END) || (c + 1 != n_chunks && (rc != Z_OK || zs.avail_in))) bad++;
+        out.resize(zs.total_out);
+        deflateEnd(&zs);
+        crcs[(size_t)c] = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)t.data(), (uInt)t.size());
+        lens[(size_t)c] = t.size();
+    }
+    if (bad) return -1;
+    FILE *fh = fopen(path, "wb");
+    if (!fh) return -1;
+    bool ok = true;
+    if (format == 1) {
+        const unsigned char hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3};
+        ok = fwrite(hdr, 1, 10, fh) == 10;
+    }
+    uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
+    uint64_t total = 0;
+    for (int64_t c = 0; c < n_chunks && ok; c++) {
+        ok = fwrite(pieces[(size_t)c].data(), 1, pieces[(size_t)c].size(), fh) == pieces[(size_t)c].size();
+        if (format == 1) { crc = (uint32_t)crc32_combine(crc, crcs[(size_t)c], (z_off_t)lens[(size_t)c]); total += lens[(size_t)c]; }
+    }
+    if (ok && format == 1) {
+        unsigned char tail[8];
+        for (int k = 0; k < 4; k++) { tail[k] = (unsigned char)(crc >> (8 * k)); tail[4 + k] = (unsigned char)((uint32_t)total >> (8 * k)); }
+        ok = fwrite(tail, 1, 8, fh) == 8;
+    }
+    if (ok && format == 2) {
+        static const unsigned char eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        ok = fwrite(eof, 1, 28, fh) == 28;
+    }
+    return (fclose(fh) == 0 && ok) ? 0 : -1;
+}
+
 // n_files file pairs, file i holding pairs [first_pair + i * pairs_per_file, ... + pairs_per_file); paths1[i] / paths2[i]
 extern "C" int afo_synth_fastq(const af_synth_t *s, int64_t first_pair, int64_t pairs_per_file, int32_t n_files,
                                const char *const *paths1, const char *const *paths2, int32_t format, int32_t level, int threads) {
     if (!s || !paths1 || !paths2 || n_files <= 0 || pairs_per_file < 0) return -1;
     int bad = 0;
+    if (2 * n_files < threads && pairs_per_file > (1 << 16)) {          // few large files: the threads share each file
+        for (int k = 0; k < 2 * n_files; k++) {
+            const int i = k >> 1, mate = k & 1;
+            if (write_one_chunked(s, first_pair + (int64_t)i * pairs_per_file, pairs_per_file, mate, mate ? paths2[i] : paths1[i], format, level, threads)) bad++;
+        }
+        return bad ? -1 : 0;
+    }
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1) reduction(+ : bad)
     for (int k = 0; k < 2 * n_files; k++) {
         const int i = k >> 1, mate = k & 1;

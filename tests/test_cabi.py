@@ -174,3 +174,19 @@ def test_host_synth_is_deterministic_and_plants_the_anchor():
     hits = oracle.anchor_reads(anchor, reads)
     assert len(set(hits["read_id"] >> 1)) >= 0.15 * 500       # ~20 % fusion fragments + natural overlap
     assert ((hits["clip_l"] > 0) | (hits["clip_r"] > 0)).sum() > 20   # junction reads are soft-clipped
+
+
+def test_wire_format_round_trip_on_the_host():
+    """tiles -> wire (4 L bits per pair, no padding) -> tiles is the identity, for ragged reads with N at every word edge."""
+    import anchored_fusion_b200 as af
+    rng = np.random.default_rng(0)
+    for L, n in ((150, 70), (36, 33), (101, 1), (250, 64), (256, 5), (16, 40), (17, 31), (1, 3), (32, 32)):
+        lens = rng.integers(max(1, L - 20), L + 1, (2, n))
+        lens[0, 0] = L
+        seqs = [["".join("ACGTN"[c] for c in rng.choice(5, int(l), p=[.245, .245, .245, .245, .02])) for l in row] for row in lens]
+        b = af.pack_pairs(seqs[0], seqs[1], max_read_len=L, pad_byte=0x6C)
+        tiles = np.asarray(b.packed).view(np.uint32)
+        wire = af.wire_from_packed(tiles, L, n)
+        assert wire.nbytes == af.wire_bytes(L, n) == ((n + 31) // 32) * ((4 * L + 31) // 32) * 128
+        assert np.array_equal(af.wire_to_packed(wire, L, n, 0x6C), tiles), (L, n)
+    assert af.wire_bytes(150, 10_000_000) == 760_000_000          # the algorithmic 76 bytes per 2 x 150 bp pair
