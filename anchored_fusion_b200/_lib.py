@@ -118,6 +118,7 @@ SIGNATURES = {
     "af_host_free": (None, [c_vp]),
     "af_genome_from_fasta": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, P(c_vp)]),
     "af_genome_from_contigs": (ctypes.c_int, [P(ctypes.c_char_p), P(ctypes.c_char_p), P(c_i64), c_i32, ctypes.c_int, P(c_vp)]),
+    "af_debug_genome_fasta": (ctypes.c_int, [ctypes.c_char_p, P(c_i64), P(c_i32), P(ctypes.c_uint64)]),
     "af_genome_synth": (ctypes.c_int, [ctypes.c_uint64, c_i64, ctypes.c_int, P(c_vp)]),
     "af_genome_free": (None, [c_vp]),
     "af_genome_length": (c_i64, [c_vp]),

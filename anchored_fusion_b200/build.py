@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libafb200.so")
-SOURCES = ["af_host.cpp", "af_fastq.cpp", "af_kernels.cu", "af_tail.cu", "af_pipeline.cu", "af_exchange.cu", "af_genome.cu"]
+SOURCES = ["af_host.cpp", "af_fastq.cpp", "af_kernels.cu", "af_tail.cu", "af_pipeline.cu", "af_exchange.cu", "af_genome.cu", "af_genome_host.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-cudart", "static"]
 

@@ -236,6 +236,17 @@ struct af_index {
 void af_filter_pick(const std::vector<uint32_t> &keys, uint32_t kmask, uint32_t nbk, int n_muls, int log2_probes,
                     uint32_t &mul_out, std::vector<uint32_t> &filt_out, int32_t *ov_out);
 
+// the genome pass's input on the host (af_genome_host.cpp): the concatenation, 2 bit/base (an N is stored as a
+// position-hashed pseudo-random base) + 1 bit/base N map, and the contigs' places in it
+struct af_genome_host {
+    std::vector<uint32_t> pk, nm;
+    int64_t n = 0;
+    std::vector<std::string> names;
+    std::vector<int64_t> starts, lens;
+};
+int af_genome_host_from_fasta(const char *path, af_genome_host &out);
+int af_genome_host_from_contigs(const char *const *names, const char *const *seqs, const int64_t *lens, int32_t n, af_genome_host &out);
+
 static inline uint8_t af_code_of(char c) {
     switch (c) {
         case 'A': case 'a': return 0;

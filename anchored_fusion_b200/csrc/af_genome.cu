@@ -18,8 +18,6 @@
 //   k_genome_finish  1 warp per read: the winning diagonal once more -> record
 // The genome is ONE sequence, contigs joined by 256 N (af_genome_from_*): an N never matches, a read cannot
 // span two contigs, and no diagonal that holds a seed leaves the sequence, so the kernels need no bounds.
-#include <zlib.h>
-
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -59,112 +57,22 @@ struct af_genome {
     af_genome_hit_t *d_recs = nullptr; int64_t q_cap = 0;
 };
 
-// ---- host side: concatenation and 2-bit packing ------------------------------------------------
-// an N is stored as a position-dependent pseudo-random base (and a set bit in the N bitmap), so the long N runs
-// of an assembly look like random sequence to the filter instead of 150 M copies of one 12-mer
-static inline uint32_t n_word(int64_t word_index) { return af_mix32((uint32_t)word_index * 0x9E3779B1u + 0x5BD1E995u); }
-
-struct GenomeBuilder {
-    std::vector<uint32_t> pk, nm;
-    int64_t n = 0;
-    uint8_t lut[256];
-    GenomeBuilder() {
-        for (int c = 0; c < 256; c++) lut[c] = af_code_of((char)c);
-        lut[(int)' '] = lut[(int)'\t'] = lut[(int)'\r'] = lut[(int)'\n'] = 5;   // skipped
-    }
-    void room(int64_t more) {
-        const size_t w = (size_t)((n + more + 15) >> 4) + 1, b = (size_t)((n + more + 31) >> 5) + 1;
-        if (pk.size() < w) { if (pk.capacity() < w) pk.reserve(w + w / 2); pk.resize(w, 0u); }
-        if (nm.size() < b) { if (nm.capacity() < b) nm.reserve(b + b / 2); nm.resize(b, 0u); }
-    }
-    inline void put(uint32_t c) {
-        const int64_t x = n++;
-        if (c == 4) { nm[(size_t)(x >> 5)] |= 1u << (x & 31); c = (n_word(x >> 4) >> (2 * (x & 15))) & 3u; }
-        pk[(size_t)(x >> 4)] |= c << (2 * (x & 15));
-    }
-    void push_n(int64_t count) { room(count); for (int64_t i = 0; i < count; i++) put(4); }
-    void push(const char *s, int64_t len) {
-        room(len);
-        for (int64_t i = 0; i < len; i++) { const uint32_t c = lut[(uint8_t)s[i]]; if (c != 5) put(c); }
-    }
-};
-
-static int genome_upload(GenomeBuilder &b, std::vector<std::string> &names, std::vector<int64_t> &starts, std::vector<int64_t> &lens,
-                         int device, af_genome_t **out);
-
-struct ContigList {
-    GenomeBuilder b;
-    std::vector<std::string> names;
-    std::vector<int64_t> starts, lens;
-    void begin(const std::string &name) {
-        if (names.empty()) b.push_n(AF_GENOME_SEP);
-        names.push_back(name); starts.push_back(b.n); lens.push_back(0);
-    }
-    void end() { lens.back() = b.n - starts.back(); b.push_n(AF_GENOME_SEP); }
-};
+// ---- host side: concatenation and 2-bit packing live in af_genome_host.cpp (no CUDA: fuzzed under ASan) ---------
+static int genome_upload(af_genome_host &h, int device, af_genome_t **out);
 
 extern "C" int af_genome_from_contigs(const char *const *names, const char *const *seqs, const int64_t *lens, int32_t n, int device,
                                       af_genome_t **out) {
-    if (!names || !seqs || !lens || n <= 0 || !out) { af_set_error("af_genome_from_contigs: bad argument"); return AF_ERR_ARG; }
-    ContigList c;
-    for (int32_t i = 0; i < n; i++) {
-        if (!names[i] || !seqs[i] || lens[i] < 0) { af_set_error("af_genome_from_contigs: contig %d is null", i); return AF_ERR_ARG; }
-        c.begin(names[i]);
-        c.b.push(seqs[i], lens[i]);
-        c.end();
-    }
-    return genome_upload(c.b, c.names, c.starts, c.lens, device, out);
+    if (!out) { af_set_error("af_genome_from_contigs: null"); return AF_ERR_ARG; }
+    af_genome_host h;
+    const int rc = af_genome_host_from_contigs(names, seqs, lens, n, h);
+    return rc ? rc : genome_upload(h, device, out);
 }
 
 extern "C" int af_genome_from_fasta(const char *path, int device, af_genome_t **out) {
-    if (!path || !out) { af_set_error("af_genome_from_fasta: null"); return AF_ERR_ARG; }
-    gzFile f = gzopen(path, "rb");
-    if (!f) { af_set_error("af_genome_from_fasta: cannot open %s", path); return AF_ERR_IO; }
-    gzbuffer(f, 1 << 20);
-    ContigList c;
-    std::vector<char> buf((size_t)4 << 20);
-    bool in_header = false, line_start = true, name_done = false, open = false;
-    std::string name;
-    int n;
-    while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) {
-        const char *p = buf.data(), *e = p + n;
-        while (p < e) {
-            if (in_header) {
-                const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
-                const char *stop = nl ? nl : e;
-                for (const char *q = p; q < stop && !name_done; q++) {
-                    if (*q == ' ' || *q == '\t' || *q == '\r') name_done = true; else name.push_back(*q);
-                }
-                if (nl) { in_header = false; line_start = true; c.begin(name); open = true; p = nl + 1; } else p = e;
-                continue;
-            }
-            if (line_start && *p == '>') {
-                if (open) { c.end(); open = false; }
-                in_header = true; name.clear(); name_done = false; line_start = false; p++;
-                continue;
-            }
-            const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
-            const char *stop = nl ? nl : e;
-            if (stop > p) {
-                if (!open) { gzclose(f); af_set_error("af_genome_from_fasta: %s does not start with a '>' header", path); return AF_ERR_IO; }
-                c.b.push(p, stop - p);
-            }
-            line_start = nl != nullptr;
-            p = nl ? nl + 1 : e;
-        }
-    }
-    int zerr = 0;
-    const char *zmsg = gzerror(f, &zerr);
-    if (n < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) {
-        af_set_error("af_genome_from_fasta: %s: %s", path, zmsg ? zmsg : "read error");
-        gzclose(f);
-        return AF_ERR_IO;
-    }
-    gzclose(f);
-    if (in_header) { c.begin(name); open = true; }
-    if (open) c.end();
-    if (c.names.empty()) { af_set_error("af_genome_from_fasta: %s holds no sequence", path); return AF_ERR_IO; }
-    return genome_upload(c.b, c.names, c.starts, c.lens, device, out);
+    if (!out) { af_set_error("af_genome_from_fasta: null"); return AF_ERR_ARG; }
+    af_genome_host h;
+    const int rc = af_genome_host_from_fasta(path, h);
+    return rc ? rc : genome_upload(h, device, out);
 }
 
 static int genome_device(int device, int *num_sms) {
@@ -193,23 +101,21 @@ static int genome_alloc(af_genome *g) {
     return AF_OK;
 }
 
-static int genome_upload(GenomeBuilder &b, std::vector<std::string> &names, std::vector<int64_t> &starts, std::vector<int64_t> &lens,
-                         int device, af_genome_t **out) {
-    if (b.n >= ((int64_t)1 << 35)) { af_set_error("af_genome: %lld bases; the candidate list indexes at most 2^35", (long long)b.n); return AF_ERR_ARG; }
+static int genome_upload(af_genome_host &h, int device, af_genome_t **out) {
+    if (h.n >= ((int64_t)1 << 35)) { af_set_error("af_genome: %lld bases; the candidate list indexes at most 2^35", (long long)h.n); return AF_ERR_ARG; }
     af_genome *g = new af_genome();
     int rc = genome_device(device, &g->num_sms);
-    if (rc == AF_OK) { g->device = device; g->G = b.n; rc = genome_alloc(g); }
+    if (rc == AF_OK) { g->device = device; g->G = h.n; rc = genome_alloc(g); }
     if (rc == AF_OK) {
-        cudaError_t e = cudaMemcpy(g->d_pk, b.pk.data(), (size_t)((b.n + 15) >> 4) * 4, cudaMemcpyHostToDevice);
+        cudaError_t e = cudaMemcpy(g->d_pk, h.pk.data(), (size_t)((h.n + 15) >> 4) * 4, cudaMemcpyHostToDevice);
         // whole N words of the stream; the partial last word keeps the 1 bits past G
-        std::vector<uint32_t> &nm = b.nm;
-        const size_t nw = (size_t)((b.n + 31) >> 5);
-        if (b.n & 31) nm[nw - 1] |= ~0u << (b.n & 31);
-        if (e == cudaSuccess) e = cudaMemcpy(g->d_nm, nm.data(), nw * 4, cudaMemcpyHostToDevice);
+        const size_t nw = (size_t)((h.n + 31) >> 5);
+        if (h.n & 31) h.nm[nw - 1] |= ~0u << (h.n & 31);
+        if (e == cudaSuccess) e = cudaMemcpy(g->d_nm, h.nm.data(), nw * 4, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { af_set_error("af_genome: upload: %s", cudaGetErrorString(e)); rc = AF_ERR_CUDA; }
     }
     if (rc != AF_OK) { af_genome_free(g); return rc; }
-    g->names.swap(names); g->starts.swap(starts); g->lens.swap(lens);
+    g->names.swap(h.names); g->starts.swap(h.starts); g->lens.swap(h.lens);
     *out = g;
     return AF_OK;
 }

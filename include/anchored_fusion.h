@@ -319,6 +319,9 @@ int af_genome_from_fasta(const char *path, int device, af_genome_t **out);
 /* n contigs given as ASCII strings (ACGT any case; anything else is N) */
 int af_genome_from_contigs(const char *const *names, const char *const *seqs, const int64_t *lens, int32_t n, int device,
                            af_genome_t **out);
+/* test hook: the host half of af_genome_from_fasta alone (parse + pack, no GPU): length of the concatenation, number of
+ * contigs and an FNV-1a checksum over the base codes 0..4 of the concatenation */
+int af_debug_genome_fasta(const char *path, int64_t *total_len, int32_t *n_contigs, uint64_t *checksum);
 /* measurement input: one contig "synth" whose base x is af_synth's random reference base f(seed, x), generated on the device */
 int af_genome_synth(uint64_t seed, int64_t len, int device, af_genome_t **out);
 void af_genome_free(af_genome_t *g);

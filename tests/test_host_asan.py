@@ -18,7 +18,7 @@ def test_host_code_is_clean_under_asan_and_ubsan(tmp_path):
     # streamed-gzip and plain-text paths of the reader all run on the small fuzz files
     cmd = ["g++", "-std=c++17", "-g", "-O1", "-DAF_FASTQ_TEST_SIZES", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
            "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "fuzz_host.cpp"),
-           os.path.join(csrc, "af_host.cpp"), os.path.join(csrc, "af_fastq.cpp"), "-o", exe, "-lz", "-lpthread"]
+           os.path.join(csrc, "af_host.cpp"), os.path.join(csrc, "af_fastq.cpp"), os.path.join(csrc, "af_genome_host.cpp"), "-o", exe, "-lz", "-lpthread"]
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)

@@ -2,7 +2,8 @@
 // FASTQ reader), which parses files it did not write.  compute-sanitizer is closed on the GPU pool, so
 // this covers the part of the code that can be sanitised here.  Built and run by tests/test_host_asan.py:
 //   g++ -std=c++17 -g -O1 -fsanitize=address,undefined -fno-sanitize-recover=undefined -Iinclude \
-//       tools/fuzz_host.cpp anchored_fusion_b200/csrc/af_host.cpp anchored_fusion_b200/csrc/af_fastq.cpp -lz -lpthread
+//       tools/fuzz_host.cpp anchored_fusion_b200/csrc/af_host.cpp anchored_fusion_b200/csrc/af_fastq.cpp \
+//       anchored_fusion_b200/csrc/af_genome_host.cpp -lz -lpthread
 // (af_fastq.cpp pulls in af_inflate.h, the DEFLATE decoder: damaged gzip / BGZF bytes go through it)
 //   ./a.out <scratch dir> <iterations> <seed>
 #include <zlib.h>
@@ -118,6 +119,34 @@ int main(int argc, char **argv) {
             af_index_t *idx = nullptr;
             int rc = af_index_build(a.data(), G, nullptr, rnd(0, 1) ? 12 : 13, &idx);
             if (rc == AF_OK) { af_index_info_t info; af_index_info(idx, &info); af_index_free(idx); }
+        }
+        // ---- genome FASTA loader (host half of af_genome_from_fasta) on valid and damaged files ----
+        {
+            const int nc = rnd(0, 6);
+            const bool crlf_fa = !rnd(0, 3);
+            std::string fa;
+            int64_t want_len = AF_GENOME_SEP;
+            for (int c = 0; c < nc; c++) {
+                fa += ">ctg" + std::to_string(c) + (rnd(0, 2) ? "" : " some description") + (crlf_fa ? "\r\n" : "\n");
+                const int len = rnd(0, 3) ? rnd(0, 3000) : 0, width = rnd(1, 120);
+                for (int i = 0; i < len; i++) {
+                    fa += "ACGTNacgtnRYKM*-"[rnd(0, 15)];
+                    if ((i + 1) % width == 0 || i + 1 == len) fa += crlf_fa ? "\r\n" : "\n";
+                }
+                want_len += len + AF_GENOME_SEP;
+            }
+            bool intact = true;
+            if (!rnd(0, 2)) { mutate(fa); intact = false; }
+            if (rnd(0, 1)) { fa = encode(fa, rnd(1, 2)); if (!rnd(0, 2)) { mutate(fa); intact = false; } }
+            const std::string pf = dir + "/g.fa";
+            write_file(pf, fa);
+            int64_t total = 0; int32_t ncon = 0; uint64_t sum = 0;
+            const int rc = af_debug_genome_fasta(pf.c_str(), &total, &ncon, &sum);
+            if (intact && nc > 0 && (rc != AF_OK || ncon != nc || total != want_len)) {
+                fprintf(stderr, "fuzz_host: FASTA of %d contigs / %lld bases came back as rc %d, %d contigs, %lld bases (iteration %d)\n",
+                        nc, (long long)want_len, rc, ncon, (long long)total, it);
+                return 1;
+            }
         }
         // ---- FASTQ reader on valid and damaged files ----
         const int n = rnd(0, 400);
