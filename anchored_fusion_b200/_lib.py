@@ -64,6 +64,7 @@ SIGNATURES = {
     "af_index_build": (ctypes.c_int, [ctypes.c_char_p, c_i64, P(Params), c_i32, P(c_vp)]),
     "af_index_free": (None, [c_vp]),
     "af_index_info": (ctypes.c_int, [c_vp, P(IndexInfo)]),
+    "af_index_filter_kind": (ctypes.c_int, [c_vp]),
     "af_index_filter": (c_vp, [c_vp]),
     "af_index_table": (c_vp, [c_vp]),
     "af_index_upload": (ctypes.c_int, [c_vp, ctypes.c_int, P(c_vp)]),

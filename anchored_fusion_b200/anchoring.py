@@ -46,6 +46,11 @@ class AnchorIndex:
     def pad_byte(self):
         return self.info.pad_byte
 
+    @property
+    def bloom(self):
+        """True when the filter words hold Bloom bits (long anchor) instead of fingerprint buckets."""
+        return bool(lib().af_index_filter_kind(self._h))
+
     def filter_words(self):
         p = lib().af_index_filter(self._h)
         return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)), (self.info.n_buckets,)).copy()

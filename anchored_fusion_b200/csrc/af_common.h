@@ -75,6 +75,20 @@ AF_HD uint32_t af_filter_probe(uint32_t key, const uint32_t *filt, uint32_t fmul
     return (v - AF_F_ONES) & ~v;                                             // & AF_F_HIGH != 0  <=>  hit
 }
 
+// Blocked-Bloom variant of the same filter, for anchors whose k'-mers overflow the 3-slot buckets (beyond ~12 kb the
+// buckets turn "always hit" one by one and the scan flags most reads): a bucket word is 32 Bloom bits, a key sets three
+// of them, chosen by bits 1..15 of the same product that picks the bucket.  No overflow state, so the false-positive
+// rate degrades smoothly (40 kb anchor: ~0.3 % per probe against "always hit" in most buckets).  Three more integer
+// instructions per probe than the fingerprint test, which is why the fingerprint buckets stay the default for anchors
+// they can hold.  Returns AF_F_HIGH on a hit so that the callers' accumulate-and-test is the same.
+AF_HD uint32_t af_bloom_mask(uint32_t lo) {
+    return (1u << ((lo >> 1) & 31u)) | (1u << ((lo >> 6) & 31u)) | (1u << ((lo >> 11) & 31u));
+}
+AF_HD uint32_t af_bloom_probe(uint32_t key, const uint32_t *filt, uint32_t fmul, uint32_t nb) {
+    const uint32_t lo = key * fmul;
+    return (~filt[af_umulhi(lo, nb)] & af_bloom_mask(lo)) ? 0u : AF_F_HIGH;
+}
+
 // The rarely taken second look at a sample that passed the filter (compile-time position P):
 // a true >= k match [q, q+k) around the sample also holds the k'-mer at P-H or the one at P+H,
 // H = ceil((k-k')/2) -- left slack a = P-q and right slack b add up to k-k', so a >= H or b >= H.
@@ -90,12 +104,13 @@ AF_HD bool af_neighbour_ok(const uint32_t (&w)[NW], const uint32_t *filt, uint32
     return ok;
 }
 
-template <int W, int KP, int OFF, int J, int NP, int NPMIN, bool REFINE, int NW>
+template <int W, int KP, int OFF, int J, int NP, int NPMIN, bool REFINE, bool BLOOM, int NW>
 AF_HD void af_scan_sample(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
                           uint32_t &acc) {
     if constexpr (J < NP) {
         constexpr int S = 20 - KP;
-        uint32_t t = af_filter_probe(af_kmer_at<W, KP, OFF, J * S>(w), filt, fmul, nb);
+        uint32_t t = BLOOM ? af_bloom_probe(af_kmer_at<W, KP, OFF, J * S>(w), filt, fmul, nb)
+                           : af_filter_probe(af_kmer_at<W, KP, OFF, J * S>(w), filt, fmul, nb);
         if (J >= NPMIN) t = J < nprobe ? t : 0u;
         if constexpr (REFINE) {
             if (t & AF_F_HIGH) {                                             // rare: ~0.14 % of the samples
@@ -103,7 +118,7 @@ AF_HD void af_scan_sample(const uint32_t (&w)[NW], int nprobe, const uint32_t *f
             }
         }
         acc |= t;
-        af_scan_sample<W, KP, OFF, J + 1, NP, NPMIN, REFINE>(w, nprobe, filt, fmul, nb, acc);
+        af_scan_sample<W, KP, OFF, J + 1, NP, NPMIN, REFINE, BLOOM>(w, nprobe, filt, fmul, nb, acc);
     }
 }
 
@@ -114,7 +129,7 @@ AF_HD void af_scan_sample(const uint32_t (&w)[NW], int nprobe, const uint32_t *f
 // chance hits (362 k -> 16 k flagged reads per 10 M pairs) but the rarely taken branch per sample
 // splits the probe sequence into 36 basic blocks and the kernel runs 2x slower (measured), so the
 // production scan uses REFINE = false and leaves the false positives to k_verify.
-template <int W, int KP, int OFF, int NW, bool REFINE = false>
+template <int W, int KP, int OFF, int NW, bool REFINE = false, bool BLOOM = false>
 AF_HD uint32_t af_scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul,
                               uint32_t nb) {
     constexpr int S = 20 - KP;  // k = 19
@@ -122,7 +137,7 @@ AF_HD uint32_t af_scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t 
     constexpr int LMIN = 16 * (W - 1) + 1;                                   // shortest L with this W
     constexpr int NPMIN = LMIN >= KP ? (LMIN - KP) / S + 1 : 0;
     uint32_t acc = 0;
-    af_scan_sample<W, KP, OFF, 0, NP, NPMIN, REFINE>(w, nprobe, filt, fmul, nb, acc);
+    af_scan_sample<W, KP, OFF, 0, NP, NPMIN, REFINE, BLOOM>(w, nprobe, filt, fmul, nb, acc);
     return acc & AF_F_HIGH;
 }
 
@@ -229,6 +244,7 @@ struct af_index {
     std::vector<uint32_t> apk[2];   // anchor, 2 bit/base: [0] forward, [1] reverse complement (N packed as A)
     int32_t anchor_has_n;
     int32_t n_keys, n_entries, n_overflow, pad_byte;
+    int32_t bloom = 0;              // filter holds Bloom bits (long anchor) instead of fingerprint buckets
 };
 
 // shared-memory filter over `keys` (distinct k'-mers) with nbk buckets: tries the first n_muls multipliers and keeps

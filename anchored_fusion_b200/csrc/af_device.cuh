@@ -36,6 +36,7 @@ struct af_dev_index {
     int pad_byte;
     int num_sms;
     bool saturated;      // many filter buckets overflowed (long anchor): flagged reads take the exact k_verify route
+    bool bloom;          // d_filter holds Bloom bits (af_bloom_probe) instead of fingerprint buckets
 };
 
 // ---- candidate stream: seed scan -> tail kernel (af_tail.cu) ---------------------------------

@@ -104,13 +104,13 @@ static const int RQ_CAP = 96;   // per-warp refine queue: up to 31 waiting + the
 // The number of flagged reads per compaction chunk is accumulated in shared memory (cc_local,
 // chunks relative to the CTA's first chunk) and flushed once per CTA: every CTA owns a
 // contiguous tile range, so concurrent CTAs never hammer the same global counter.
-template <int W, int KP, int Q>
+template <int W, int KP, int Q, bool BLOOM = false>
 __device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long tile, long long n_pairs, int lane,
                                           int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
                                           uint2 *__restrict__ flags, uint32_t *cc_local, long long chunk0,
                                           uint32_t *__restrict__ chunk_counts) {
-    uint32_t a1 = af_scan_read<W, KP, 0, 4 * Q>(w, nprobe, filt, fmul, nb);
-    uint32_t a2 = af_scan_read<W, KP, W, 4 * Q>(w, nprobe, filt, fmul, nb);
+    uint32_t a1 = af_scan_read<W, KP, 0, 4 * Q, false, BLOOM>(w, nprobe, filt, fmul, nb);
+    uint32_t a2 = af_scan_read<W, KP, W, 4 * Q, false, BLOOM>(w, nprobe, filt, fmul, nb);
     const uint32_t vm = tile_valid_mask(tile, n_pairs);
     const uint32_t b1 = __ballot_sync(FULL, a1 != 0) & vm, b2 = __ballot_sync(FULL, a2 != 0) & vm;
     if (lane == 0) {
@@ -296,9 +296,10 @@ __device__ __forceinline__ void scan_tile_emit(const uint32_t (&w)[4 * Q], long 
 // PF = false (<= 1024 threads, 64 registers): latency is hidden by occupancy alone.
 // RQ = true: flags[] receives the REFINED flag words (see refine_pass), chunk_counts their per-chunk
 // counts and counts[AF_CNT_FLAGGED] the number of reads that passed the plain filter.
+// BLOOM = true (plain mode only): the filter words are Bloom bits (long anchors, af_bloom_probe).
 // EMIT = true: no flag words at all -- every flagged read goes into the candidate stream (emit_reads) that
 // k_tail consumes; counts[AF_CNT_FLAGGED] receives their number.
-template <int W, int KP, int MAXT, bool PF, bool RQ, bool EMIT = false>
+template <int W, int KP, int MAXT, bool PF, bool RQ, bool EMIT = false, bool BLOOM = false>
 __global__ void __launch_bounds__(MAXT, 1)
 k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pairs, int nprobe,
             const uint32_t *__restrict__ g_filter, uint32_t fmul, uint32_t nb, uint2 *__restrict__ flags,
@@ -323,7 +324,7 @@ k_seed_scan(const uint4 *__restrict__ packed, long long n_tiles, long long n_pai
     auto do_tile = [&](const uint32_t (&w)[4 * Q], long long t) {
         if constexpr (EMIT) scan_tile_emit<W, KP, Q>(w, t, n_tiles, n_pairs, lane, nprobe, filt, fmul, nb, E, S);
         else if constexpr (RQ) scan_tile_rq<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, packed, (uint32_t *)flags, chunk_counts, q, qn, nflag);
-        else scan_tile<W, KP, Q>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
+        else scan_tile<W, KP, Q, BLOOM>(w, t, n_pairs, lane, nprobe, filt, fmul, nb, flags, cc_local, chunk0, chunk_counts);
     };
     if constexpr (PF) {
         uint32_t wa[4 * Q], wb[4 * Q];
@@ -407,18 +408,18 @@ static int scan_grid(const af_dev_index *d, long long n_tiles) {
     return (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
 }
 
-template <int W, int KP, int MAXT, bool PF, bool RQ, bool EMIT>
+template <int W, int KP, int MAXT, bool PF, bool RQ, bool EMIT, bool BLOOM = false>
 static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
                        uint32_t *chunk_counts, uint32_t *counts, const af_emit &E, cudaStream_t st) {
     size_t smem = (size_t)d->nb * 4;
     static bool attr_set[64] = {false};  // per device
     if (!attr_set[d->device & 63]) {
-        int rc = allow_full_smem(k_seed_scan<W, KP, MAXT, PF, RQ, EMIT>, nullptr);  // the filter + a few static words (chunk counters, mbarrier, refine queues)
+        int rc = allow_full_smem(k_seed_scan<W, KP, MAXT, PF, RQ, EMIT, BLOOM>, nullptr);  // the filter + a few static words (chunk counters, mbarrier, refine queues)
         if (rc) return rc;
         attr_set[d->device & 63] = true;
     }
     const int grid = scan_grid(d, n_tiles);
-    k_seed_scan<W, KP, MAXT, PF, RQ, EMIT><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
+    k_seed_scan<W, KP, MAXT, PF, RQ, EMIT, BLOOM><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
                                                                                d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts, counts, E);
     g_launches++;
     AF_CUDA(cudaGetLastError());
@@ -428,6 +429,10 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
 template <int W, int KP>
 static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
                             uint32_t *cc, uint32_t *counts, bool rq, const af_emit *emit, cudaStream_t st) {
+    if (d->bloom) {
+        if (emit || rq) { af_set_error("seed scan: a Bloom-filter index (long anchor) runs the plain scan only"); return AF_ERR_ARG; }
+        return launch_scan<W, KP, AF_SCAN_BOUND, true, false, false, true>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st);
+    }
     if (emit) return launch_scan<W, KP, AF_SCAN_BOUND, true, false, true>(d, b, n_tiles, nprobe, flags, cc, counts, *emit, st);
     if (rq) return launch_scan<W, KP, AF_SCAN_BOUND, true, true, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st);
     return launch_scan<W, KP, AF_SCAN_BOUND, true, false, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st);
@@ -1371,7 +1376,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     const int sg2 = (int)(w.nch2 < (uint32_t)scatter_grid ? w.nch2 : scatter_grid);
     cudaEvent_t ev;
     prof_mark(&ev, st);
-    if (g_fused) {
+    if (g_fused && !d->bloom) {
         // fused: seed scan + verify in one warp-specialised kernel -> seeded flag words
         AF_CUDA(cudaMemsetAsync(flags, 0, (size_t)lay.n_tiles * 8, st));
         rc = fused_impl(d, b, lay, flags, cc1, d_counts, st);
@@ -1410,7 +1415,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     prof_span(ev, st, ST_COMPACT1);
     prof_mark(&ev, st);
     {
-    if (g_verify_smem) {
+    if (g_verify_smem && !d->bloom) {                      // (a Bloom index's half-size fingerprint copy is saturated: k_verify's exact bitmap instead)
         const size_t vsmem = ((size_t)d->nb2 + (size_t)(lay.words_per_read + 3) * 1024) * 4;
         static bool vattr[64][2] = {{false}};
         if (!vattr[d->device & 63][d->kp == 12 ? 0 : 1]) {
@@ -1494,6 +1499,7 @@ extern "C" int af_index_upload(const af_index_t *idx, int device, af_dev_index_t
     d->fmul = idx->fmul; d->nb = idx->nb; d->tmask = idx->tmask; d->pad_byte = idx->pad_byte;
     d->num_sms = prop.multiProcessorCount;
     d->saturated = (long long)idx->n_overflow * 200 > (long long)idx->nb;
+    d->bloom = idx->bloom != 0;
     d->d_filter = nullptr; d->d_table = nullptr; d->d_anchor = nullptr; d->d_member = nullptr;
     d->d_apk[0] = d->d_apk[1] = nullptr;
     d->anchor_has_n = idx->anchor_has_n;

@@ -475,11 +475,11 @@ class GeneAnchorer:
         self.gene = gene_name or name.split()[0]
         self.index = AnchorIndex(self.seq, kp=kp)
         info = self.index.info
-        if info.n_overflow * 200 > info.n_buckets:
-            # the shared-memory filter holds ~3 k'-mers per bucket; past ~12 kb of anchor more and more buckets
-            # overflow into "always hit" and the exact verify stage has to sort out the difference
-            print("[anchoring] %s: anchor of %d bp fills the seed filter (%d of %d buckets overflow); results are "
-                  "unaffected, the scan flags more reads than usual" % (self.gene, len(self.seq), info.n_overflow, info.n_buckets),
+        if self.index.bloom:
+            # the 3-slot fingerprint buckets hold anchors up to ~12 kb; beyond that the same shared memory holds a
+            # blocked Bloom filter: exact results, more reads than usual reach the verify stage
+            print("[anchoring] %s: anchor of %d bp is beyond the fingerprint filter (%d of %d buckets would overflow); "
+                  "using the Bloom filter, results are unaffected" % (self.gene, len(self.seq), info.n_overflow, info.n_buckets),
                   file=sys.stderr)
         self.engine = Anchorer(self.index, resolve_device(gpu_number))
 

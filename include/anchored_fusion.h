@@ -126,6 +126,9 @@ void af_default_params(af_params_t *p);
 int af_index_build(const char *anchor, int64_t len, const af_params_t *params, int32_t kp, af_index_t **out);
 void af_index_free(af_index_t *idx);
 int af_index_info(const af_index_t *idx, af_index_info_t *info);
+/* 0: the filter words are fingerprint buckets; 1: they hold a blocked Bloom filter (anchors beyond ~12 kb, whose
+ * k'-mers overflow the 3-slot buckets) */
+int af_index_filter_kind(const af_index_t *idx);
 /* raw views for tests (host memory owned by the index) */
 const uint32_t *af_index_filter(const af_index_t *idx);
 const uint32_t *af_index_table(const af_index_t *idx); /* table_slots x {key, value} */

@@ -33,11 +33,18 @@ def expected_flags(index, codes, lens=None, refine=False):
             full[lens <= i, i] = pad[i & 3]
     H = (19 - KP + 1) // 2
 
+    bloom = getattr(index, "bloom", False)
+
     def probe(p):
         key = np.zeros(n, np.uint64)
         for t in range(KP):
             key |= full[:, p + t] << np.uint64(2 * t)
         b, fp3 = filter_hash(key, fm, KP, nb)
+        if bloom:                                  # af_bloom_probe: three bits of the bucket's word
+            lo = (key * np.uint64(fm)) & np.uint64(0xFFFFFFFF)
+            one = np.uint64(1)
+            mask = (one << ((lo >> np.uint64(1)) & np.uint64(31))) | (one << ((lo >> np.uint64(6)) & np.uint64(31))) | (one << ((lo >> np.uint64(11)) & np.uint64(31)))
+            return (~filt[b] & mask & np.uint64(0xFFFFFFFF)) == 0
         v = filt[b] ^ fp3
         return (((v - np.uint64(0x40100401)) & ~v & np.uint64(0xA0080200)) & np.uint64(0xFFFFFFFF)) != 0
 

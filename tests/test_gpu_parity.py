@@ -194,22 +194,39 @@ def test_unsupported_seed_length_is_refused(af):
         af.AnchorIndex("ACGT" * 100, params=af.default_params(k=15))
 
 
-def test_long_anchor_saturating_the_filter_stays_exact(af):
-    """A 40 kb anchor overflows thousands of filter buckets ("always hit"): most reads are flagged and the
-    exact verify stage decides -- the records must still equal the oracle's."""
+@pytest.mark.parametrize("anchor_len,bloom", [(40_000, True), (40_000, False), (20_000, False), (100_000, True)])
+def test_long_anchor_stays_exact_with_bloom_filter_or_saturated_buckets(af, anchor_len, bloom, monkeypatch):
+    """Anchors beyond ~12 kb overflow the 3-slot filter buckets ("always hit").  By default the index then carries a
+    blocked Bloom filter in the same shared memory (far fewer flagged reads); AF_NO_BLOOM keeps the saturated buckets,
+    where most reads are flagged and the exact verify stage decides.  Either way the records equal the oracle's."""
     from oracle import oracle
-    spec = af.synth_spec(seed=40, ref_len=600_000, anchor_start=200_000, anchor_len=40_000, read_len=150,
+    if not bloom and anchor_len > 30_000:
+        monkeypatch.setenv("AF_NO_BLOOM", "1")
+    spec = af.synth_spec(seed=40, ref_len=600_000, anchor_start=200_000, anchor_len=anchor_len, read_len=150,
                          frag_mean=300, frag_sd=30, sub_ppm=15_000, fusion_ppm=20_000)
     anchor = af.synth_anchor(spec)
     index = af.AnchorIndex(anchor)
-    assert index.info.n_overflow > 2000
+    assert index.bloom == bloom and index.info.n_overflow * 200 > index.info.n_buckets
     eng = af.Anchorer(index, 0)
     n = 60_000
-    hits, stats = eng.anchor(af.synth_pairs_device(spec, 0, n, index.pad_byte, 0))
-    assert stats["flagged"] > n                                     # more than half of the 2n reads
+    dev = af.synth_pairs_device(spec, 0, n, index.pad_byte, 0)
+    hits, stats = eng.anchor(dev)
     m1, m2 = af.synth_pairs_host(spec, 0, n)
     want = oracle.anchor_reads(oracle.encode(anchor), _interleave(m1, m2), threads=8)
-    assert len(want) > 5000 and hits_equal(hits, want)
+    assert len(want) > 2500 and hits_equal(hits, want)
+    if anchor_len == 40_000:
+        assert (stats["flagged"] < 0.7 * n) if bloom else (stats["flagged"] > n)      # of 2n reads: < 35 % against > 50 %
+    # the scan's flag words are exactly what the filter words say (numpy emulation of the probe)
+    from filter_emulator import expected_flags
+    flags = eng.seed_scan(dev).cpu().numpy().view(np.uint32)
+    sub = 4096
+    codes = _interleave(m1, m2)[: 2 * sub]
+    got = np.array([(flags[(r >> 1) >> 5, r & 1] >> ((r >> 1) & 31)) & 1 for r in range(2 * sub)], dtype=bool)
+    assert np.array_equal(got, expected_flags(index, codes))
+    # ... and the host-buffer pipeline takes the same route
+    host = af.PackedBatch(dev.packed.cpu().numpy().view(np.uint32), n, 150, 150)
+    hits2, _ = eng.anchor_host(host, slot_pairs=16_384, n_slots=2)
+    assert hits_equal(hits2, want)
 
 
 def test_robustness_set_n_bases_and_trimmed_reads(af):

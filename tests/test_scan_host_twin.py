@@ -50,3 +50,40 @@ def test_host_twin_equals_emulation_and_has_no_false_negatives(read_len, kp):
     ref = _scan_pairs_host(af, index, batch, refine=True)
     assert np.array_equal(ref, expected_flags(index, codes, refine=True))
     assert ref[hits["read_id"]].all() and not (ref & ~got).any() and ref.sum() <= got.sum()
+
+
+@pytest.mark.parametrize("anchor_len", [40_000, 100_000])
+def test_long_anchor_switches_to_the_bloom_filter_without_false_negatives(anchor_len, monkeypatch):
+    """Beyond ~12 kb the 3-slot buckets overflow; the index then holds a blocked Bloom filter in the same words.  The
+    probe sequence the kernel runs (host twin) equals the numpy emulation, flags every anchored read, and flags far
+    fewer random reads than the overflowing buckets would."""
+    import anchored_fusion_b200 as af
+    from filter_emulator import expected_flags
+    from oracle import oracle
+    read_len, n = 150, 1200
+    spec = af.synth_spec(seed=anchor_len, ref_len=200_000, anchor_start=50_000, anchor_len=anchor_len, read_len=read_len,
+                         frag_mean=300, sub_ppm=15_000, fusion_ppm=50_000)
+    anchor = af.synth_anchor(spec)
+    index = af.AnchorIndex(anchor)
+    assert index.bloom and index.info.n_overflow * 25 > index.info.n_buckets
+    assert not af.AnchorIndex(anchor[:6783]).bloom and not af.AnchorIndex(anchor[:20_000]).bloom
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    batch = af.pack_pairs([lut[r].tobytes() for r in m1], [lut[r].tobytes() for r in m2], pad_byte=index.pad_byte)
+    got = _scan_pairs_host(af, index, batch)
+    codes = np.empty((2 * n, read_len), dtype=np.uint8)
+    codes[0::2], codes[1::2] = m1, m2
+    assert np.array_equal(got, expected_flags(index, codes))
+    hits = oracle.anchor_reads(oracle.encode(anchor), codes, threads=4)
+    assert len(hits) > 100 and got[hits["read_id"]].all()
+    # reads that do not touch the anchor: the Bloom filter lets far fewer through than the saturated buckets
+    rng = np.random.default_rng(1)
+    rnd = rng.integers(0, 4, (2 * n, read_len)).astype(np.uint8)
+    rb = af.pack_pairs([lut[r].tobytes() for r in rnd[0::2]], [lut[r].tobytes() for r in rnd[1::2]], pad_byte=index.pad_byte)
+    bloom_rate = _scan_pairs_host(af, index, rb).mean()
+    monkeypatch.setenv("AF_NO_BLOOM", "1")
+    plain = af.AnchorIndex(anchor)
+    assert not plain.bloom
+    bucket_rate = _scan_pairs_host(af, plain, af.pack_pairs([lut[r].tobytes() for r in rnd[0::2]], [lut[r].tobytes() for r in rnd[1::2]],
+                                                            pad_byte=plain.pad_byte)).mean()
+    assert bloom_rate < 0.7 * bucket_rate and bloom_rate < (0.25 if anchor_len == 40_000 else 0.7), (bloom_rate, bucket_rate)
