@@ -3,12 +3,16 @@
 // the parser of foreign files runs under AddressSanitizer / UBSan in tools/fuzz_host.cpp.
 #include <zlib.h>
 
+#include <sys/stat.h>
+
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "af_common.h"
+#include "af_crc32.h"
 
 // an N is stored as a position-dependent pseudo-random base (and a set bit in the N bitmap), so the long N runs
 // of an assembly look like random sequence to the filter instead of 150 M copies of one 12-mer
@@ -69,8 +73,7 @@ int af_genome_host_from_contigs(const char *const *names, const char *const *seq
     return AF_OK;
 }
 
-int af_genome_host_from_fasta(const char *path, af_genome_host &out) {
-    if (!path) { af_set_error("af_genome_from_fasta: null"); return AF_ERR_ARG; }
+static int parse_fasta(const char *path, af_genome_host &out) {
     gzFile f = gzopen(path, "rb");
     if (!f) { af_set_error("af_genome_from_fasta: cannot open %s", path); return AF_ERR_IO; }
     gzbuffer(f, 1 << 20);
@@ -119,6 +122,93 @@ int af_genome_host_from_fasta(const char *path, af_genome_host &out) {
     if (c.names.empty()) { af_set_error("af_genome_from_fasta: %s holds no sequence", path); return AF_ERR_IO; }
     finish(c, out);
     return AF_OK;
+}
+
+// ---- packed-genome cache: <fasta>.af2bit beside the FASTA --------------------------------------------------------
+// Parsing and packing a human genome takes ~9 s per process (330 Mbp/s); the packed form is 1.2 GB and loads at disk
+// speed.  The cache is the host structure as it is: header {magic, version, FASTA size, FASTA mtime, bases, contigs},
+// contig table, packed words, N words.  It is used only when its header matches the FASTA it sits next to and every
+// size in it is consistent with the file's own length; anything else falls back to the FASTA (and rewrites the cache).
+// AF_GENOME_CACHE=0 switches it off; an unwritable directory just means no cache.
+static const uint64_t CACHE_MAGIC = 0x3154494232464101ull;   // "\x01AF2BIT1"
+struct CacheHeader { uint64_t magic, version, fasta_size, fasta_mtime, n_bases, n_contigs, names_bytes, checksum; };
+
+static uint64_t cache_checksum(const std::vector<int64_t> &tab, const std::string &names, const std::vector<uint32_t> &pk, const std::vector<uint32_t> &nm) {
+    const uint64_t a = af_crc32((const uint8_t *)pk.data(), pk.size() * 4), b = af_crc32((const uint8_t *)nm.data(), nm.size() * 4);
+    const uint64_t c = af_crc32((const uint8_t *)tab.data(), tab.size() * 8), d = af_crc32((const uint8_t *)names.data(), names.size());
+    return (a | (b << 32)) ^ (c << 13) ^ (d << 29);
+}
+
+static bool fasta_stamp(const char *path, uint64_t *size, uint64_t *mtime) {
+    struct stat st;
+    if (stat(path, &st) != 0) return false;
+    *size = (uint64_t)st.st_size; *mtime = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+    return true;
+}
+
+static bool cache_load(const std::string &cpath, uint64_t fsize, uint64_t fmtime, af_genome_host &out) {
+    FILE *f = fopen(cpath.c_str(), "rb");
+    if (!f) return false;
+    bool ok = false;
+    CacheHeader h;
+    struct stat st;
+    if (fread(&h, sizeof(h), 1, f) == 1 && h.magic == CACHE_MAGIC && h.version == 1 && h.fasta_size == fsize && h.fasta_mtime == fmtime &&
+        h.n_bases < (1ull << 35) && h.n_contigs >= 1 && h.n_contigs < (1ull << 24) && h.names_bytes < (1ull << 30) && fstat(fileno(f), &st) == 0) {
+        const uint64_t pkw = (h.n_bases + 15) / 16 + 1, nmw = (h.n_bases + 31) / 32 + 1;
+        const uint64_t want = sizeof(h) + h.n_contigs * 16 + h.names_bytes + (pkw + nmw) * 4;
+        if ((uint64_t)st.st_size == want) {
+            std::vector<int64_t> tab((size_t)h.n_contigs * 2);
+            std::string names((size_t)h.names_bytes, '\0');
+            out.pk.resize((size_t)pkw); out.nm.resize((size_t)nmw);
+            ok = fread(tab.data(), 16, (size_t)h.n_contigs, f) == h.n_contigs && (h.names_bytes == 0 || fread(&names[0], 1, names.size(), f) == names.size()) &&
+                 fread(out.pk.data(), 4, (size_t)pkw, f) == pkw && fread(out.nm.data(), 4, (size_t)nmw, f) == nmw;
+            if (ok && cache_checksum(tab, names, out.pk, out.nm) != h.checksum) ok = false;      // damaged body
+            if (ok) {
+                out.n = (int64_t)h.n_bases;
+                out.names.clear(); out.starts.clear(); out.lens.clear();
+                size_t at = 0;
+                for (uint64_t i = 0; i < h.n_contigs && ok; i++) {
+                    const size_t e = names.find('\0', at);
+                    const int64_t start = tab[(size_t)i * 2], len = tab[(size_t)i * 2 + 1];
+                    if (e == std::string::npos || start < AF_GENOME_SEP || len < 0 || start + len + AF_GENOME_SEP > out.n) { ok = false; break; }
+                    out.names.push_back(names.substr(at, e - at)); out.starts.push_back(start); out.lens.push_back(len);
+                    at = e + 1;
+                }
+            }
+        }
+    }
+    fclose(f);
+    return ok;
+}
+
+static void cache_save(const std::string &cpath, uint64_t fsize, uint64_t fmtime, const af_genome_host &g) {
+    const std::string tmp = cpath + ".partial";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;                                           // read-only directory: no cache
+    std::string names;
+    std::vector<int64_t> tab;
+    for (size_t i = 0; i < g.names.size(); i++) { names += g.names[i]; names.push_back('\0'); tab.push_back(g.starts[i]); tab.push_back(g.lens[i]); }
+    const uint64_t pkw = (uint64_t)(g.n + 15) / 16 + 1, nmw = (uint64_t)(g.n + 31) / 32 + 1;
+    std::vector<uint32_t> pk(g.pk), nm(g.nm);
+    pk.resize((size_t)pkw, 0u); nm.resize((size_t)nmw, 0u);
+    CacheHeader h = {CACHE_MAGIC, 1, fsize, fmtime, (uint64_t)g.n, (uint64_t)g.names.size(), (uint64_t)names.size(), cache_checksum(tab, names, pk, nm)};
+    const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(tab.data(), 16, g.names.size(), f) == g.names.size() &&
+                    (names.empty() || fwrite(names.data(), 1, names.size(), f) == names.size()) && fwrite(pk.data(), 4, (size_t)pkw, f) == pkw &&
+                    fwrite(nm.data(), 4, (size_t)nmw, f) == nmw;
+    if (fclose(f) == 0 && ok) rename(tmp.c_str(), cpath.c_str()); else remove(tmp.c_str());
+}
+
+int af_genome_host_from_fasta(const char *path, af_genome_host &out) {
+    if (!path) { af_set_error("af_genome_from_fasta: null"); return AF_ERR_ARG; }
+    const char *ce = getenv("AF_GENOME_CACHE");
+    const bool use_cache = !(ce && ce[0] == '0');
+    uint64_t fsize = 0, fmtime = 0;
+    const std::string cpath = std::string(path) + ".af2bit";
+    if (use_cache && fasta_stamp(path, &fsize, &fmtime) && cache_load(cpath, fsize, fmtime, out)) return AF_OK;
+    out = af_genome_host();
+    const int rc = parse_fasta(path, out);
+    if (rc == AF_OK && use_cache && fsize) cache_save(cpath, fsize, fmtime, out);
+    return rc;
 }
 
 // test hook: parse + pack on the host only; FNV-1a over (code 0..4 of every base of the concatenation) lets a test

@@ -65,3 +65,37 @@ def test_fasta_errors_are_reported(tmp_path):
     (tmp_path / "cut.fa.gz").write_bytes(good[: len(good) // 2])
     with pytest.raises(AnchoredFusionError):
         _parse(tmp_path / "cut.fa.gz")
+
+
+def test_packed_genome_cache_is_used_validated_and_rebuilt(tmp_path, monkeypatch):
+    """<fasta>.af2bit: written on the first load, read on the second, ignored (and rewritten) when the FASTA changed or
+    the cache is damaged; AF_GENOME_CACHE=0 switches it off."""
+    import os
+    rng = np.random.default_rng(4)
+    contigs = [("c%d" % i, "".join("ACGTN"[c] for c in rng.integers(0, 5, n))) for i, n in enumerate((3000, 10, 70000))]
+    fa = tmp_path / "g.fa"
+    fa.write_text("".join(">%s\n%s\n" % c for c in contigs))
+    concat = "N" * SEP + "".join(s + "N" * SEP for _, s in contigs)
+    want = (len(concat), len(contigs), _fnv(_codes(concat)))
+    cache = tmp_path / "g.fa.af2bit"
+    assert _parse(fa) == want and cache.exists()
+    stamp = cache.stat().st_mtime_ns
+    assert _parse(fa) == want and cache.stat().st_mtime_ns == stamp          # second load: cache read, not rewritten
+    raw = bytearray(cache.read_bytes())
+    cache.write_bytes(bytes(raw[: len(raw) // 2]))                             # truncated cache: ignored, rebuilt
+    assert _parse(fa) == want and cache.stat().st_size == len(raw)
+    flipped = bytearray(raw)
+    flipped[len(raw) // 2] ^= 0x10                                             # one bit of the packed bases: the checksum catches it
+    cache.write_bytes(bytes(flipped))
+    assert _parse(fa) == want and cache.read_bytes() == bytes(raw)
+    contigs2 = contigs + [("extra", "ACGT" * 100)]
+    fa.write_text("".join(">%s\n%s\n" % c for c in contigs2))                  # the FASTA changed: size stamp differs
+    concat2 = "N" * SEP + "".join(s + "N" * SEP for _, s in contigs2)
+    assert _parse(fa) == (len(concat2), len(contigs2), _fnv(_codes(concat2)))
+    raw = bytearray(cache.read_bytes())
+    raw[16:24] = (1 << 40).to_bytes(8, "little")                               # header claims another FASTA size
+    cache.write_bytes(bytes(raw))
+    assert _parse(fa) == (len(concat2), len(contigs2), _fnv(_codes(concat2)))
+    monkeypatch.setenv("AF_GENOME_CACHE", "0")
+    os.remove(cache)
+    assert _parse(fa)[0] == len(concat2) and not cache.exists()

@@ -141,7 +141,26 @@ int main(int argc, char **argv) {
             const std::string pf = dir + "/g.fa";
             write_file(pf, fa);
             int64_t total = 0; int32_t ncon = 0; uint64_t sum = 0;
-            const int rc = af_debug_genome_fasta(pf.c_str(), &total, &ncon, &sum);
+            setenv("AF_GENOME_CACHE", rnd(0, 2) ? "0" : "1", 1);
+            remove((pf + ".af2bit").c_str());
+            int rc = af_debug_genome_fasta(pf.c_str(), &total, &ncon, &sum);
+            if (rc == AF_OK && !rnd(0, 1)) {                           // a second load through a (possibly damaged) cache file
+                FILE *cf = fopen((pf + ".af2bit").c_str(), "rb");
+                if (cf) {
+                    std::string cb;
+                    char tmp[4096]; size_t got;
+                    while ((got = fread(tmp, 1, sizeof(tmp), cf)) > 0) cb.append(tmp, got);
+                    fclose(cf);
+                    const bool damage = rnd(0, 1);
+                    if (damage) { mutate(cb); write_file(pf + ".af2bit", cb); }
+                    int64_t total2 = 0; int32_t ncon2 = 0; uint64_t sum2 = 0;
+                    const int rc2 = af_debug_genome_fasta(pf.c_str(), &total2, &ncon2, &sum2);
+                    if (rc2 != AF_OK || total2 != total || ncon2 != ncon || sum2 != sum) {
+                        fprintf(stderr, "fuzz_host: genome cache (damaged: %d) changed the result in iteration %d\n", (int)damage, it);
+                        return 1;
+                    }
+                }
+            }
             if (intact && nc > 0 && (rc != AF_OK || ncon != nc || total != want_len)) {
                 fprintf(stderr, "fuzz_host: FASTA of %d contigs / %lld bases came back as rc %d, %d contigs, %lld bases (iteration %d)\n",
                         nc, (long long)want_len, rc, ncon, (long long)total, it);
