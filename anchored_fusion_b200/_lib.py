@@ -85,6 +85,7 @@ SIGNATURES = {
     "af_fastq_peek": (ctypes.c_int, [ctypes.c_char_p, c_i32, P(c_i32)]),
     "af_fastq_close": (None, [c_vp]),
     "af_debug_crc32": (c_u32, [c_vp, c_i64]),
+    "af_debug_gunzip_chunks": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, P(c_i64), P(c_i32)]),
     "af_fastq_next": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64), P(c_i32),
                                      P(c_i64)]),
     "af_fastq_record": (ctypes.c_int, [c_vp, c_i64, P(c_vp), P(c_i32), P(c_vp), P(c_vp), P(c_i32)]),

@@ -12,7 +12,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 
 
 OBJDIR = os.path.join(HERE, "build")
-COMMON_DEPS = [os.path.join(CSRC, "af_common.h"), os.path.join(CSRC, "af_device.cuh"), os.path.join(CSRC, "af_inflate.h"), os.path.join(CSRC, "af_crc32.h"), os.path.join(HERE, "..", "include", "anchored_fusion.h"), os.path.abspath(__file__)]
+COMMON_DEPS = [os.path.join(CSRC, "af_common.h"), os.path.join(CSRC, "af_device.cuh"), os.path.join(CSRC, "af_inflate.h"), os.path.join(CSRC, "af_inflate_par.h"), os.path.join(CSRC, "af_crc32.h"), os.path.join(HERE, "..", "include", "anchored_fusion.h"), os.path.abspath(__file__)]
 
 
 def _newer(target, deps):

@@ -37,6 +37,7 @@
 
 #include "af_common.h"
 #include "af_inflate.h"
+#include "af_inflate_par.h"
 #include "af_crc32.h"
 
 struct SeqRef { const char *p; int32_t len; };
@@ -64,6 +65,36 @@ static const size_t SLICE = 1u << 20;          // newline-index / CRC / copy gra
 static const size_t SMALL_FILE = 3u << 20;     // files up to this size (on disk) are one task each
 #endif
 static const size_t AHEAD_BYTES = 192u << 20;  // decoded text a driver may hold ready ahead of the consumer
+// one gzip member decoded by several workers (af_inflate_par.h): compressed bytes per chunk, and the size from which
+// a member is worth it
+#ifdef AF_FASTQ_TEST_SIZES
+static const size_t PAR_CHUNK_DEFAULT = 6000;
+static const int PAR_MIN_WORKERS = 2;
+#else
+static const size_t PAR_CHUNK_DEFAULT = 8u << 20;
+static const int PAR_MIN_WORKERS = 6;              // below that the two serial inflate threads are as fast (measured)
+#endif
+// AF_GZIP_PAR_CHUNK=<bytes> (tests): chunk size, which also makes members from 4 chunks on and pools from 2 workers on eligible
+static size_t par_chunk_env() { const char *v = getenv("AF_GZIP_PAR_CHUNK"); const long long x = v ? atoll(v) : 0; return x >= 2048 ? (size_t)x : 0; }
+
+// cell buffers of the parallel gzip path, recycled (2 bytes per decoded byte: fresh pages would cost more than the decode)
+struct CellCache {
+    std::mutex mu;
+    std::vector<afz::CellBuf> free_list;
+    afz::CellBuf get() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_list.empty()) return afz::CellBuf();
+        afz::CellBuf b = std::move(free_list.back());
+        free_list.pop_back();
+        return b;
+    }
+    void put(afz::CellBuf &&b) {
+        b.clear();
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_list.size() < 24) free_list.push_back(std::move(b));
+    }
+};
+static CellCache g_cells;
 
 // ---- worker pool ---------------------------------------------------------------------------------
 class Pool {
@@ -473,6 +504,126 @@ struct Side {
         return true;
     }
 
+    // ONE large gzip member at `off`, decoded by several workers at once (af_inflate_par.h): the compressed bytes are cut
+    // into chunks; waves of chunks are decoded symbolically on the pool, each from a block start its task found by
+    // search; the driver then closes them in order -- a chunk must start where the one before stopped (else it is
+    // decoded again from there), its markers are resolved against the 32 KB that precede it -- and cuts the text into
+    // segments whose slices are resolved, indexed and CRC-ed on the pool.  Returns 1 when the member was handled (off
+    // moves behind its trailer), 0 when the path does not apply or the start could not be trusted (nothing was
+    // pushed: the serial path takes over at off), -1 on error / close.
+    int member_parallel(const std::shared_ptr<MappedFile> &mf, int file_idx, size_t &off, bool &first, std::string &err) {
+        if (getenv("AF_GZIP_SERIAL")) return 0;
+        const uint8_t *p = mf->p + off, *end = mf->p + mf->n;
+        size_t hl; uint32_t bs;
+        const int workers = pool->size();
+        const size_t env_chunk = par_chunk_env(), PAR_CHUNK = env_chunk ? env_chunk : PAR_CHUNK_DEFAULT, PAR_MIN = 4 * PAR_CHUNK;
+        if ((size_t)(end - p) < PAR_MIN || workers < (env_chunk ? 2 : PAR_MIN_WORKERS) || !afz::gzip_header(p, end, &hl, &bs) || bs) return 0;
+        const uint8_t *base = p + hl;
+        const uint64_t total_bits = (uint64_t)(end - base) * 8u;
+        const size_t n_chunks = ((size_t)(end - base) + PAR_CHUNK - 1) / PAR_CHUNK;
+        const size_t wave = (size_t)std::min(12, std::max(2, workers / 2));
+        struct Chunk { afz::SymResult r; Latch done; };
+        auto new_chunk = [] {
+            return std::shared_ptr<Chunk>(new Chunk(), [](Chunk *c) { g_cells.put(std::move(c->r.sym)); delete c; });
+        };
+        uint64_t at = 0;                                  // bit position of the next block to decode (a known block start)
+        bool member_done = false, pushed_any = false;
+        auto window = std::make_shared<std::vector<uint8_t>>(afz::WINDOW, (uint8_t)0);
+        // a rolling window of `wave` chunks is in flight on the pool: chunk c + wave is submitted when chunk c is taken
+        std::deque<std::shared_ptr<Chunk>> inflight;
+        size_t next_submit = 0;
+        auto stop_of = [&](size_t c) { return c + 1 < n_chunks ? (uint64_t)(c + 1) * PAR_CHUNK * 8u : ~0ull; };
+        auto submit_chunk = [&](size_t c) {
+            std::shared_ptr<Chunk> ck = new_chunk();
+            ck->r.sym = g_cells.get();
+            ck->done.add();
+            const uint64_t nominal = (uint64_t)c * PAR_CHUNK * 8u, stop = stop_of(c);
+            pool->submit([ck, mf, base, end, nominal, stop, c] {      // (mf keeps the mapping alive if the driver has left)
+                afz::decode_chunk(base, end, c == 0 ? 0 : ~0ull, nominal, stop, c != 0, ck->r);
+                ck->done.done();
+            });
+            inflight.push_back(ck);
+        };
+        {
+            for (size_t c = 0; c < n_chunks && !member_done; c++) {
+                while (next_submit < n_chunks && next_submit < c + wave) submit_chunk(next_submit++);
+                std::shared_ptr<Chunk> ck = inflight.front();
+                inflight.pop_front();
+                const uint64_t stop = stop_of(c);
+                if (c > 0 && at >= stop) continue;        // the chunk before ran past this one entirely
+                ck->done.wait();
+                if (ck->r.status != afz::OK_DONE || ck->r.start_bit != at) {
+                    // not where the stream really continues (no block start found, or a false one): decode it again from `at`
+                    afz::decode_chunk(base, end, at, at, stop, c != 0, ck->r);
+                    if (ck->r.status != afz::OK_DONE) {
+                        if (!pushed_any) return 0;        // let the serial decoder say what is wrong with this stream
+                        err = ck->r.status == afz::ERR_TRUNCATED ? "gzip stream is truncated" : "corrupt deflate data";
+                        return -1;
+                    }
+                }
+                const afz::SymResult &r = ck->r;
+                member_done = r.stream_end;
+                uint32_t want_crc = 0, want_size = 0;
+                if (member_done) {
+                    const uint8_t *t = base + (r.end_bit + 7) / 8;
+                    if (end - t < 8) { if (!pushed_any) return 0; err = "gzip stream is truncated (no trailer)"; return -1; }
+                    want_crc = rd32(t); want_size = rd32(t + 4);
+                    off = (size_t)(t + 8 - mf->p);
+                }
+                // the text of this chunk, one segment per SEG_TEXT bytes; every slice resolves, indexes and CRCs itself
+                const size_t n = r.sym.size();
+                const bool file_ends = member_done && off >= mf->n;
+                for (size_t b0 = 0; b0 < n || (b0 == 0 && member_done); b0 += SEG_TEXT) {
+                    const size_t len = std::min(SEG_TEXT, n - b0);
+                    if (!wait_room()) return -1;
+                    SegP seg = std::make_shared<Segment>();
+                    seg->file_idx = file_idx; seg->file_first = first; first = false;
+                    if (!seg->alloc(len + 1)) { err = "out of memory"; return -1; }
+                    seg->len = len;
+                    const bool last_of_member = member_done && b0 + len >= n;
+                    for (size_t b = 0; b < len || (b == 0 && last_of_member); b += SLICE) {
+                        const size_t e = std::min(b + SLICE, len);
+                        Segment::Slice *sl = seg->add_slice(b, e);
+                        seg->latch.add();
+                        SegP keep = seg;
+                        const bool mend = last_of_member && e == len;
+                        pool->submit([keep, sl, ck, window, b0, mend, want_crc, want_size] {
+                            Segment *sp = keep.get();
+                            afz::resolve_cells(ck->r.sym.data() + b0 + sl->b, sl->e - sl->b, window->data(), (uint8_t *)sp->text + sl->b);
+                            index_slice(*sp, *sl);
+                            CrcPiece cp;
+                            cp.crc = af_crc32((const uint8_t *)sp->text + sl->b, sl->e - sl->b);
+                            cp.len = sl->e - sl->b; cp.member_end = mend; cp.want_crc = want_crc; cp.want_size = want_size;
+                            sl->crc.push_back(cp);
+                            sp->latch.done();
+                        });
+                        if (e == len) break;
+                    }
+                    if (last_of_member && file_ends) {
+                        // (a last line without a terminator is closed by the consumer through file_end; the byte is added
+                        // once the slices are done -- the latch is waited for by the consumer before it reads the text)
+                        seg->file_end = true;
+                    }
+                    push(seg);
+                    pushed_any = true;
+                    if (b0 + len >= n) break;
+                }
+                // the window in front of the next chunk: the last 32 KB of everything resolved so far
+                auto nw = std::make_shared<std::vector<uint8_t>>(afz::WINDOW, (uint8_t)0);
+                if (n >= afz::WINDOW) afz::resolve_cells(r.sym.data() + n - afz::WINDOW, afz::WINDOW, window->data(), nw->data());
+                else {
+                    memcpy(nw->data(), window->data() + n, afz::WINDOW - n);
+                    afz::resolve_cells(r.sym.data(), n, window->data(), nw->data() + afz::WINDOW - n);
+                }
+                window = nw;
+                at = r.end_bit;
+            }
+        }
+        if (!member_done) { err = "gzip stream is truncated"; return -1; }
+        (void)total_bits;
+        return 1;
+    }
+
     // a serial gzip stream (one or more plain members) from `off`: the driver inflates, the pool indexes + CRCs
     bool stream_file(const std::shared_ptr<MappedFile> &mf, int file_idx, size_t off, bool first, std::string &err) {
         const uint8_t *p = mf->p + off, *end = mf->p + mf->n;
@@ -562,7 +713,13 @@ struct Side {
             size_t off = 0;
             bool first = true;
             if (!bgzf_file(mf, (int)fi, off, first, err)) { if (err.empty()) return; break; }
-            if (off < mf->n && !stream_file(mf, (int)fi, off, first, err)) { if (err.empty()) return; break; }
+            bool failed = false;
+            while (off < mf->n) {                         // large plain members in parallel, whatever else serially
+                const int pr = member_parallel(mf, (int)fi, off, first, err);
+                if (pr < 0) { failed = true; break; }
+                if (pr == 0) { if (!stream_file(mf, (int)fi, off, first, err)) failed = true; break; }
+            }
+            if (failed) { if (err.empty()) return; break; }
         }
         finish(err);
     }
@@ -997,3 +1154,54 @@ extern "C" int64_t af_fastq_batch_first_pair(const af_fastq_t *fq) { return fq ?
 
 // test hook: the reader's CRC-32 (carry-less multiplication where the CPU has it) of a host buffer
 extern "C" uint32_t af_debug_crc32(const void *buf, int64_t len) { return buf && len > 0 ? af_crc32((const uint8_t *)buf, (size_t)len) : af_crc32((const uint8_t *)"", 0); }
+
+// test hook: one gzip member decoded as the reader's parallel path decodes it -- the deflate payload cut into n_chunks
+// pieces, each decoded symbolically by its own thread from a block start it found itself, then chained and resolved.
+// *n_redone = chunks that had to be decoded again because they did not start where the chunk before them stopped.
+extern "C" int af_debug_gunzip_chunks(const void *gz, int64_t n, int32_t n_chunks, void *out, int64_t cap, int64_t *out_len, int32_t *n_redone) {
+    const uint8_t *p = (const uint8_t *)gz, *end = p + n;
+    size_t hl; uint32_t bs;
+    if (!gz || !out_len || n_chunks < 1 || !afz::gzip_header(p, end, &hl, &bs)) { af_set_error("af_debug_gunzip_chunks: not a gzip member"); return AF_ERR_ARG; }
+    const uint8_t *base = p + hl;
+    const uint64_t total_bits = (uint64_t)(end - base) * 8u;
+    std::vector<afz::SymResult> res((size_t)n_chunks);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n_chunks; k++)
+        th.emplace_back([&, k] {
+            const uint64_t nominal = total_bits / (uint64_t)n_chunks * (uint64_t)k / 8u * 8u, stop = k + 1 < n_chunks ? total_bits / (uint64_t)n_chunks * (uint64_t)(k + 1) / 8u * 8u : ~0ull;
+            afz::decode_chunk(base, end, k == 0 ? 0 : ~0ull, nominal, stop, k != 0, res[(size_t)k]);
+        });
+    for (auto &t : th) t.join();
+    // chain: chunk k must start where the last good chunk stopped
+    int redone = 0;
+    std::vector<uint8_t> window(afz::WINDOW, 0);
+    uint8_t *o = (uint8_t *)out;
+    int64_t len = 0;
+    uint64_t at = 0;
+    bool done = false;
+    for (int k = 0; k < n_chunks && !done; k++) {
+        afz::SymResult &r = res[(size_t)k];
+        const uint64_t stop = k + 1 < n_chunks ? total_bits / (uint64_t)n_chunks * (uint64_t)(k + 1) / 8u * 8u : ~0ull;
+        if (k > 0 && at >= stop) continue;                    // the chunk before ran past this one entirely
+        if (r.status != afz::OK_DONE || r.start_bit != at) {
+            afz::decode_chunk(base, end, at, at, stop, k != 0, r);
+            redone += k != 0;
+            if (r.status != afz::OK_DONE) { af_set_error("af_debug_gunzip_chunks: corrupt deflate data in chunk %d", k); return AF_ERR_IO; }
+        }
+        const int64_t m = (int64_t)r.sym.size();
+        if (len + m > cap) { af_set_error("af_debug_gunzip_chunks: output buffer too small"); return AF_ERR_CAPACITY; }
+        afz::resolve_cells(r.sym.data(), (size_t)m, window.data(), o + len);
+        len += m;
+        // the window of the next chunk: the last 32 KB of everything resolved so far
+        if (len >= (int64_t)afz::WINDOW) memcpy(window.data(), o + len - afz::WINDOW, afz::WINDOW);
+        else { memset(window.data(), 0, afz::WINDOW); memcpy(window.data() + afz::WINDOW - len, o, (size_t)len); }
+        at = r.end_bit;
+        done = r.stream_end;
+    }
+    if (!done) { af_set_error("af_debug_gunzip_chunks: the stream does not end"); return AF_ERR_IO; }
+    const uint8_t *t = base + (at + 7) / 8;
+    if (end - t < 8 || af_crc32(o, (size_t)len) != rd32(t) || (uint32_t)len != rd32(t + 4)) { af_set_error("af_debug_gunzip_chunks: CRC or length check failed"); return AF_ERR_IO; }
+    *out_len = len;
+    if (n_redone) *n_redone = redone;
+    return AF_OK;
+}

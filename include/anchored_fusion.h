@@ -181,6 +181,9 @@ int af_fastq_records(const af_fastq_t *fq, const int64_t *read_ids, int64_t n, c
 /* test hook: the CRC-32 the reader checks every inflated BGZF block / gzip member with (PCLMULQDQ folding where the
  * CPU has it, zlib otherwise); equals zlib's crc32(0, buf, len) */
 uint32_t af_debug_crc32(const void *buf, int64_t len);
+/* test hook: ONE gzip member decoded the way the reader's parallel single-member path decodes it (payload cut into
+ * n_chunks pieces, block starts found by search, symbolic decode, chaining, marker resolution, CRC check) */
+int af_debug_gunzip_chunks(const void *gz, int64_t n, int32_t n_chunks, void *out, int64_t cap, int64_t *out_len, int32_t *n_redone);
 /* index (over the whole run) of the first pair of every input file started so far; returns the count */
 int af_fastq_file_starts(const af_fastq_t *fq, int64_t *first_pair_out, int32_t cap);
 /* index (over the whole run) of the current batch's first pair */

@@ -433,3 +433,90 @@ def test_reader_crc32_equals_zlib_on_every_length_and_alignment():
             raw = rng.integers(0, 256, n + off, dtype=np.uint8)
             view = raw[off:]
             assert L.af_debug_crc32(view.ctypes.data, n) == zlib.crc32(view.tobytes()), (n, off)
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+@pytest.mark.parametrize("chunk", [4096, 50_000])
+def test_single_member_gzip_decoded_by_several_workers(tmp_path, monkeypatch, level, chunk):
+    """One gzip member per file, decoded in parallel (af_inflate_par.h: block starts found by search, symbolic decode,
+    chaining, marker resolution): identical batches and record text to the serial path, for streams of real gzip at
+    several levels (back-references across every chunk boundary) and for two large members back to back."""
+    import gzip as gz
+    from anchored_fusion_b200.stage import FastqPairReader
+    n = 30_000
+    s1, s2, q1, q2 = _random_pairs(n, 11 + level)
+    t1 = _fastq_text(["INSTR:%d:FLOW:1:%d:%d:%d 1:N:0:ACGT" % (7, 1100 + i // 1000, 1000 + i * 3, 2000 + i * 7) for i in range(n)], s1, q1)
+    t2 = _fastq_text(["INSTR:%d:FLOW:1:%d:%d:%d 2:N:0:ACGT" % (7, 1100 + i // 1000, 1000 + i * 3, 2000 + i * 7) for i in range(n)], s2, q2)
+    p1, p2 = str(tmp_path / "s_1.fastq.gz"), str(tmp_path / "s_2.fastq.gz")
+    open(p1, "wb").write(gz.compress(t1, compresslevel=level))
+    half = t2.index(b"\n@INSTR", len(t2) // 2) + 1
+    open(p2, "wb").write(gz.compress(t2[:half], compresslevel=level) + gz.compress(t2[half:], compresslevel=level))   # two members
+    monkeypatch.setenv("AF_GZIP_SERIAL", "1")
+    rd = FastqPairReader(p1, p2, 160, 0xE4, 8192, threads=4)
+    want_batches, want_recs = _read_all(rd)
+    rd.close()
+    monkeypatch.delenv("AF_GZIP_SERIAL")
+    monkeypatch.setenv("AF_GZIP_PAR_CHUNK", str(chunk))
+    for threads in (2, 5):
+        rd = FastqPairReader(p1, p2, 160, 0xE4, 8192, threads=threads)
+        got_batches, got_recs = _read_all(rd)
+        rd.close()
+        assert got_recs == want_recs and len(got_recs) == 2 * n
+        assert len(got_batches) == len(want_batches)
+        for g, w in zip(got_batches, want_batches):
+            assert g[0] == w[0] and np.array_equal(g[1], w[1]) and np.array_equal(g[2], w[2]) and g[4] == w[4]
+            assert (g[3] is None and w[3] is None) or np.array_equal(g[3], w[3])
+
+
+def test_parallel_gzip_path_reports_damage(tmp_path, monkeypatch):
+    """Truncation, a flipped bit in the deflate data (caught by the member CRC at the latest) and trailing garbage on the
+    parallel single-member path."""
+    import gzip as gz
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200.stage import FastqPairReader
+    n = 20_000
+    s1, s2, q1, q2 = _random_pairs(n, 3, with_n=False)
+    t1, t2 = _fastq_text(["a%d" % i for i in range(n)], s1, q1), _fastq_text(["a%d" % i for i in range(n)], s2, q2)
+    good1, good2 = gz.compress(t1, 6), gz.compress(t2, 6)
+    monkeypatch.setenv("AF_GZIP_PAR_CHUNK", "30000")
+
+    def run(b1, b2):
+        p1, p2 = str(tmp_path / "d_1.fastq.gz"), str(tmp_path / "d_2.fastq.gz")
+        open(p1, "wb").write(b1)
+        open(p2, "wb").write(b2)
+        rd = FastqPairReader(p1, p2, 160, 0xE4, 4096, threads=4)
+        try:
+            total = 0
+            while True:
+                b = rd.next_batch()
+                if b is None:
+                    return total
+                total += b.n_pairs
+        finally:
+            rd.close()
+    assert run(good1, good2) == n
+    assert run(good1 + b"trailing garbage that is not gzip", good2) == n            # ignored, as gzip does
+    with pytest.raises(af.AnchoredFusionError, match="truncated|CRC|corrupt"):
+        run(good1[: len(good1) * 2 // 3], good2)
+    for at in (len(good1) // 3, len(good1) // 2, len(good1) - 5):
+        bad = bytearray(good1)
+        bad[at] ^= 0x04
+        with pytest.raises(af.AnchoredFusionError, match="CRC|corrupt|truncated|record|FASTQ"):
+            run(bytes(bad), good2)
+
+
+def test_chunked_gunzip_equals_zlib_and_finds_its_block_starts():
+    """af_debug_gunzip_chunks: the parallel decode alone, any number of chunks, against the source text."""
+    import ctypes
+    import gzip as gz
+    from anchored_fusion_b200._lib import check, lib
+    n = 15_000
+    s1, _, q1, _ = _random_pairs(n, 21)
+    text = _fastq_text(["M01:%d:%d" % (i // 500, i) for i in range(n)], s1, q1)
+    for level in (1, 6, 9):
+        blob = np.frombuffer(gz.compress(text, level), dtype=np.uint8)
+        for k in (1, 2, 7, 23):
+            out = np.zeros(len(text) + 64, dtype=np.uint8)
+            m, redone = ctypes.c_int64(), ctypes.c_int32()
+            check(lib().af_debug_gunzip_chunks(blob.ctypes.data, len(blob), k, out.ctypes.data, len(out), ctypes.byref(m), ctypes.byref(redone)))
+            assert out[: m.value].tobytes() == text and redone.value <= 1, (level, k, redone.value)

@@ -25,6 +25,7 @@ ap.add_argument("--threads", type=str, default="1,2,4,8,16")
 ap.add_argument("--level", type=int, default=6)
 ap.add_argument("--batch", type=int, default=1 << 19)
 ap.add_argument("--out", type=str, default="")
+ap.add_argument("--real-gzip", type=int, default=0, help="also time a single member written by zlib itself at this level (one continuous stream, back-references across every chunk)")
 args = ap.parse_args()
 L = lib()
 spec = oracle.synth_spec(seed=1, ref_len=10_000_000, anchor_start=2_000_000, anchor_len=6783, read_len=150, frag_mean=300, sub_ppm=10_000)
@@ -68,6 +69,34 @@ try:
         res["formats"][key] = {"file_bytes": os.path.getsize(p1) + os.path.getsize(p2), "by_threads": rows}
         os.remove(p1)
         os.remove(p2)
+    if args.real_gzip:
+        import zlib
+        p1, p2 = os.path.join(d, "z_1.fastq.gz"), os.path.join(d, "z_2.fastq.gz")
+        q1, q2 = os.path.join(d, "z_1.fastq"), os.path.join(d, "z_2.fastq")
+        oracle.synth_fastq(spec, 0, args.pairs, [q1], [q2], oracle.FASTQ_PLAIN, 0, threads=8)
+        for src, dst in ((q1, p1), (q2, p2)):
+            co = zlib.compressobj(args.real_gzip, zlib.DEFLATED, 31)
+            with open(src, "rb") as fi, open(dst, "wb") as fo:
+                while True:
+                    blk = fi.read(1 << 24)
+                    if not blk:
+                        break
+                    fo.write(co.compress(blk))
+                fo.write(co.flush())
+            os.remove(src)
+        run(p1, p2, 0)
+        rows = {}
+        for label, env in (("parallel", None), ("serial", "1")):
+            if env:
+                os.environ["AF_GZIP_SERIAL"] = env
+            else:
+                os.environ.pop("AF_GZIP_SERIAL", None)
+            for t in [int(x) for x in args.threads.split(",")]:
+                best = min(run(p1, p2, t) for _ in range(3))
+                rows["%s_%d" % (label, t)] = {"seconds": best, "pairs_per_s": args.pairs / best}
+                print("zlib-%d %-8s threads=%-2d %.3f s  %.2f M pairs/s" % (args.real_gzip, label, t, best, args.pairs / best / 1e6), file=sys.stderr, flush=True)
+        os.environ.pop("AF_GZIP_SERIAL", None)
+        res["formats"]["zlib_single_member"] = {"level": args.real_gzip, "file_bytes": os.path.getsize(p1) + os.path.getsize(p2), "by_mode_threads": rows}
 finally:
     shutil.rmtree(d, ignore_errors=True)
 print(json.dumps(res))
