@@ -93,6 +93,10 @@ struct CellCache {
         std::lock_guard<std::mutex> lk(mu);
         if (free_list.size() < 24) free_list.push_back(std::move(b));
     }
+    void trim() {                        // a reader was closed: hand the memory back (another open reader will allocate again)
+        std::vector<afz::CellBuf> drop;
+        { std::lock_guard<std::mutex> lk(mu); drop.swap(free_list); }
+    }
 };
 static CellCache g_cells;
 
@@ -966,6 +970,7 @@ extern "C" void af_fastq_close(af_fastq_t *fq) {
     for (int i = 0; i < 2; i++) fq->side[i].stop();
     fq->pool.reset();        // joins the workers; queued tasks still run (they hold their segments alive)
     delete fq;
+    g_cells.trim();
 }
 
 // Gathers up to max_pairs records per mate; n = pairs available on both.  Errors are sticky.
