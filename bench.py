@@ -193,6 +193,70 @@ def fastq_rates(args, index, eng):
     return res
 
 
+# ---- genome pass of the contiguity filter (the stage after the path; csrc/af_genome.cu) --------------------------
+def genome_pass_rate(args, device, hbm_peak):
+    """`--genome-reads` reads drawn from a synthetic genome of `--genome-bases` bases (1 % substitutions, both strands)
+    aligned back to it through Genome.align (wall clock, best of 3, host text -> records on the host); every read must
+    come back where it was drawn.  On a 10 Mbp genome the records are also compared with the CPU oracle."""
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200.genome import Genome
+    from oracle import oracle
+    rng = np.random.default_rng(17)
+    rc = str.maketrans("ACGT", "TGCA")
+    L = args.read_len
+
+    def draw(n_bases, n_reads, seed):
+        reads, where = [], []
+        for _ in range(n_reads):
+            at = int(rng.integers(0, n_bases - L))
+            s = af.synth_anchor(af.synth_spec(seed=seed, ref_len=n_bases, anchor_start=at, anchor_len=L))
+            b = bytearray(s if isinstance(s, bytes) else s.encode())
+            for i in np.flatnonzero(rng.random(L) < 0.01):
+                b[i] = b"ACGT"[(b"ACGT".index(b[i]) + 1 + int(rng.integers(0, 3))) % 4]
+            s = b.decode()
+            strand = int(rng.integers(0, 2))
+            reads.append(s.translate(rc)[::-1] if strand else s)
+            where.append((at, strand))
+        return reads, where
+
+    g = Genome.synthetic(23, args.genome_bases, device)
+    reads, where = draw(args.genome_bases, args.genome_reads, 23)
+    g.align(reads[:8])
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        hits = g.align(reads)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, dict(g.last_stats))
+    by = {int(h["read_id"]): h for h in hits}
+    placed = sum(1 for i, (at, strand) in enumerate(where) if i in by and (int(by[i]["score_strand"]) & 1) == strand
+                 and int(by[i]["pos"]) - int(by[i]["clip_l"]) == at + 256 + 1)
+    g.close()
+    # parity on a genome the oracle can index in a few seconds
+    nb = 10_000_000
+    g2 = Genome.synthetic(29, nb, device)
+    reads2, _ = draw(nb, 400, 29)
+    h2 = g2.align(reads2)
+    g2.close()
+    ref = af.synth_anchor(af.synth_spec(seed=29, ref_len=nb, anchor_start=0, anchor_len=nb))
+    concat = oracle.encode(b"N" * 256 + (ref if isinstance(ref, bytes) else ref.encode()) + b"N" * 256)
+    o = oracle.anchor_reads(concat, np.stack([oracle.encode(r) for r in reads2]), threads=os.cpu_count() or 1)
+    equal = len(o) == len(h2) and all(np.array_equal(o[f].astype(np.int64), h2[f].astype(np.int64))
+                                      for f in ("read_id", "pos", "clip_l", "m_len", "clip_r", "score_strand"))
+    st = best[1]
+    scan_bytes = args.genome_bases / 4.0 * st["n_passes"]
+    return {"what": "Genome.align: reads vs a synthetic genome resident in HBM (2 bit/base), no index; replaces `bwa mem` on the genome "
+                    "inside del_too_many_reads", "genome_bases": args.genome_bases, "reads": args.genome_reads, "read_len": L,
+            "value": args.genome_reads / best[0], "unit": "reads/s", "ms_per_call": best[0] * 1e3, "passes": st["n_passes"],
+            "scan_ms_per_pass": st["scan_ms"] / max(st["n_passes"], 1),
+            "scan_gb_per_s": scan_bytes / (st["scan_ms"] * 1e-3) / 1e9 if st["scan_ms"] else None,
+            "scan_frac_of_hbm_peak": scan_bytes / (st["scan_ms"] * 1e-3) / 1e9 / hbm_peak if st["scan_ms"] else None,
+            "reads_back_where_drawn": placed,
+            "parity": {"genome_bases": nb, "reads": len(reads2), "records": int(len(o)), "equal": bool(equal),
+                       "compared": "records of 400 reads on a 10 Mbp genome vs oracle/af_oracle.c with the concatenated genome as its anchor"}}
+
+
 # ---- configs[4]: the single-cell layout --------------------------------------------------------------------------
 def run_singlecell(args):
     """Thousands of per-cell FASTQ.gz pairs through the single-cell stage (all of a rank's cells through one
@@ -315,6 +379,8 @@ def main():
                     help="N > 1: how the ranks' hit lists reach every rank -- p2p: the hit-compaction kernel stores them "
                          "into every GPU's log over NVLink peer memory; nccl: one all-gather per step")
     ap.add_argument("--fastq-pairs", type=int, default=4_000_000, help="pairs of the FASTQ end-to-end samples (0: skip)")
+    ap.add_argument("--genome-bases", type=int, default=3_100_000_000, help="synthetic genome of the genome-pass leg (0: skip)")
+    ap.add_argument("--genome-reads", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -666,6 +732,11 @@ def main():
     if rank == 0 and world == 1 and args.fastq_pairs > 0 and not args.no_e2e and args.workload == "config1":
         fastq = fastq_rates(args, index, eng)
 
+    # the next stage: genome pass of the contiguity filter -- 2-op reads against a genome resident in HBM
+    genome = None
+    if rank == 0 and world == 1 and args.genome_bases > 0 and not args.no_e2e and args.workload == "config1":
+        genome = genome_pass_rate(args, local, peak)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -685,7 +756,7 @@ def main():
               "scaling": "strong" if args.workload == "config3" else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
               "config": config_dict(args, world),
               "run": {"streams": n_slots, "cuda_graphs": bool(args.graphs), "exchange": exchange_info},
-              "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq_gz": fastq, "parity": parity,
+              "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fastq_gz": fastq, "genome_pass": genome, "parity": parity,
               "gpu_launches": int(launches), "clocks": clocks,
               "per_step": {"flagged_reads": int(stats_counts[0]), "seeded_reads": int(stats_counts[3]),
                            "anchored_reads": nh, "kp": index.info.kp, "stride": index.info.stride}})

@@ -48,7 +48,7 @@ def test_both_arms_describe_the_same_config():
 @pytest.mark.gpu
 def test_gpu_arm_live_line_follows_the_contract():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "3", "--cpu-pairs", "2000000",
-                        "--fastq-pairs", "200000"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                        "--fastq-pairs", "200000", "--genome-bases", "200000000", "--genome-reads", "300"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -69,6 +69,8 @@ def test_gpu_arm_live_line_follows_the_contract():
     assert j["parity"]["equal"] is True and j["parity"]["pairs"] == 1_000_000 and j["parity"]["records"] > 1000
     c = j["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    gp = j["genome_pass"]
+    assert gp["reads_back_where_drawn"] == gp["reads"] and gp["parity"]["equal"] is True and gp["value"] > 0 and 0 < gp["scan_frac_of_hbm_peak"] < 1
     fq = j["fastq_gz"]
     assert fq["value"] > 0 and fq["threads"] >= 1 and fq["single_member_gzip"]["value"] > 0 and fq["plain_text"]["value"] > 0
     assert fq["anchored_reads"] == fq["single_member_gzip"]["anchored_reads"] == fq["plain_text"]["anchored_reads"] > 0
