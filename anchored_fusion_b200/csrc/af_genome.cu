@@ -55,6 +55,7 @@ struct af_genome {
     uint32_t *d_filter = nullptr; uint2 *d_table = nullptr; int64_t table_cap = 0;
     uint32_t *d_qpk = nullptr, *d_qnm = nullptr; uint16_t *d_qlen = nullptr; unsigned long long *d_best = nullptr;
     af_genome_hit_t *d_recs = nullptr; int64_t q_cap = 0;
+    std::mutex call_mu;   // af_genome_align uses the buffers above: one call at a time per genome
 };
 
 // ---- host side: concatenation and 2-bit packing live in af_genome_host.cpp (no CUDA: fuzzed under ASan) ---------
@@ -494,6 +495,7 @@ extern "C" int af_genome_align(af_genome_t *g, const char *reads, const int64_t 
     *n_hits_out = 0;
     if (stats) *stats = S;
     if (n_reads == 0) return AF_OK;
+    std::lock_guard<std::mutex> call_lock(g->call_mu);
     AF_CUDA(cudaSetDevice(g->device));
 
     // oriented reads: 2j = the read, 2j+1 = its reverse complement; N packed as A with its mask bit set

@@ -335,7 +335,8 @@ int64_t af_genome_length(const af_genome_t *g); /* separators included */
 int32_t af_genome_n_contigs(const af_genome_t *g);
 int af_genome_contig(const af_genome_t *g, int32_t i, const char **name, int64_t *start /* 0-based in the concatenation */, int64_t *len);
 /* reads: concatenated ASCII, offs[i]..offs[i+1] delimit read i (<= AF_MAX_READ_LEN bases each).  hits_out holds up to
- * n_reads records, ordered by read_id; reads without a record are unaligned.  reads_per_pass = 0 picks the default. */
+ * n_reads records, ordered by read_id; reads without a record are unaligned.  reads_per_pass = 0 picks the default.
+ * Calls on one genome object are serialised (they share its device buffers); use one object per thread for concurrency. */
 int af_genome_align(af_genome_t *g, const char *reads, const int64_t *offs, int64_t n_reads, const af_params_t *params,
                     int32_t reads_per_pass, af_genome_hit_t *hits_out, int64_t *n_hits_out, af_genome_stats_t *stats);
 
