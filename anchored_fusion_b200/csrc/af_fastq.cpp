@@ -523,6 +523,9 @@ struct Side {
         const size_t env_chunk = par_chunk_env(), PAR_CHUNK = env_chunk ? env_chunk : PAR_CHUNK_DEFAULT, PAR_MIN = 4 * PAR_CHUNK;
         if ((size_t)(end - p) < PAR_MIN || workers < (env_chunk ? 2 : PAR_MIN_WORKERS) || !afz::gzip_header(p, end, &hl, &bs) || bs) return 0;
         const uint8_t *base = p + hl;
+        // text that compresses more than 20:1 is not what this path is sized for (its cell buffers are 2 bytes per decoded
+        // byte): ISIZE, the last four bytes of a one-member file, says so up front
+        if ((uint64_t)rd32(end - 4) > (uint64_t)(end - base) * 20u) return 0;
         const uint64_t total_bits = (uint64_t)(end - base) * 8u;
         const size_t n_chunks = ((size_t)(end - base) + PAR_CHUNK - 1) / PAR_CHUNK;
         const size_t wave = (size_t)std::min(12, std::max(2, workers / 2));

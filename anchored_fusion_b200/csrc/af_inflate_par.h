@@ -269,7 +269,10 @@ static inline void decode_chunk(const uint8_t *base, const uint8_t *end, uint64_
     dec.seek(base, end, start_bit);
     const uint64_t last_bit = (uint64_t)(end - base) * 8u, upto = stop_bit < last_bit ? stop_bit : last_bit;
     r.sym.reserve((size_t)((upto > start_bit ? upto - start_bit : 0) / 8u) * 5u + 65536u);
-    r.status = dec.run(r.sym, stop_bit, (size_t)1 << 40, false, have_window, &r.stream_end, &r.uses_window);
+    // (a chunk of FASTQ text expands 4-5x; the caller sends members that compress far better than that down the serial path,
+    // so the bound only stops a damaged or hostile stream from asking for tens of gigabytes)
+    const size_t max_cells = (size_t)((upto > start_bit ? upto - start_bit : 0) / 8u) * 64u + ((size_t)64 << 20);
+    r.status = dec.run(r.sym, stop_bit, max_cells, false, have_window, &r.stream_end, &r.uses_window);
     r.end_bit = dec.bitpos();
 }
 
