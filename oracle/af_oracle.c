@@ -22,7 +22,10 @@
  * records this pass emits (functions.py:656-702 deal_cigar, :892-950
  * contact_reads); see oracle/ref_bridge.py and tests/golden/.  The positions
  * it reports on the reference's bundled sample are also checked against the
- * ground truth in the wgsim read names of that sample (tests/test_oracle.py).
+ * ground truth in the wgsim read names of that sample (tests/test_oracle.py),
+ * and every record of that sample attains the optimum of an exhaustive
+ * affine-gap DP under bwa-mem's scores and clip penalty (af_sw.c,
+ * tests/test_oracle_vs_sw.py).
  *
  * Semantics (frozen; DESIGN.md "Anchoring spec v1"):
  *   anchor a[0..G), read r[0..L): base codes 0..3 = A,C,G,T; 4 = N/other.
