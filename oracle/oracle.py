@@ -36,6 +36,9 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libaf_oracle.so"], stdout=subprocess.DEVNULL, env=env)
     if force or not os.path.exists(_SYNTH_SO) or os.path.getmtime(_SYNTH_SO) < max(os.path.getmtime(_SYNTH_SRC), os.path.getmtime(_SYNTH_HDR)):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libaf_synth.so"], stdout=subprocess.DEVNULL, env=env)
+    sw_so, sw_src = os.path.join(_HERE, "libaf_sw.so"), os.path.join(_HERE, "af_sw.c")   # exhaustive DP the oracle is checked against
+    if force or not os.path.exists(sw_so) or os.path.getmtime(sw_so) < os.path.getmtime(sw_src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libaf_sw.so"], stdout=subprocess.DEVNULL, env=env)
     return _SO
 
 
