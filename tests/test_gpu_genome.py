@@ -301,3 +301,48 @@ def test_bulk_cli_runs_the_contiguity_stage_when_given_a_genome(bundled, tmp_pat
     assert all(len(l.split("\t")) == 11 for l in got)
     assert os.path.exists(w + "_split_points_filtered.txt")
     g.close()
+
+
+def test_singlecell_cli_runs_the_contiguity_stage_per_cell(bundled, tmp_path):
+    """Single-cell layout with --file_ref_seq: every cell gets its <w>_anchored_reads.sam, and the union of the cells'
+    survivors is what the bulk run on the concatenation keeps (the filter judges each read on its own)."""
+    import gzip
+    from anchored_fusion_b200.cli import main_bulk, main_singlecell
+    d = str(tmp_path)
+    fa = os.path.join(d, "t.fa")
+    open(fa, "w").write(bundled["header"] + "\n" + bundled["anchor"] + "\n")
+    rng = np.random.default_rng(2)
+    gfa = os.path.join(d, "genome.fa")
+    hits = bundled["oracle_hits"]
+    whole = []
+    for h in [h for h in hits if int(h["clip_l"]) >= 20 or int(h["clip_r"]) >= 20][::4]:
+        rid = int(h["read_id"])
+        whole.append((bundled["seqs1"], bundled["seqs2"])[rid & 1][rid >> 1])
+    with open(gfa, "w") as fh:
+        fh.write(">chrG\n" + _rand_seq(rng, 3000) + bundled["anchor"] + _rand_seq(rng, 3000) + "\n>chrJ\n" + _rand_seq(rng, 200).join(whole) + "\n")
+    q = bundled["qual_char"] * bundled["read_len"]
+    n = len(bundled["seqs1"])
+
+    def write(prefix, sel):
+        with gzip.open(prefix + "_1.fastq.gz", "wt") as f1, gzip.open(prefix + "_2.fastq.gz", "wt") as f2:
+            for i in sel:
+                f1.write("@%s\n%s\n+\n%s\n" % (bundled["names1"][i], bundled["seqs1"][i], q))
+                f2.write("@%s\n%s\n+\n%s\n" % (bundled["names2"][i], bundled["seqs2"][i], q))
+    cells = os.path.join(d, "cells")
+    os.mkdir(cells)
+    parts = {"cellA": range(0, n, 3), "cellB": range(1, n, 3), "cellC": range(2, n, 3)}
+    for c, sel in parts.items():
+        write(os.path.join(cells, c), sel)
+    write(os.path.join(d, "all"), range(n))
+    out_sc, out_bulk = os.path.join(d, "sc"), os.path.join(d, "bulk")
+    assert main_singlecell(["--file_anchored_cds", fa, "--fastq_dir", cells, "--out_folder", out_sc, "--file_ref_seq", gfa, "--thread", "4"]) == 0
+    assert main_bulk(["--file_anchored_cds", fa, "--fastq1", os.path.join(d, "all_1.fastq.gz"), "--fastq2", os.path.join(d, "all_2.fastq.gz"),
+                      "--out_folder", out_bulk, "--file_ref_seq", gfa, "--thread", "4"]) == 0
+    bulk = open(os.path.join(out_bulk, "BCR_fusion", "work_dir", "BCR_fusion_anchored_reads.sam")).read().splitlines()
+    union = []
+    for c in parts:
+        w = os.path.join(out_sc, "BCR", "work_dir", c, "BCR_fusion")
+        assert os.path.exists(w + "_split_points_filtered.txt")
+        union += open(w + "_anchored_reads.sam").read().splitlines()
+    assert sorted(union) == sorted(bulk) and len(bulk) > 30
+    assert os.path.exists(gfa + ".af2bit")                         # the packed genome was cached beside the FASTA
