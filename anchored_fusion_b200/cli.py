@@ -123,6 +123,61 @@ def contiguity_stage(out_dir_name, gene, args):
         return sum(1 for _ in fh)
 
 
+class ContiguityBatcher:
+    """The contiguity stage for many (cell, gene) outputs at once: the 2-op reads of many cells share the passes over the
+    genome (one pass serves ~86 reads whoever they belong to; a 5 000-pair cell has a handful), the decision and the
+    files stay per cell.  Same files as contiguity_stage."""
+
+    def __init__(self, args, flush_reads=2048):
+        self.args, self.flush_reads = args, flush_reads
+        ref = getattr(args, 'file_ref_seq', '')
+        self.enabled = bool(ref) and os.path.isfile(ref)
+        self.items, self.n_reads = [], 0
+
+    def add(self, out_dir_name, gene):
+        if not self.enabled or os.path.exists(out_dir_name + '_anchored_reads.sam'):
+            return
+        from .bam import read_bam, sam_line
+        from .functions import two_op_records
+        recs = list(two_op_records([sam_line(r) for r in read_bam(out_dir_name + '_anchored_reads.bam')[2]]))
+        self.items.append((out_dir_name, gene, recs))
+        self.n_reads += len(recs)
+        if self.n_reads >= self.flush_reads:
+            self.flush()
+
+    def flush(self):
+        if not self.items:
+            return
+        from .functions import contact_reads, contiguity_filter
+        from .genome import genome_for
+        from .stage import resolve_device
+        g = genome_for(self.args.file_ref_seq, resolve_device(self.args.gpu_number))
+        seqs = [s for _, _, recs in self.items for _, s in recs]
+        hits = g.align([s if len(s) <= 256 else '' for s in seqs]) if seqs else []
+        by_read = {int(h['read_id']): h for h in hits}
+        base = 0
+        for out_dir_name, gene, recs in self.items:
+            mine = [dict_hit(by_read[base + i], i) for i in range(len(recs)) if base + i in by_read]
+            lines = g.sam_lines([t for t, _ in recs], [s for _, s in recs], mine)
+            base += len(recs)
+            out_sam = out_dir_name + '_anchored_reads.sam'
+            with open(out_sam + '.partial', 'w') as fo:
+                fo.writelines(contiguity_filter(lines))
+            os.replace(out_sam + '.partial', out_sam)
+            groups = contact_reads(out_sam, out_dir_name, self.args.file_ref_seq, self.args.thread)
+            with open(out_dir_name + '_split_points_filtered.txt', 'w') as o:
+                o.write('gene\tsplit_point\ttype\tsupport\tseq_left\tseq_right\n')
+                for gr in sorted(groups, key=lambda gr: (-gr.cnt, gr.breakpoint)):
+                    o.write('%s\t%d\t%s\t%d\t%s\t%s\n' % (gene, gr.breakpoint, gr.type_, gr.cnt, gr.seq_left, gr.seq_right))
+        self.items, self.n_reads = [], 0
+
+
+def dict_hit(h, local_id):
+    """a genome record re-addressed to its cell's own read numbering (Genome.sam_lines looks records up by read_id)"""
+    return {'read_id': local_id, 'pos': int(h['pos']), 'clip_l': int(h['clip_l']), 'm_len': int(h['m_len']),
+            'clip_r': int(h['clip_r']), 'score_strand': int(h['score_strand'])}
+
+
 def run_gene_sample(file_anchored_seq, gene, fastq1, fastq2, out_dir_name, args, gene_anchorer=None):
     done = out_dir_name + '_anchored_reads.bam'
     if os.path.exists(done) and os.path.exists(out_dir_name + '_realign_reads.bam'):
@@ -255,12 +310,15 @@ def main_singlecell(argv=None):
         # All of this rank's cells go through ONE reader: their files are decoded concurrently, packed back to
         # back into shared batches (1 M pairs per GPU pass instead of one pass per 5 k-pair cell) and every
         # batch is scanned for all genes while resident; the hit lists are split back per cell on the host.
+        batcher = ContiguityBatcher(args)          # with --file_ref_seq: the genome pass, shared by many cells per call
+
         def on_cell(cell, cell_stats):
             for gene, st in zip(gene_names, cell_stats):
                 write_split_points(st, gene, prefix_of(gene, cell) + '_split_points.txt')
-                contiguity_stage(prefix_of(gene, cell), gene, args)
+                batcher.add(prefix_of(gene, cell), gene)
 
         res = anchor_cells(gas, mine, prefix_of, thread=args.thread, on_cell=on_cell)
+        batcher.flush()
         n_pairs, n_cells = res['pairs'], res['cells']
         print('[anchoring] rank %d/%d: scan %.2f s, per-cell files %.2f s (%.2f ms per cell), %d reader threads'
               % (rank, world, res['seconds_scan'], res['seconds_write'], 1e3 * res['seconds_write'] / max(n_cells, 1), res['threads']))
