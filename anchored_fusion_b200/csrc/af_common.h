@@ -104,17 +104,29 @@ AF_HD bool af_neighbour_ok(const uint32_t (&w)[NW], const uint32_t *filt, uint32
     return ok;
 }
 
+// ---- sample positions -----------------------------------------------------------------------
+// A read of L bases is sampled at p_j = P0 + j*S with P0 = k - k' and S = k - k' + 1 (k = 19): any window of k matching
+// bases [q, q+k), 0 <= q <= L-k, has exactly one sample start in [q, q+S-1], and that sample ends at p_j + k' <= q + k --
+// inside the window.  Starting at P0 instead of 0 needs floor((L-k)/S) + 1 samples: 17 for 150 bases where the
+// zero-based grid needs 18, 11 instead of 12 for 101.  Every stage (scan, verify, extend, tail, host twin) uses these
+// two functions, so the sample grid is defined here only.
+AF_HD constexpr int af_sample0(int kp) { return 19 - kp; }
+AF_HD constexpr int af_nsamples(int L, int kp) { return L >= 19 ? (L - 19) / (20 - kp) + 1 : 0; }
+
 template <int W, int KP, int OFF, int J, int NP, int NPMIN, bool REFINE, bool BLOOM, int NW>
 AF_HD void af_scan_sample(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
                           uint32_t &acc) {
     if constexpr (J < NP) {
-        constexpr int S = 20 - KP;
-        uint32_t t = BLOOM ? af_bloom_probe(af_kmer_at<W, KP, OFF, J * S>(w), filt, fmul, nb)
-                           : af_filter_probe(af_kmer_at<W, KP, OFF, J * S>(w), filt, fmul, nb);
-        if (J >= NPMIN) t = J < nprobe ? t : 0u;
+        constexpr int S = 20 - KP, PJ = af_sample0(KP) + J * S;
+        uint32_t t = 0u;
+        // samples past NPMIN exist only for the longer reads this W can hold: a warp-uniform predicate around the
+        // probe, so that a sample the batch does not have costs no shared-memory wavefronts
+        if (J < NPMIN || J < nprobe)
+            t = BLOOM ? af_bloom_probe(af_kmer_at<W, KP, OFF, PJ>(w), filt, fmul, nb)
+                      : af_filter_probe(af_kmer_at<W, KP, OFF, PJ>(w), filt, fmul, nb);
         if constexpr (REFINE) {
             if (t & AF_F_HIGH) {                                             // rare: ~0.14 % of the samples
-                if (!af_neighbour_ok<W, KP, OFF, J * S>(w, filt, fmul, nb)) t = 0u;
+                if (!af_neighbour_ok<W, KP, OFF, PJ>(w, filt, fmul, nb)) t = 0u;
             }
         }
         acc |= t;
@@ -132,10 +144,9 @@ AF_HD void af_scan_sample(const uint32_t (&w)[NW], int nprobe, const uint32_t *f
 template <int W, int KP, int OFF, int NW, bool REFINE = false, bool BLOOM = false>
 AF_HD uint32_t af_scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul,
                               uint32_t nb) {
-    constexpr int S = 20 - KP;  // k = 19
-    constexpr int NP = (16 * W - KP) / S + 1;                                // samples when L == 16 W
+    constexpr int NP = af_nsamples(16 * W, KP);                              // samples when L == 16 W
     constexpr int LMIN = 16 * (W - 1) + 1;                                   // shortest L with this W
-    constexpr int NPMIN = LMIN >= KP ? (LMIN - KP) / S + 1 : 0;
+    constexpr int NPMIN = af_nsamples(LMIN, KP);
     uint32_t acc = 0;
     af_scan_sample<W, KP, OFF, 0, NP, NPMIN, REFINE, BLOOM>(w, nprobe, filt, fmul, nb, acc);
     return acc & AF_F_HIGH;

@@ -554,7 +554,7 @@ extern "C" int af_debug_scan_pair(const af_index_t *idx, const uint32_t *words, 
                                   int32_t with_neighbour_test, int32_t *flag1, int32_t *flag2) {
     const bool refine = with_neighbour_test != 0;
     if (!idx || !words || !flag1 || !flag2 || (idx->kp != 12 && idx->kp != 13) || idx->P.k != 19) { af_set_error("af_debug_scan_pair: bad argument"); return AF_ERR_ARG; }
-    const int nprobe = read_len >= idx->kp ? (read_len - idx->kp) / idx->stride + 1 : 0;
+    const int nprobe = af_nsamples(read_len, idx->kp);
     switch (words_per_read) {
         AF_HOST_SCAN_CASE(1) AF_HOST_SCAN_CASE(2) AF_HOST_SCAN_CASE(3) AF_HOST_SCAN_CASE(4) AF_HOST_SCAN_CASE(5)
         AF_HOST_SCAN_CASE(6) AF_HOST_SCAN_CASE(7) AF_HOST_SCAN_CASE(8) AF_HOST_SCAN_CASE(9) AF_HOST_SCAN_CASE(10)

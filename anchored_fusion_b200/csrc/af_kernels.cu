@@ -462,9 +462,9 @@ static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *
     if (lay.n_tiles == 0) return AF_OK;
     const int kp = d->kp;
     if (d->P.k != 19 || (kp != 12 && kp != 13)) { af_set_error("seed scan is built for k=19, k' in {12,13}"); return AF_ERR_ARG; }
-    // sample positions p = j*s with p + k' <= L (L = longest read of the batch)
+    // sample positions p_j = (k - k') + j*s (af_common.h); L = longest read of the batch
     int L = b->uniform_len > 0 ? b->uniform_len : b->max_read_len;
-    int nprobe = L >= kp ? (L - kp) / d->stride + 1 : 0;
+    int nprobe = af_nsamples(L, kp);
     long long n_tiles = lay.n_tiles;
     switch (lay.words_per_read) {
         AF_SCAN_CASE(1) AF_SCAN_CASE(2) AF_SCAN_CASE(3) AF_SCAN_CASE(4) AF_SCAN_CASE(5) AF_SCAN_CASE(6)
@@ -673,7 +673,7 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
          const uint8_t *__restrict__ anchor, int G, int K, uint8_t *__restrict__ keep,
          uint32_t *__restrict__ chunk_counts) {
     constexpr int S = 20 - KP;
-    constexpr int NPMAX = (AF_MAX_READ_LEN - KP) / S + 1;
+    constexpr int NPMAX = af_nsamples(AF_MAX_READ_LEN, KP);
     constexpr uint32_t kpmask = (1u << (2 * KP)) - 1u;
     const uint32_t ncand = min(counts[AF_CNT_FLAGGED], cand_cap);
     const int lane = threadIdx.x & 31;
@@ -694,7 +694,7 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
                 if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
             }
-            const int nprobe = r.L >= KP ? (r.L - KP) / S + 1 : 0;
+            const int nprobe = af_nsamples(r.L, KP);
             uint32_t w[17];
 #pragma unroll
             for (int t = 0; t < 16; t++) w[t] = t < W ? r.word(t) : 0u;
@@ -703,7 +703,7 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
             uint32_t mbits[NPMAX];
 #pragma unroll
             for (int j = 0; j < NPMAX; j++) {
-                const int o = 2 * j * S, wi = o >> 5;
+                const int o = 2 * (af_sample0(KP) + j * S), wi = o >> 5;
                 const uint32_t key = __funnelshift_r(w[wi], w[wi + 1], o & 31) & kpmask;
                 mbits[j] = j < nprobe ? ((member[key >> 5] >> (key & 31)) & 1u) : 0u;
             }
@@ -714,7 +714,7 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
             while (hit && !seeded) {
                 const int j = __ffsll((long long)hit) - 1;
                 hit &= hit - 1;
-                const int p = j * S, o = 2 * p;
+                const int p = af_sample0(KP) + j * S, o = 2 * p;
                 const uint32_t key = __funnelshift_r(r.word(o >> 5), (o >> 5) + 1 < W ? r.word((o >> 5) + 1) : 0u, o & 31) & kpmask;
                 if (r.nm) {   // a k'-mer that overlaps an N is no seed material
                     bool n = false;
@@ -786,7 +786,7 @@ k_verify_smem(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
                 if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
             }
-            const int np = r.L >= KP ? (r.L - KP) / S + 1 : 0;
+            const int np = af_nsamples(r.L, KP);
             // the read's words: whole quads (128-bit loads), then the W words it owns into shared memory
             const int q0 = r.wofs >> 2, q1 = (r.wofs + W - 1) >> 2;
             for (int q = q0; q <= q1; q++) {
@@ -801,7 +801,7 @@ k_verify_smem(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len
             sw[W * VT] = 0; sw[(W + 1) * VT] = 0; sw[(W + 2) * VT] = 0;
             unsigned long long hit = 0;
             for (int j = 0; j < np; j++) {                   // which samples pass the shared-memory filter
-                const int o = 2 * j * S, wi = o >> 5;
+                const int o = 2 * (af_sample0(KP) + j * S), wi = o >> 5;
                 const uint32_t key = __funnelshift_r(sw[wi * VT], sw[(wi + 1) * VT], o & 31) & kpmask;
                 uint32_t b, fp3;
                 af_filter_hash(key, fmul, nb, b, fp3);
@@ -811,7 +811,7 @@ k_verify_smem(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len
             while (hit && !seeded) {
                 const int j = __ffsll((long long)hit) - 1;
                 hit &= hit - 1;
-                const int p = j * S, o = 2 * p;
+                const int p = af_sample0(KP) + j * S, o = 2 * p;
                 const uint32_t key = __funnelshift_r(sw[(o >> 5) * VT], sw[((o >> 5) + 1) * VT], o & 31) & kpmask;
                 if (r.nm) {   // a k'-mer that overlaps an N is no seed material
                     bool n = false;
@@ -1051,10 +1051,10 @@ k_scan_verify(const uint4 *__restrict__ packed, long long n_tiles, long long n_p
                     while (lo < hi) { int mid = (lo + hi) >> 1; if (nread_ids[mid] < rid) lo = mid + 1; else hi = mid; }
                     if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
                 }
-                const int np = r.L >= KP ? (r.L - KP) / S + 1 : 0;
+                const int np = af_nsamples(r.L, KP);
                 unsigned long long hit = 0;
                 for (int j = 0; j < np; j++) {                           // which samples pass the filter
-                    const int o = 2 * j * S, wi = o >> 5;
+                    const int o = 2 * (af_sample0(KP) + j * S), wi = o >> 5;
                     const uint32_t key = __funnelshift_r(sw[wi * 32], sw[(wi + 1) * 32], o & 31) & kpmask;
                     uint32_t b, fp3;
                     af_filter_hash(key, fmul, nb, b, fp3);
@@ -1064,7 +1064,7 @@ k_scan_verify(const uint4 *__restrict__ packed, long long n_tiles, long long n_p
                 while (hit && !seeded) {
                     const int j = __ffsll((long long)hit) - 1;
                     hit &= hit - 1;
-                    const int p = j * S, o = 2 * p;
+                    const int p = af_sample0(KP) + j * S, o = 2 * p;
                     const uint32_t key = __funnelshift_r(sw[(o >> 5) * 32], sw[((o >> 5) + 1) * 32], o & 31) & kpmask;
                     if (r.nm) {   // a k'-mer that overlaps an N is no seed material
                         bool n = false;
@@ -1156,9 +1156,9 @@ k_extend(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
         }
         int best_sc = -1, best_qb = 0, best_qe = 0;
         uint32_t best_key = 0xFFFFFFFFu;
-        const int nprobe = L >= KP ? (KP == 12 ? (L - 12) >> 3 : (L - KP) / S) + 1 : 0;      // S == 20 - KP
+        const int nprobe = af_nsamples(L, KP);                                                    // S == 20 - KP
         for (int p0 = 0; p0 < nprobe; p0 += 32) {
-            const int pi = p0 + lane, p = pi * S;
+            const int pi = p0 + lane, p = af_sample0(KP) + pi * S;
             bool active = pi < nprobe;
             // this lane's k'-mer (forward read orientation)
             const int o = 2 * (active ? p : 0), wi = o >> 5;
@@ -1259,7 +1259,7 @@ static int fused_impl(const af_dev_index *d, const af_batch_t *b, const af_layou
                       uint32_t *counts, cudaStream_t st) {
     if (d->P.k != 19 || (d->kp != 12 && d->kp != 13)) { af_set_error("seed scan is built for k=19, k' in {12,13}"); return AF_ERR_ARG; }
     const int L = b->uniform_len > 0 ? b->uniform_len : b->max_read_len;
-    const int nprobe = L >= d->kp ? (L - d->kp) / d->stride + 1 : 0;
+    const int nprobe = af_nsamples(L, d->kp);
     switch (lay.words_per_read) {
         AF_FUSED_CASE(1) AF_FUSED_CASE(2) AF_FUSED_CASE(3) AF_FUSED_CASE(4) AF_FUSED_CASE(5) AF_FUSED_CASE(6)
         AF_FUSED_CASE(7) AF_FUSED_CASE(8) AF_FUSED_CASE(9) AF_FUSED_CASE(10) AF_FUSED_CASE(11) AF_FUSED_CASE(12)

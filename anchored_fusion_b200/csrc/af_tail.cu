@@ -54,9 +54,9 @@ __device__ __forceinline__ bool tail_extend(uint32_t rid, int L, uint32_t rw, ui
     const uint32_t kpmask = (1u << (2 * KP)) - 1u;
     int best_sc = -1, best_qb = 0, best_qe = 0;
     uint32_t best_key = 0xFFFFFFFFu;
-    const int nprobe = L >= KP ? (L - KP) / S + 1 : 0;
+    const int nprobe = af_nsamples(L, KP);
     for (int p0 = 0; p0 < nprobe; p0 += 32) {
-        const int pi = p0 + lane, p = pi * S;
+        const int pi = p0 + lane, p = af_sample0(KP) + pi * S;
         bool active = pi < nprobe;
         const int o = 2 * (active ? p : 0), wi = o >> 5;
         uint32_t w0 = __shfl_sync(FULL, rw, wi), w1 = __shfl_sync(FULL, rw, min(wi + 1, 31));
@@ -145,11 +145,11 @@ __device__ __forceinline__ bool tail_prefilter(const uint32_t *sw, int VT, int L
                                                uint32_t fmul, uint32_t nb, int K) {
     constexpr int S = 20 - KP;
     constexpr uint32_t kpmask = (1u << (2 * KP)) - 1u;
-    const int np = L >= KP ? (L - KP) / S + 1 : 0;
+    const int np = af_nsamples(L, KP);
     unsigned long long hit = 0;
 #pragma unroll 6
     for (int j = 0; j < np; j++) {                       // which samples pass the shared-memory filter
-        const int o = 2 * j * S, wi = o >> 5;
+        const int o = 2 * (af_sample0(KP) + j * S), wi = o >> 5;
         const uint32_t key = __funnelshift_r(sw[wi * VT], sw[(wi + 1) * VT], o & 31) & kpmask;
         uint32_t b, fp3;
         af_filter_hash(key, fmul, nb, b, fp3);
@@ -159,7 +159,7 @@ __device__ __forceinline__ bool tail_prefilter(const uint32_t *sw, int VT, int L
     while (hit) {
         const int j = __ffsll((long long)hit) - 1;
         hit &= hit - 1;
-        const int p = j * S;
+        const int p = af_sample0(KP) + j * S;
         if (nm) {                                        // a k'-mer that overlaps an N is no seed material
             bool n = false;
             for (int t = 0; t < KP; t++) n |= (nm[(p + t) >> 5] >> ((p + t) & 31)) & 1u;

@@ -48,7 +48,8 @@ def expected_flags(index, codes, lens=None, refine=False):
         v = filt[b] ^ fp3
         return (((v - np.uint64(0x40100401)) & ~v & np.uint64(0xA0080200)) & np.uint64(0xFFFFFFFF)) != 0
 
-    for p in range(0, Lmax - KP + 1, S):          # the kernel samples up to the batch's longest read
+    # sample grid of af_common.h: p_j = (19 - k') + j*S, floor((L - 19) / S) + 1 samples, L = the batch's longest read
+    for p in range(19 - KP, Lmax - KP + 1, S):
         hit = probe(p)
         if refine and hit.any():                  # neighbour test (af_neighbour_ok)
             ok = np.zeros(n, bool)
