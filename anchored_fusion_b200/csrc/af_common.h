@@ -118,12 +118,23 @@ AF_HD void af_scan_sample(const uint32_t (&w)[NW], int nprobe, const uint32_t *f
                           uint32_t &acc) {
     if constexpr (J < NP) {
         constexpr int S = 20 - KP, PJ = af_sample0(KP) + J * S;
-        uint32_t t = 0u;
-        // samples past NPMIN exist only for the longer reads this W can hold: a warp-uniform predicate around the
-        // probe, so that a sample the batch does not have costs no shared-memory wavefronts
-        if (J < NPMIN || J < nprobe)
-            t = BLOOM ? af_bloom_probe(af_kmer_at<W, KP, OFF, PJ>(w), filt, fmul, nb)
-                      : af_filter_probe(af_kmer_at<W, KP, OFF, PJ>(w), filt, fmul, nb);
+        // samples past NPMIN exist only for the longer reads this W can hold: a warp-uniform predicate on the
+        // load alone (the arithmetic around it stays branch-free), so that a sample the batch does not have costs
+        // no shared-memory wavefronts
+        uint32_t t;
+        if constexpr (BLOOM) {
+            const uint32_t lo = af_kmer_at<W, KP, OFF, PJ>(w) * fmul;
+            uint32_t word = 0u;
+            if (J < NPMIN || J < nprobe) word = filt[af_umulhi(lo, nb)];
+            t = (~word & af_bloom_mask(lo)) ? 0u : AF_F_HIGH;
+        } else {
+            uint32_t b, fp3;
+            af_filter_hash(af_kmer_at<W, KP, OFF, PJ>(w), fmul, nb, b, fp3);
+            uint32_t word = ~fp3;                                            // no field can match
+            if (J < NPMIN || J < nprobe) word = filt[b];
+            const uint32_t v = word ^ fp3;
+            t = (v - AF_F_ONES) & ~v;
+        }
         if constexpr (REFINE) {
             if (t & AF_F_HIGH) {                                             // rare: ~0.14 % of the samples
                 if (!af_neighbour_ok<W, KP, OFF, PJ>(w, filt, fmul, nb)) t = 0u;
