@@ -52,8 +52,9 @@ GENOME_HIT_DTYPE = np.dtype([("pos", "<i8"), ("read_id", "<u4"), ("clip_l", "<u2
                              ("score_strand", "<u2"), ("reserved", "<u4")])
 GENOME_SEP = 256
 CNT_FLAGGED, CNT_HITS, CNT_STATUS, CNT_SEEDED, N_COUNTS = 0, 1, 2, 3, 8
-NMASK_WORDS = 8
-MAX_READ_LEN = 256
+NMASK_WORDS = 16
+MAX_READ_LEN = 512
+GENOME_MAX_READ_LEN = 256
 
 # every symbol include/anchored_fusion.h declares: name -> (restype, argtypes)
 P = ctypes.POINTER

@@ -105,13 +105,15 @@ AF_HD bool af_neighbour_ok(const uint32_t (&w)[NW], const uint32_t *filt, uint32
 }
 
 // ---- sample positions -----------------------------------------------------------------------
-// A read of L bases is sampled at p_j = P0 + j*S with P0 = k - k' and S = k - k' + 1 (k = 19): any window of k matching
-// bases [q, q+k), 0 <= q <= L-k, has exactly one sample start in [q, q+S-1], and that sample ends at p_j + k' <= q + k --
-// inside the window.  Starting at P0 instead of 0 needs floor((L-k)/S) + 1 samples: 17 for 150 bases where the
-// zero-based grid needs 18, 11 instead of 12 for 101.  Every stage (scan, verify, extend, tail, host twin) uses these
-// two functions, so the sample grid is defined here only.
-AF_HD constexpr int af_sample0(int kp) { return 19 - kp; }
-AF_HD constexpr int af_nsamples(int L, int kp) { return L >= 19 ? (L - 19) / (20 - kp) + 1 : 0; }
+// A read of L bases is sampled at p_j = P0 + j*S, S = k - k' + 1 (k = 19): a window of k matching bases [q, q+k),
+// 0 <= q <= L-k, contains the sample that starts in [q, q+S-1] (it ends at p_j + k' <= q + k), so the grid needs
+// P0 <= S-1 and a last sample at or beyond L-k: ceil((L-k-P0)/S) + 1 samples.  P0 = 0 takes 18 samples for 150 bases,
+// any P0 in 3..7 takes 17 (11 instead of 12 for 101 bases).  For k' = 12, P0 = 4 puts the samples at bit offsets 8 and
+// 24 of the packed words: every other k'-mer is one shift of one word (8 + 24 = 32 bits, no mask, no funnel).
+// Every stage (scan, verify, extend, tail, host twin) takes the grid from these two functions.
+AF_HD constexpr int af_sample0(int kp) { return kp == 12 ? 4 : 19 - kp; }
+AF_HD constexpr int af_lmin(int W) { return 16 * (W > 16 ? W - 4 : W - 1) + 1; }   // shortest longest-read of a batch laid out with W words (af_layout rounds W to 20, 24, 28, 32 beyond 16)
+AF_HD constexpr int af_nsamples(int L, int kp) { return L >= 19 ? (L - 19 - af_sample0(kp) + (20 - kp) - 1) / (20 - kp) + 1 : 0; }
 
 template <int W, int KP, int OFF, int J, int NP, int NPMIN, bool REFINE, bool BLOOM, int NW>
 AF_HD void af_scan_sample(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
@@ -156,11 +158,36 @@ template <int W, int KP, int OFF, int NW, bool REFINE = false, bool BLOOM = fals
 AF_HD uint32_t af_scan_read(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul,
                               uint32_t nb) {
     constexpr int NP = af_nsamples(16 * W, KP);                              // samples when L == 16 W
-    constexpr int LMIN = 16 * (W - 1) + 1;                                   // shortest L with this W
-    constexpr int NPMIN = af_nsamples(LMIN, KP);
+    constexpr int NPMIN = af_nsamples(af_lmin(W), KP);                       // af_lmin: shortest L with this W
     uint32_t acc = 0;
     af_scan_sample<W, KP, OFF, 0, NP, NPMIN, REFINE, BLOOM>(w, nprobe, filt, fmul, nb, acc);
     return acc & AF_F_HIGH;
+}
+
+// Both reads of a pair (w[0..W) and w[W..2W)), as the production scan runs them: the samples every read length of
+// this W has are branch-free; the last few, which only the longer lengths have, sit behind warp-uniform branches
+// shared by the two reads -- a sample the batch lacks costs neither arithmetic nor shared-memory wavefronts.
+// Same flags as af_scan_read on each read.
+template <int W, int KP, int J, int NP, bool BLOOM, int NW>
+AF_HD void af_scan_pair_tail(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
+                             uint32_t &acc1, uint32_t &acc2) {
+    if constexpr (J < NP) {
+        if (J < nprobe) {
+            af_scan_sample<W, KP, 0, J, J + 1, J + 1, false, BLOOM>(w, nprobe, filt, fmul, nb, acc1);
+            af_scan_sample<W, KP, W, J, J + 1, J + 1, false, BLOOM>(w, nprobe, filt, fmul, nb, acc2);
+            af_scan_pair_tail<W, KP, J + 1, NP, BLOOM>(w, nprobe, filt, fmul, nb, acc1, acc2);
+        }
+    }
+}
+template <int W, int KP, int NW, bool BLOOM = false>
+AF_HD void af_scan_pair(const uint32_t (&w)[NW], int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
+                        uint32_t &a1, uint32_t &a2) {
+    constexpr int NP = af_nsamples(16 * W, KP), NPMIN = af_nsamples(af_lmin(W), KP);
+    uint32_t acc1 = 0, acc2 = 0;
+    af_scan_sample<W, KP, 0, 0, NPMIN, NPMIN, false, BLOOM>(w, nprobe, filt, fmul, nb, acc1);
+    af_scan_sample<W, KP, W, 0, NPMIN, NPMIN, false, BLOOM>(w, nprobe, filt, fmul, nb, acc2);
+    af_scan_pair_tail<W, KP, NPMIN, NP, BLOOM>(w, nprobe, filt, fmul, nb, acc1, acc2);
+    a1 = acc1 & AF_F_HIGH; a2 = acc2 & AF_F_HIGH;
 }
 
 // ---- exact table (global memory): open addressing, duplicates allowed ---------------------

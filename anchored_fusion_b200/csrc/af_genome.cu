@@ -485,8 +485,8 @@ extern "C" int af_genome_align(af_genome_t *g, const char *reads, const int64_t 
     if (!g || !offs || n_reads < 0 || !n_hits_out || (n_reads && (!reads || !hits_out)) || n_reads >= (1 << 23)) { af_set_error("af_genome_align: bad argument"); return AF_ERR_ARG; }
     af_params_t Pp;
     if (params) Pp = *params; else af_default_params(&Pp);
-    if (Pp.k != 19 || Pp.A <= 0 || Pp.B < 0 || Pp.X < 0 || (int64_t)2 * Pp.A * AF_MAX_READ_LEN + 1 > 65535 || Pp.clip5 < 0 || Pp.clip3 < 0) {
-        af_set_error("af_genome_align: unsupported parameters (k must be 19, 2*A*%d+1 must fit 16 bits)", AF_MAX_READ_LEN);
+    if (Pp.k != 19 || Pp.A <= 0 || Pp.B < 0 || Pp.X < 0 || (int64_t)2 * Pp.A * AF_GENOME_MAX_READ_LEN + 1 > 65535 || Pp.clip5 < 0 || Pp.clip3 < 0) {
+        af_set_error("af_genome_align: unsupported parameters (k must be 19, 2*A*%d+1 must fit 16 bits)", AF_GENOME_MAX_READ_LEN);
         return AF_ERR_ARG;
     }
     af_genome_stats_t S;
@@ -502,10 +502,10 @@ extern "C" int af_genome_align(af_genome_t *g, const char *reads, const int64_t 
     const int64_t nq = 2 * n_reads;
     std::vector<uint32_t> qpk((size_t)nq * GQ_WORDS, 0u), qnm((size_t)nq * GQ_NWORDS, 0u);
     std::vector<uint16_t> qlen((size_t)nq, 0);
-    std::vector<uint8_t> codes(AF_MAX_READ_LEN);
+    std::vector<uint8_t> codes(AF_GENOME_MAX_READ_LEN);
     for (int64_t j = 0; j < n_reads; j++) {
         const int64_t L = offs[j + 1] - offs[j];
-        if (L < 0 || L > AF_MAX_READ_LEN) { af_set_error("af_genome_align: read %lld has %lld bases, the limit is %d", (long long)j, (long long)L, AF_MAX_READ_LEN); return AF_ERR_ARG; }
+        if (L < 0 || L > AF_GENOME_MAX_READ_LEN) { af_set_error("af_genome_align: read %lld has %lld bases, the limit is %d", (long long)j, (long long)L, AF_GENOME_MAX_READ_LEN); return AF_ERR_ARG; }
         for (int64_t i = 0; i < L; i++) codes[(size_t)i] = af_code_of(reads[offs[j] + i]);
         for (int s = 0; s < 2; s++) {
             const size_t q = (size_t)(2 * j + s);

@@ -226,6 +226,7 @@ extern "C" int af_layout(int32_t max_read_len, int64_t n_pairs, af_layout_t *out
     }
     out->max_read_len = max_read_len;
     out->words_per_read = (max_read_len + 15) / 16;
+    if (out->words_per_read > 16) out->words_per_read = (out->words_per_read + 3) & ~3;   // long reads: the scan is built for W = 20, 24, 28, 32
     out->quads_per_pair = (2 * out->words_per_read + 3) / 4;
     out->reserved = 0;
     out->n_pairs = n_pairs;
@@ -256,12 +257,13 @@ extern "C" int af_wire_from_packed(const void *packed, int32_t L, int64_t n_pair
     for (int64_t tile = 0; tile < lay.n_tiles; tile++)
         for (int lane = 0; lane < 32; lane++) {
             const uint32_t *pb = in + (tile * Q * 32 + lane) * 4;
-            uint32_t o[33];
+            uint32_t o[2 * AF_MAX_READ_LEN / 16 + 1];
             memset(o, 0, sizeof(o));
             int bit = 0;
             for (int m = 0; m < 2; m++)
                 for (int t = 0; t < W; t++) {
-                    const int wi = m * W + t, nb = std::min(32, 2 * L - 32 * t);
+                    const int wi = m * W + t, nb = std::max(0, std::min(32, 2 * L - 32 * t));
+                    if (nb == 0) continue;
                     uint32_t v = pb[(wi >> 2) * 128 + (wi & 3)];
                     if (nb < 32) v &= (1u << nb) - 1u;
                     const int a = bit >> 5, sh = bit & 31;
@@ -289,10 +291,13 @@ extern "C" int af_wire_to_packed(const void *wire, int32_t L, int64_t n_pairs, i
                 uint32_t word = 0;
                 if (wi < 2 * W) {
                     const int m = wi >= W, t = wi - m * W, nb = std::min(32, 2 * L - 32 * t), bit = m * 2 * L + 32 * t;
-                    const int a = bit >> 5, sh = bit & 31;
-                    const uint32_t lo = in[(tile * NW + a) * 32 + lane], hi = a + 1 < NW ? in[(tile * NW + a + 1) * 32 + lane] : 0u;
-                    const uint32_t v = af_funnel_r(lo, hi, sh), mask = nb >= 32 ? 0xFFFFFFFFu : (1u << nb) - 1u;
-                    word = (v & mask) | (padw & ~mask);
+                    word = padw;                            // nb <= 0: a word past the read (W is rounded up for long reads)
+                    if (nb > 0) {
+                        const int a = bit >> 5, sh = bit & 31;
+                        const uint32_t lo = in[(tile * NW + a) * 32 + lane], hi = a + 1 < NW ? in[(tile * NW + a + 1) * 32 + lane] : 0u;
+                        const uint32_t v = af_funnel_r(lo, hi, sh), mask = nb >= 32 ? 0xFFFFFFFFu : (1u << nb) - 1u;
+                        word = (v & mask) | (padw & ~mask);
+                    }
                 }
                 pb[(wi >> 2) * 128 + (wi & 3)] = word;
             }
@@ -397,7 +402,7 @@ void af_pack_range(const SeqRef *r, int m, int64_t p0, int64_t p1, int64_t n_pai
             if (st.ulen == -1) st.ulen = len; else if (st.ulen != len) st.ulen = -2;
             if (lens_out) lens_out[2 * p + m] = (uint16_t)len;
         }
-        uint32_t nm[AF_NMASK_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t nm[AF_NMASK_WORDS] = {0};
         uint32_t anyn = 0;
         for (int t = 0; t < W; t++) {
             const int i0 = 16 * t, cnt = len - i0 < 16 ? (len - i0 > 0 ? len - i0 : 0) : 16;
@@ -559,7 +564,7 @@ extern "C" int af_debug_scan_pair(const af_index_t *idx, const uint32_t *words, 
         AF_HOST_SCAN_CASE(1) AF_HOST_SCAN_CASE(2) AF_HOST_SCAN_CASE(3) AF_HOST_SCAN_CASE(4) AF_HOST_SCAN_CASE(5)
         AF_HOST_SCAN_CASE(6) AF_HOST_SCAN_CASE(7) AF_HOST_SCAN_CASE(8) AF_HOST_SCAN_CASE(9) AF_HOST_SCAN_CASE(10)
         AF_HOST_SCAN_CASE(11) AF_HOST_SCAN_CASE(12) AF_HOST_SCAN_CASE(13) AF_HOST_SCAN_CASE(14) AF_HOST_SCAN_CASE(15)
-        AF_HOST_SCAN_CASE(16)
+        AF_HOST_SCAN_CASE(16) AF_HOST_SCAN_CASE(20) AF_HOST_SCAN_CASE(24) AF_HOST_SCAN_CASE(28) AF_HOST_SCAN_CASE(32)
     }
     af_set_error("af_debug_scan_pair: words_per_read %d", words_per_read);
     return AF_ERR_ARG;

@@ -109,8 +109,8 @@ __device__ __forceinline__ void scan_tile(const uint32_t (&w)[4 * Q], long long 
                                           int nprobe, const uint32_t *filt, uint32_t fmul, uint32_t nb,
                                           uint2 *__restrict__ flags, uint32_t *cc_local, long long chunk0,
                                           uint32_t *__restrict__ chunk_counts) {
-    uint32_t a1 = af_scan_read<W, KP, 0, 4 * Q, false, BLOOM>(w, nprobe, filt, fmul, nb);
-    uint32_t a2 = af_scan_read<W, KP, W, 4 * Q, false, BLOOM>(w, nprobe, filt, fmul, nb);
+    uint32_t a1, a2;
+    af_scan_pair<W, KP, 4 * Q, BLOOM>(w, nprobe, filt, fmul, nb, a1, a2);
     const uint32_t vm = tile_valid_mask(tile, n_pairs);
     const uint32_t b1 = __ballot_sync(FULL, a1 != 0) & vm, b2 = __ballot_sync(FULL, a2 != 0) & vm;
     if (lane == 0) {
@@ -402,15 +402,16 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     return AF_OK;
 }
 
-static int scan_grid(const af_dev_index *d, long long n_tiles) {
-    const int nwarps = g_scan_threads / 32;
+static int scan_grid(const af_dev_index *d, long long n_tiles, int threads = 0) {
+    const int nwarps = (threads ? threads : g_scan_threads) / 32;
     const long long want = (n_tiles + nwarps - 1) / nwarps;
     return (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
 }
 
 template <int W, int KP, int MAXT, bool PF, bool RQ, bool EMIT, bool BLOOM = false>
 static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
-                       uint32_t *chunk_counts, uint32_t *counts, const af_emit &E, cudaStream_t st) {
+                       uint32_t *chunk_counts, uint32_t *counts, const af_emit &E, cudaStream_t st, int threads = 0) {
+    if (!threads) threads = g_scan_threads;
     size_t smem = (size_t)d->nb * 4;
     static bool attr_set[64] = {false};  // per device
     if (!attr_set[d->device & 63]) {
@@ -418,8 +419,8 @@ static int launch_scan(const af_dev_index *d, const af_batch_t *b, long long n_t
         if (rc) return rc;
         attr_set[d->device & 63] = true;
     }
-    const int grid = scan_grid(d, n_tiles);
-    k_seed_scan<W, KP, MAXT, PF, RQ, EMIT, BLOOM><<<grid, g_scan_threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
+    const int grid = scan_grid(d, n_tiles, threads);
+    k_seed_scan<W, KP, MAXT, PF, RQ, EMIT, BLOOM><<<grid, threads, smem, st>>>((const uint4 *)b->packed, n_tiles, b->n_pairs, nprobe,
                                                                                d->d_filter, d->fmul, d->nb, (uint2 *)flags, chunk_counts, counts, E);
     g_launches++;
     AF_CUDA(cudaGetLastError());
@@ -437,6 +438,23 @@ static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long lon
     if (rq) return launch_scan<W, KP, AF_SCAN_BOUND, true, true, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st);
     return launch_scan<W, KP, AF_SCAN_BOUND, true, false, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st);
 }
+
+// Reads of 257..512 bases (W = 20, 24, 28, 32; af_layout rounds W up to a multiple of 4 beyond 16): the plain scan
+// without the register double buffer -- a pair alone is up to 64 registers -- on 384 threads.  2x300 MiSeq runs and
+// merged pairs are small next to the 2x150 bulk, so this instance is built for coverage, not tuned.
+static const int AF_LONG_SCAN_THREADS = 384;
+template <int W, int KP>
+static int launch_scan_long(const af_dev_index *d, const af_batch_t *b, long long n_tiles, int nprobe, uint32_t *flags,
+                            uint32_t *cc, uint32_t *counts, bool rq, const af_emit *emit, cudaStream_t st) {
+    if (rq || emit) { af_set_error("seed scan: reads beyond 256 bases run the plain scan only"); return AF_ERR_ARG; }
+    const int threads = g_scan_threads < AF_LONG_SCAN_THREADS ? g_scan_threads : AF_LONG_SCAN_THREADS;
+    return d->bloom ? launch_scan<W, KP, AF_LONG_SCAN_THREADS, false, false, false, true>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st, threads)
+                    : launch_scan<W, KP, AF_LONG_SCAN_THREADS, false, false, false, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st, threads);
+}
+#define AF_SCAN_CASE_LONG(WW)                                                                                  \
+    case WW:                                                                                                   \
+        return kp == 12 ? launch_scan_long<WW, 12>(d, b, n_tiles, nprobe, flags, cc, counts, rq, emit, st)     \
+                        : launch_scan_long<WW, 13>(d, b, n_tiles, nprobe, flags, cc, counts, rq, emit, st);
 
 #define AF_SCAN_CASE(WW)                                                                                       \
     case WW:                                                                                                   \
@@ -470,6 +488,7 @@ static int seed_scan_impl(const af_dev_index *d, const af_batch_t *b, uint32_t *
         AF_SCAN_CASE(1) AF_SCAN_CASE(2) AF_SCAN_CASE(3) AF_SCAN_CASE(4) AF_SCAN_CASE(5) AF_SCAN_CASE(6)
         AF_SCAN_CASE(7) AF_SCAN_CASE(8) AF_SCAN_CASE(9) AF_SCAN_CASE(10) AF_SCAN_CASE(11) AF_SCAN_CASE(12)
         AF_SCAN_CASE(13) AF_SCAN_CASE(14) AF_SCAN_CASE(15) AF_SCAN_CASE(16)
+        AF_SCAN_CASE_LONG(20) AF_SCAN_CASE_LONG(24) AF_SCAN_CASE_LONG(28) AF_SCAN_CASE_LONG(32)
     }
     af_set_error("unsupported words_per_read %d", lay.words_per_read);
     return AF_ERR_ARG;
@@ -664,7 +683,7 @@ k_hit_scatter(const uint4 *__restrict__ slots, uint32_t cap, const uint32_t *__r
 // diagonal holds >= k consecutive matches: exactly the SEEDED predicate of the spec, so
 // k_extend only ever sees reads it has to extend.
 // ------------------------------------------------------------------------------------------
-template <int KP>
+template <int KP, int WMAX = 16>                        // WMAX = 32: the long-read instance (reads of 257..512 bases)
 __global__ void __launch_bounds__(256)
 k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, const uint16_t *__restrict__ lens,
          const uint32_t *__restrict__ nread_ids, const uint32_t *__restrict__ nmask, int n_nreads,
@@ -673,7 +692,7 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
          const uint8_t *__restrict__ anchor, int G, int K, uint8_t *__restrict__ keep,
          uint32_t *__restrict__ chunk_counts) {
     constexpr int S = 20 - KP;
-    constexpr int NPMAX = af_nsamples(AF_MAX_READ_LEN, KP);
+    constexpr int NPMAX = af_nsamples(16 * WMAX, KP);        // <= 63, the hit bitmap below is 64 bits
     constexpr uint32_t kpmask = (1u << (2 * KP)) - 1u;
     const uint32_t ncand = min(counts[AF_CNT_FLAGGED], cand_cap);
     const int lane = threadIdx.x & 31;
@@ -695,10 +714,10 @@ k_verify(const uint32_t *__restrict__ packed, int W, int Q, int uniform_len, con
                 if (lo < n_nreads && nread_ids[lo] == rid) r.nm = nmask + (size_t)lo * AF_NMASK_WORDS;
             }
             const int nprobe = af_nsamples(r.L, KP);
-            uint32_t w[17];
+            uint32_t w[WMAX + 1];
 #pragma unroll
-            for (int t = 0; t < 16; t++) w[t] = t < W ? r.word(t) : 0u;
-            w[16] = 0;
+            for (int t = 0; t < WMAX; t++) w[t] = t < W ? r.word(t) : 0u;
+            w[WMAX] = 0;
             // phase 1: membership bit of every sample; all loads are independent
             uint32_t mbits[NPMAX];
 #pragma unroll
@@ -1299,7 +1318,7 @@ static WsLayout ws_layout(long long n_pairs, long long cand_cap, int max_read_le
     o = u0;
     w.r_max = (uint32_t)(n_tiles / AF_REG_TILES + 1 + 256);
     w.pool_chunks = (uint32_t)((cand_cap + AF_CHUNK - 1) / AF_CHUNK + 24ll * w.r_max + 1);
-    w.rq = af_rec_quads((max_read_len + 15) / 16);
+    w.rq = af_rec_quads(max_read_len > 256 ? 16 : (max_read_len + 15) / 16);   // reads beyond 256 bases never take the candidate-stream path
     w.ctl = o; w.ctl_bytes = align256((16 + 2 * (size_t)w.r_max) * 4); o += w.ctl_bytes;   // [0] pool counter, [16..) dir_count[R], region_state[R]: zeroed per call
     w.dir = o; o += align256((size_t)w.r_max * AF_DIR_CAP * 4);
     w.chunk_hits = o; o += align256((size_t)w.pool_chunks * 4);
@@ -1338,7 +1357,8 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     uint4 *slots = (uint4 *)(ws + w.slots);
     AF_CUDA(cudaMemsetAsync(d_counts, 0, AF_N_COUNTS * sizeof(uint32_t), st));
     if (lay.n_tiles == 0) return AF_OK;
-    if (g_stream && !g_fused && g_middle == 7 && !d->saturated) {
+    const bool long_reads = lay.words_per_read > 16;        // 257..512 bases: plain scan, bitmap verify, base-by-base extension masks
+    if (g_stream && !g_fused && g_middle == 7 && !d->saturated && !long_reads) {
         // candidate-stream path: the scan emits the flagged reads, k_tail does the rest -- 2 kernels
         const int grid = scan_grid(d, lay.n_tiles);
         const int m = (int)((lay.n_tiles + (long long)grid * AF_REG_TILES - 1) / ((long long)grid * AF_REG_TILES));
@@ -1376,7 +1396,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     const int sg2 = (int)(w.nch2 < (uint32_t)scatter_grid ? w.nch2 : scatter_grid);
     cudaEvent_t ev;
     prof_mark(&ev, st);
-    if (g_fused && !d->bloom) {
+    if (g_fused && !d->bloom && !long_reads) {
         // fused: seed scan + verify in one warp-specialised kernel -> seeded flag words
         AF_CUDA(cudaMemsetAsync(flags, 0, (size_t)lay.n_tiles * 8, st));
         rc = fused_impl(d, b, lay, flags, cc1, d_counts, st);
@@ -1389,7 +1409,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
         prof_mark(&ev, st);
         g_launches -= 2;                                    // this path has 4 kernels, the code below counts 5 more
     } else {
-    const bool rq = g_middle == 11 && !d->saturated;
+    const bool rq = g_middle == 11 && !d->saturated && !long_reads;
     rc = seed_scan_impl(d, b, flags, cc1, d_counts, rq, nullptr, st);
     if (rc) return rc;
     prof_span(ev, st, ST_SCAN);
@@ -1415,6 +1435,15 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     prof_span(ev, st, ST_COMPACT1);
     prof_mark(&ev, st);
     {
+    if (lay.words_per_read > 16) {                          // long reads (257..512 bases): the bitmap kernel with 32 words per read
+        long long vthreads = cand_cap < (long long)d->num_sms * 2048 ? cand_cap : (long long)d->num_sms * 2048;
+        const unsigned vgrid = (unsigned)((vthreads + 255) / 256);
+#define AF_VERIFY_LONG_ARGS (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, \
+        b->nread_ids, b->nmask, (int)b->n_nreads, cand, d_counts, (uint32_t)cand_cap, d->d_member, d->d_table,         \
+        d->tmask, d->d_anchor, d->G, d->P.k, keep, cc2
+        if (d->kp == 12) k_verify<12, 32><<<vgrid, 256, 0, st>>>(AF_VERIFY_LONG_ARGS);
+        else k_verify<13, 32><<<vgrid, 256, 0, st>>>(AF_VERIFY_LONG_ARGS);
+    } else
     if (g_verify_smem && !d->bloom) {                      // (a Bloom index's half-size fingerprint copy is saturated: k_verify's exact bitmap instead)
         const size_t vsmem = ((size_t)d->nb2 + (size_t)(lay.words_per_read + 3) * 1024) * 4;
         static bool vattr[64][2] = {{false}};
@@ -1451,7 +1480,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     k_extend<<<ext_blocks, 256, 0, st>>>((const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair,
                                          b->uniform_len, b->lens, b->nread_ids, b->nmask, (int)b->n_nreads, cand2,
                                          d_counts, (uint32_t)cand_cap, d->d_table, d->tmask, d->d_anchor, d->G, d->kp,
-                                         d->stride, P, slots, cc3, d_counts + AF_CNT_SCRATCH, d->d_apkp[0], d->d_apkp[1], d->d_apn[0], d->d_apn[1], g_walk);
+                                         d->stride, P, slots, cc3, d_counts + AF_CNT_SCRATCH, d->d_apkp[0], d->d_apkp[1], d->d_apn[0], d->d_apn[1], long_reads ? 0 : g_walk);   // the word-parallel mask is built for 256 positions
     prof_span(ev, st, ST_EXTEND);
     prof_mark(&ev, st);
     if (sink) k_hit_scatter<true><<<sg2, CB_THREADS, 0, st>>>(slots, (uint32_t)cand_cap, cc3, (uint4 *)d_hits, (uint32_t)hits_cap, d_counts, *sink);

@@ -44,10 +44,13 @@ k_wire_expand(const uint32_t *__restrict__ wire, long long n_tiles, int L, int W
             uint32_t word = 0u;
             if (wi < 2 * W) {
                 const int m = wi >= W, t = wi - m * W, nb = min(32, 2 * L - 32 * t), bit = m * 2 * L + 32 * t;
-                const int a = bit >> 5, sh = bit & 31;
-                const uint32_t lo = __ldg(src + a * 32), hi = a + 1 < NW ? __ldg(src + (a + 1) * 32) : 0u;
-                const uint32_t v = __funnelshift_r(lo, hi, sh), mask = nb >= 32 ? 0xFFFFFFFFu : (1u << nb) - 1u;
-                word = (v & mask) | (padw & ~mask);
+                word = padw;                                // nb <= 0: a word past the read (W is rounded up for long reads)
+                if (nb > 0) {
+                    const int a = bit >> 5, sh = bit & 31;
+                    const uint32_t lo = __ldg(src + a * 32), hi = a + 1 < NW ? __ldg(src + (a + 1) * 32) : 0u;
+                    const uint32_t v = __funnelshift_r(lo, hi, sh), mask = nb >= 32 ? 0xFFFFFFFFu : (1u << nb) - 1u;
+                    word = (v & mask) | (padw & ~mask);
+                }
             }
             o[c] = word;
         }

@@ -140,6 +140,6 @@ def genome_sam(f_ref, fasta_records, device=0):
     g = genome_for(f_ref, device)
     names = [r[0] for r in fasta_records]
     seqs = [r[1] for r in fasta_records]
-    usable = [len(s) <= _lib.MAX_READ_LEN for s in seqs]
+    usable = [len(s) <= _lib.GENOME_MAX_READ_LEN for s in seqs]
     hits = g.align([s if ok else "" for s, ok in zip(seqs, usable)])
     return g.sam_lines(names, seqs, hits)

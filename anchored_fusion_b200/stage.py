@@ -339,12 +339,12 @@ def scan_fastq_pair_multi(gene_engines, fastq1, fastq2, batch_pairs=1 << 20, max
         except AnchoredFusionError as e:
             reader.close()
             if "max_read_len" in str(e) and mrl < _lib.MAX_READ_LEN:
-                mrl = _lib.MAX_READ_LEN      # a later read was longer than the peeked ones: start over
+                mrl = 256 if mrl < 256 else _lib.MAX_READ_LEN      # a later read was longer than the peeked ones: start over
                 continue
             if "max_read_len" in str(e):
                 raise AnchoredFusionError(
-                    "%s -- this path packs reads of at most %d bases (AF_MAX_READ_LEN); longer reads (2x300 MiSeq, merged "
-                    "pairs) are not supported: trim them or run that sample through the reference's bwa stage"
+                    "%s -- this path packs reads of at most %d bases (AF_MAX_READ_LEN); longer reads (merged pairs, "
+                    "long-read platforms) are not supported: trim them or run that sample through the reference's bwa stage"
                     % (e, _lib.MAX_READ_LEN))
             raise
 

@@ -29,9 +29,10 @@ extern "C" {
 #endif
 
 #define AF_ABI_VERSION 1
-#define AF_MAX_READ_LEN 256 /* bases; 16 packed words per read */
+#define AF_MAX_READ_LEN 512 /* bases; up to 32 packed words per read (reads beyond 256 bases take the long-read kernels) */
 #define AF_TILE_PAIRS 32    /* pairs per packed tile == lanes per warp */
-#define AF_NMASK_WORDS 8    /* 256-bit N mask per read that holds an N */
+#define AF_NMASK_WORDS 16   /* 512-bit N mask per read that holds an N */
+#define AF_GENOME_MAX_READ_LEN 256 /* af_genome_align (the contiguity filter's genome pass) takes reads up to this length */
 
 enum af_status {
     AF_OK = 0,
@@ -88,7 +89,7 @@ typedef struct {
  * 128-bit loads are 512 contiguous bytes. */
 typedef struct {
     int32_t max_read_len;
-    int32_t words_per_read; /* W = ceil(max_read_len/16) */
+    int32_t words_per_read; /* W = ceil(max_read_len/16), rounded up to a multiple of 4 beyond 16 */
     int32_t quads_per_pair; /* Q = ceil(2W/4) */
     int32_t reserved;
     int64_t n_pairs;
@@ -334,7 +335,7 @@ void af_genome_free(af_genome_t *g);
 int64_t af_genome_length(const af_genome_t *g); /* separators included */
 int32_t af_genome_n_contigs(const af_genome_t *g);
 int af_genome_contig(const af_genome_t *g, int32_t i, const char **name, int64_t *start /* 0-based in the concatenation */, int64_t *len);
-/* reads: concatenated ASCII, offs[i]..offs[i+1] delimit read i (<= AF_MAX_READ_LEN bases each).  hits_out holds up to
+/* reads: concatenated ASCII, offs[i]..offs[i+1] delimit read i (<= AF_GENOME_MAX_READ_LEN bases each).  hits_out holds up to
  * n_reads records, ordered by read_id; reads without a record are unaligned.  reads_per_pass = 0 picks the default.
  * Calls on one genome object are serialised (they share its device buffers); use one object per thread for concurrency. */
 int af_genome_align(af_genome_t *g, const char *reads, const int64_t *offs, int64_t n_reads, const af_params_t *params,

@@ -23,6 +23,8 @@ def expected_flags(index, codes, lens=None, refine=False):
     Lmax = int(lens.max()) if lens is not None else stride
     flag = np.zeros(n, bool)
     W = (stride + 15) // 16
+    if W > 16:
+        W = (W + 3) & ~3                          # af_layout: long reads round W up to a multiple of 4
     pad = [(info.pad_byte >> (2 * k)) & 3 for k in range(4)]
     full = np.empty((n, 16 * W), dtype=np.uint64)
     full[:, :stride] = codes
@@ -48,8 +50,10 @@ def expected_flags(index, codes, lens=None, refine=False):
         v = filt[b] ^ fp3
         return (((v - np.uint64(0x40100401)) & ~v & np.uint64(0xA0080200)) & np.uint64(0xFFFFFFFF)) != 0
 
-    # sample grid of af_common.h: p_j = (19 - k') + j*S, floor((L - 19) / S) + 1 samples, L = the batch's longest read
-    for p in range(19 - KP, Lmax - KP + 1, S):
+    # sample grid of af_common.h (af_sample0 / af_nsamples), L = the batch's longest read
+    p0 = 4 if KP == 12 else 19 - KP
+    nsamp = (Lmax - 19 - p0 + S - 1) // S + 1 if Lmax >= 19 else 0
+    for p in range(p0, p0 + nsamp * S, S):
         hit = probe(p)
         if refine and hit.any():                  # neighbour test (af_neighbour_ok)
             ok = np.zeros(n, bool)

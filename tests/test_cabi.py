@@ -85,8 +85,11 @@ def test_layout_and_errors():
     assert (lay.words_per_read, lay.quads_per_pair, lay.n_tiles, lay.packed_bytes) == (10, 5, 312_500, 800_000_000)
     lay = af.layout(101, 33)
     assert (lay.words_per_read, lay.quads_per_pair, lay.n_tiles, lay.packed_bytes) == (7, 4, 2, 4096)
+    lay = af.layout(300, 64)                            # beyond 256 bases W is rounded up to a multiple of 4 (long-read scan)
+    assert (lay.words_per_read, lay.quads_per_pair, lay.n_tiles, lay.packed_bytes) == (20, 10, 2, 10240)
+    assert af.layout(257, 1).words_per_read == 20 and af.layout(512, 1).words_per_read == 32
     with pytest.raises(af.AnchoredFusionError):
-        af.layout(257, 1)
+        af.layout(513, 1)
     with pytest.raises(af.AnchoredFusionError):
         af.AnchorIndex("ACGT" * 10, kp=20)
     with pytest.raises(af.AnchoredFusionError):
@@ -149,7 +152,7 @@ def test_pack_roundtrip_ragged_with_n():
             npos = [k for k, c in enumerate(ss[p]) if c == "N"]
             if npos:
                 mask = nset[rid]
-                assert [k for k in range(256) if (mask[k >> 5] >> (k & 31)) & 1] == npos
+                assert [k for k in range(512) if (mask[k >> 5] >> (k & 31)) & 1] == npos
             else:
                 assert rid not in nset
     assert sorted(nset) == b.nread_ids.tolist()
@@ -180,7 +183,7 @@ def test_wire_format_round_trip_on_the_host():
     """tiles -> wire (4 L bits per pair, no padding) -> tiles is the identity, for ragged reads with N at every word edge."""
     import anchored_fusion_b200 as af
     rng = np.random.default_rng(0)
-    for L, n in ((150, 70), (36, 33), (101, 1), (250, 64), (256, 5), (16, 40), (17, 31), (1, 3), (32, 32)):
+    for L, n in ((150, 70), (36, 33), (101, 1), (250, 64), (256, 5), (16, 40), (17, 31), (1, 3), (32, 32), (257, 9), (300, 40), (301, 33), (512, 7)):
         lens = rng.integers(max(1, L - 20), L + 1, (2, n))
         lens[0, 0] = L
         seqs = [["".join("ACGTN"[c] for c in rng.choice(5, int(l), p=[.245, .245, .245, .245, .02])) for l in row] for row in lens]

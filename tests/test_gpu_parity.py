@@ -158,6 +158,73 @@ def test_variable_length_reads_with_n(af):
     assert hits_equal(hits2, want)
 
 
+@pytest.mark.parametrize("read_len", [300, 257, 512])
+def test_long_reads_uniform(af, read_len):
+    """Reads beyond 256 bases (2x300 MiSeq, merged pairs up to 512): the long-read instances of the scan (W = 20..32,
+    no register double buffer), the bitmap verify with 32 words per read and the base-by-base extension masks --
+    every record equals the oracle's, through device tiles, host tiles and the wire format."""
+    from oracle import oracle
+    spec = af.synth_spec(seed=900 + read_len, ref_len=400_000, anchor_start=150_000, anchor_len=7000, read_len=read_len,
+                         frag_mean=2 * read_len + 100, frag_sd=40, sub_ppm=15_000, fusion_ppm=30_000)
+    anchor = af.synth_anchor(spec)
+    index = af.AnchorIndex(anchor)
+    eng = af.Anchorer(index, 0)
+    n = 40_000
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    want = oracle.anchor_reads(oracle.encode(anchor), _interleave(m1, m2), threads=8)
+    assert len(want) > 1000 and int(want["m_len"].max()) > 256
+    hits, st = eng.anchor(af.synth_pairs_device(spec, 0, n, index.pad_byte, 0))
+    assert hits_equal(hits, want)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    host = af.pack_pairs([lut[r].tobytes() for r in m1], [lut[r].tobytes() for r in m2], pad_byte=index.pad_byte)
+    assert host.uniform_len == read_len
+    hits2, _ = eng.anchor_host(host, slot_pairs=4096, n_slots=3)
+    assert hits_equal(hits2, want)
+    wire = af.wire_from_packed(np.asarray(host.packed).view(np.uint32), read_len, n)
+    hits3, _ = eng.anchor_host(af.PackedBatch(wire, n, read_len, read_len), slot_pairs=4096, n_slots=3, wire=True)
+    assert hits_equal(hits3, want)
+
+
+def test_long_reads_ragged_with_n(af):
+    """ragged lengths 19..500 in one batch, Ns in reads and anchor, reads hanging over both anchor ends, both strands."""
+    from oracle import oracle
+    rng = np.random.default_rng(11)
+    G = 4000
+    anchor = rng.integers(0, 4, G).astype(np.uint8)
+    anchor[[100, 101, 2500]] = 4
+    n, stride = 3000, 500
+    reads = np.full((2 * n, stride), 4, dtype=np.uint8)
+    lens = rng.integers(19, stride + 1, 2 * n).astype(np.uint16)
+    lens[:8] = [500, 499, 257, 256, 300, 301, 19, 480]
+    for i in range(2 * n):
+        L = int(lens[i])
+        kind = i % 4
+        if kind == 0:
+            r = rng.integers(0, 4, L)
+        else:
+            p = int(rng.integers(-60, G - L + 60))
+            r = np.array([anchor[j] if 0 <= j < G and anchor[j] < 4 else rng.integers(0, 4) for j in range(p, p + L)])
+            if kind == 2:
+                j = int(rng.integers(0, L))
+                r[j:] = rng.integers(0, 4, L - j)
+            for _ in range(int(rng.integers(0, 6))):
+                r[rng.integers(0, L)] = rng.integers(0, 5)
+            if i % 8 >= 4:
+                r = np.array([3 - c if c < 4 else 4 for c in r[::-1]])
+        reads[i, :L] = r
+    want = oracle.anchor_reads(anchor, reads, lens=lens)
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    index = af.AnchorIndex(lut[anchor].tobytes())
+    seqs = [lut[reads[i, : lens[i]]].tobytes() for i in range(2 * n)]
+    host = af.pack_pairs(seqs[0::2], seqs[1::2], pad_byte=index.pad_byte)
+    assert host.uniform_len == 0 and host.n_nreads > 100 and host.max_read_len > 256
+    eng = af.Anchorer(index, 0)
+    hits, _ = eng.anchor(host.to_device(0))
+    assert len(want) > 500 and hits_equal(hits, want)
+    hits2, _ = eng.anchor_host(host, slot_pairs=512, n_slots=3)
+    assert hits_equal(hits2, want)
+
+
 @pytest.mark.parametrize("over", [{"B": 2, "X": 12, "T": 35, "clip5": 3, "clip3": 8},
                                   {"A": 2, "B": 5, "X": 30, "T": 50, "clip5": 0, "clip3": 0}])
 def test_other_scores_and_a_repetitive_anchor(af, over):

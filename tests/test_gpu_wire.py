@@ -18,7 +18,7 @@ def _ragged_batch(af, rng, L, n, pad_byte):
     return af.pack_pairs([draw(l) for l in lens1], [draw(l) for l in lens2], max_read_len=L, pad_byte=pad_byte)
 
 
-@pytest.mark.parametrize("L,n", [(150, 1000), (36, 33), (101, 4097), (250, 64), (256, 31), (16, 40), (17, 1)])
+@pytest.mark.parametrize("L,n", [(150, 1000), (36, 33), (101, 4097), (250, 64), (256, 31), (16, 40), (17, 1), (257, 5), (300, 100), (301, 64), (512, 33)])
 def test_device_expansion_restores_the_tiles_bit_for_bit(L, n):
     import torch
     import anchored_fusion_b200 as af

@@ -24,7 +24,7 @@ def _scan_pairs_host(af, index, batch, refine=False):
     return out
 
 
-@pytest.mark.parametrize("read_len", [36, 76, 101, 125, 150, 151, 250])
+@pytest.mark.parametrize("read_len", [36, 76, 101, 125, 150, 151, 250, 300, 410])
 @pytest.mark.parametrize("kp", [12, 13])
 def test_host_twin_equals_emulation_and_has_no_false_negatives(read_len, kp):
     import anchored_fusion_b200 as af
