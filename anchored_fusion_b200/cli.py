@@ -188,7 +188,14 @@ def run_gene_sample(file_anchored_seq, gene, fastq1, fastq2, out_dir_name, args,
                          gpu_number=args.gpu_number, gene_name=gene, gene_anchorer=gene_anchorer)
     if stats is None:               # a rank other than 0 of a torchrun job: rank 0 writes the files
         return None
-    groups = write_split_points(stats, gene, out_dir_name + '_split_points.txt')
+    try:
+        groups = write_split_points(stats, gene, out_dir_name + '_split_points.txt')
+    except IndexError:
+        # the reference's pile-up (Co_Split_reads, functions.py:166) holds 200 bases on either side of a junction and
+        # raises on a longer side (2x300 reads); the stage's own files above are complete, only this summary table is not
+        print('[anchoring] %s: a split read has more than 200 bases on one side of its junction -- the reference\'s '
+              'Co_Split_reads array (400 columns) cannot hold it; %s_split_points.txt not written' % (gene, out_dir_name))
+        groups = []
     kept = contiguity_stage(out_dir_name, gene, args)
     if kept is not None:
         print('[anchoring] %s: %d 2-op reads survive the genome-contiguity filter' % (gene, kept))

@@ -95,6 +95,64 @@ def test_bulk_cli_on_the_bundled_sample(bundled, tmp_path):
     assert main_bulk(["--file_anchored_cds", fa, "--fastq1", p1, "--fastq2", p2, "--out_folder", out]) == 0
 
 
+def test_bulk_cli_with_2x300_reads(tmp_path):
+    """2x300 MiSeq-shaped input (ragged 250..300, a few N) through the reference's CLI flags: the anchored-reads BAM holds
+    the oracle's records, read for read (the round-1 limit of 256 bases made this input fail)."""
+    import numpy as np
+    import anchored_fusion_b200 as af
+    from anchored_fusion_b200.bam import read_bam
+    from anchored_fusion_b200.cli import main_bulk
+    from anchored_fusion_b200.records import cigar_string, sort_hits
+    from oracle import oracle
+    d = str(tmp_path)
+    spec = af.synth_spec(seed=31, ref_len=300_000, anchor_start=100_000, anchor_len=5000, read_len=300,
+                         frag_mean=650, frag_sd=40, sub_ppm=12_000, fusion_ppm=40_000)
+    anchor = af.synth_anchor(spec)
+    anchor = anchor.decode() if isinstance(anchor, bytes) else anchor
+    n = 20_000
+    m1, m2 = af.synth_pairs_host(spec, 0, n)
+    rng = np.random.default_rng(3)
+    lens = rng.integers(250, 301, (2, n))
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    seqs = [[], []]
+    for m, mm in enumerate((m1, m2)):
+        for i in range(n):
+            r = mm[i, : lens[m, i]].copy()
+            if i % 50 == 7:
+                r[int(rng.integers(0, len(r)))] = 4
+            seqs[m].append(lut[r].tobytes().decode())
+    fa = os.path.join(d, "target_gene.fasta")
+    with open(fa, "w") as fh:
+        fh.write(">GENEX synthetic\n")
+        for i in range(0, len(anchor), 70):
+            fh.write(anchor[i:i + 70] + "\n")
+    p1, p2 = os.path.join(d, "s_1.fastq.gz"), os.path.join(d, "s_2.fastq.gz")
+    with gzip.open(p1, "wt", compresslevel=1) as f1, gzip.open(p2, "wt", compresslevel=1) as f2:
+        for i in range(n):
+            f1.write("@r%d/1\n%s\n+\n%s\n" % (i, seqs[0][i], "F" * len(seqs[0][i])))
+            f2.write("@r%d/2\n%s\n+\n%s\n" % (i, seqs[1][i], "F" * len(seqs[1][i])))
+    out = os.path.join(d, "out")
+    assert main_bulk(["--file_anchored_cds", fa, "--fastq1", p1, "--fastq2", p2, "--out_folder", out,
+                      "--not_filter_false_positive", "--thread", "4"]) == 0
+    w = os.path.join(out, "GENEX_fusion", "work_dir", "GENEX_fusion")
+    codes = np.full((2 * n, 300), 4, dtype=np.uint8)
+    ol = np.empty(2 * n, dtype=np.uint16)
+    for i in range(n):
+        for m in range(2):
+            c = oracle.encode(seqs[m][i])
+            codes[2 * i + m, : len(c)] = c
+            ol[2 * i + m] = len(c)
+    want = sort_hits(oracle.anchor_reads(oracle.encode(anchor), codes, lens=ol, threads=4))
+    _, refs, recs = read_bam(w + "_anchored_reads.bam")
+    assert refs == [("GENEX", 5000)] and len(recs) == len(want) > 500
+    assert int(want["m_len"].max()) > 256
+    for r, h in zip(recs, want):
+        rid = int(h["read_id"])
+        seq = seqs[rid & 1][rid >> 1]
+        assert (r["qname"], r["pos"], r["cigar"]) == ("r%d" % (rid >> 1), int(h["pos"]), cigar_string(h))
+        assert r["seq"] == (_rc(seq) if int(h["score_strand"]) & 1 else seq)
+
+
 def test_singlecell_cli_matches_bulk_union(bundled, tmp_path):
     """Per-cell FASTQ pairs (the reference's single-cell layout): the union of the cells' anchored
     reads equals the bulk result on the concatenation."""
