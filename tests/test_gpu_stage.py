@@ -123,7 +123,7 @@ def test_bulk_cli_with_2x300_reads(tmp_path):
             seqs[m].append(lut[r].tobytes().decode())
     fa = os.path.join(d, "target_gene.fasta")
     with open(fa, "w") as fh:
-        fh.write(">GENEX synthetic\n")
+        fh.write(">ABL9\n")
         for i in range(0, len(anchor), 70):
             fh.write(anchor[i:i + 70] + "\n")
     p1, p2 = os.path.join(d, "s_1.fastq.gz"), os.path.join(d, "s_2.fastq.gz")
@@ -134,7 +134,7 @@ def test_bulk_cli_with_2x300_reads(tmp_path):
     out = os.path.join(d, "out")
     assert main_bulk(["--file_anchored_cds", fa, "--fastq1", p1, "--fastq2", p2, "--out_folder", out,
                       "--not_filter_false_positive", "--thread", "4"]) == 0
-    w = os.path.join(out, "GENEX_fusion", "work_dir", "GENEX_fusion")
+    w = os.path.join(out, "ABL9_fusion", "work_dir", "ABL9_fusion")
     codes = np.full((2 * n, 300), 4, dtype=np.uint8)
     ol = np.empty(2 * n, dtype=np.uint16)
     for i in range(n):
@@ -144,7 +144,7 @@ def test_bulk_cli_with_2x300_reads(tmp_path):
             ol[2 * i + m] = len(c)
     want = sort_hits(oracle.anchor_reads(oracle.encode(anchor), codes, lens=ol, threads=4))
     _, refs, recs = read_bam(w + "_anchored_reads.bam")
-    assert refs == [("GENEX", 5000)] and len(recs) == len(want) > 500
+    assert refs == [("ABL9", 5000)] and len(recs) == len(want) > 500
     assert int(want["m_len"].max()) > 256
     for r, h in zip(recs, want):
         rid = int(h["read_id"])
