@@ -402,10 +402,14 @@ extern "C" int af_seed_scan_config(int32_t threads_per_block, int32_t mode) {
     return AF_OK;
 }
 
+// SM partition (af_sm_partition): the scan's persistent grid leaves `g_small_sms` SMs to the kernels of the previous
+// batch (the verify stage needs whole SMs for its shared-memory filter and can never sit next to a scan CTA); 0 = none.
+static int g_small_sms = env_flag("AF_SMALL_SMS", 0);
 static int scan_grid(const af_dev_index *d, long long n_tiles, int threads = 0) {
     const int nwarps = (threads ? threads : g_scan_threads) / 32;
     const long long want = (n_tiles + nwarps - 1) / nwarps;
-    return (int)(want < d->num_sms ? (want > 0 ? want : 1) : d->num_sms);
+    const int sms = g_small_sms > 0 && g_small_sms < d->num_sms ? d->num_sms - g_small_sms : d->num_sms;
+    return (int)(want < sms ? (want > 0 ? want : 1) : sms);
 }
 
 template <int W, int KP, int MAXT, bool PF, bool RQ, bool EMIT, bool BLOOM = false>
@@ -1453,7 +1457,8 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
             vattr[d->device & 63][d->kp == 12 ? 0 : 1] = true;
         }
         long long vb = (cand_cap + 1023) / 1024;
-        const unsigned vg = (unsigned)(vb < d->num_sms ? vb : d->num_sms);
+        const int vsms = g_small_sms > 0 && g_small_sms < d->num_sms ? g_small_sms : d->num_sms;
+        const unsigned vg = (unsigned)(vb < vsms ? vb : vsms);
 #define AF_VERIFY_SMEM_ARGS (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, \
         b->nread_ids, b->nmask, (int)b->n_nreads, cand, d_counts, (uint32_t)cand_cap, d->d_filter2, d->fmul2, d->nb2,       \
         d->d_table, d->tmask, d->d_anchor, d->d_apk[0], d->d_apk[1], d->anchor_has_n, d->G, d->P.k, keep, cc2
