@@ -154,7 +154,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.af_abi_version() != 1:
+        if handle.af_abi_version() != 2:
             raise AnchoredFusionError("libafb200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AF_ABI_VERSION 1
+#define AF_ABI_VERSION 2 /* 2: AF_NMASK_WORDS 8 -> 16, AF_MAX_READ_LEN 256 -> 512, W rounded to a multiple of 4 beyond 16 */
 #define AF_MAX_READ_LEN 512 /* bases; up to 32 packed words per read (reads beyond 256 bases take the long-read kernels) */
 #define AF_TILE_PAIRS 32    /* pairs per packed tile == lanes per warp */
 #define AF_NMASK_WORDS 16   /* 512-bit N mask per read that holds an N */
