@@ -444,7 +444,7 @@ static int launch_scan_mode(const af_dev_index *d, const af_batch_t *b, long lon
 }
 
 // Reads of 257..512 bases (W = 20, 24, 28, 32; af_layout rounds W up to a multiple of 4 beyond 16): the plain scan
-// without the register double buffer -- a pair alone is up to 64 registers -- on 384 threads.  2x300 MiSeq runs and
+// on 384 threads, with the register double buffer up to W = 24 (a pair alone is up to 64 registers).  2x300 MiSeq runs and
 // merged pairs are small next to the 2x150 bulk, so this instance is built for coverage, not tuned.
 static const int AF_LONG_SCAN_THREADS = 384;
 template <int W, int KP>
@@ -452,8 +452,9 @@ static int launch_scan_long(const af_dev_index *d, const af_batch_t *b, long lon
                             uint32_t *cc, uint32_t *counts, bool rq, const af_emit *emit, cudaStream_t st) {
     if (rq || emit) { af_set_error("seed scan: reads beyond 256 bases run the plain scan only"); return AF_ERR_ARG; }
     const int threads = g_scan_threads < AF_LONG_SCAN_THREADS ? g_scan_threads : AF_LONG_SCAN_THREADS;
-    return d->bloom ? launch_scan<W, KP, AF_LONG_SCAN_THREADS, false, false, false, true>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st, threads)
-                    : launch_scan<W, KP, AF_LONG_SCAN_THREADS, false, false, false, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st, threads);
+    constexpr bool PF = W <= 24;                            // two tiles of 2 x 24 words still fit the 170 registers of a 384-thread CTA
+    return d->bloom ? launch_scan<W, KP, AF_LONG_SCAN_THREADS, PF, false, false, true>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st, threads)
+                    : launch_scan<W, KP, AF_LONG_SCAN_THREADS, PF, false, false, false>(d, b, n_tiles, nprobe, flags, cc, counts, af_emit(), st, threads);
 }
 #define AF_SCAN_CASE_LONG(WW)                                                                                  \
     case WW:                                                                                                   \

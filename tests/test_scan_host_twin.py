@@ -87,3 +87,33 @@ def test_long_anchor_switches_to_the_bloom_filter_without_false_negatives(anchor
     bucket_rate = _scan_pairs_host(af, plain, af.pack_pairs([lut[r].tobytes() for r in rnd[0::2]], [lut[r].tobytes() for r in rnd[1::2]],
                                                             pad_byte=plain.pad_byte)).mean()
     assert bloom_rate < 0.7 * bucket_rate and bloom_rate < (0.25 if anchor_len == 40_000 else 0.7), (bloom_rate, bucket_rate)
+
+
+@pytest.mark.parametrize("kp", [12, 13])
+def test_sample_grid_covers_every_window_of_19_matches(kp):
+    """The sample grid (af_sample0 / af_nsamples, csrc/af_common.h) starts at base 4 (k' = 12) or 6 (k' = 13) and has
+    one sample fewer than a zero-based grid.  Exhaustive check of its guarantee through the kernel's probe sequence
+    (host twin): a read that matches the anchor in exactly one window of 19 bases [q, q+19) -- everything else
+    mismatching -- is flagged for EVERY q in 0..L-19, at every read length class including both ends of each word
+    count and the long-read instances."""
+    import anchored_fusion_b200 as af
+    rng = np.random.default_rng(kp)
+    G = 3000
+    anchor = rng.integers(0, 4, G).astype(np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    index = af.AnchorIndex(lut[anchor].tobytes(), kp=kp)
+    for L in (19, 20, 26, 27, 28, 36, 50, 76, 101, 125, 144, 145, 150, 151, 160, 161, 250, 256, 257, 300, 301, 320, 321, 512):
+        qs = list(range(L - 18))
+        reads = []
+        for q in qs:
+            a0 = int(rng.integers(L, G - 2 * L))
+            r = (anchor[a0 - q: a0 - q + L] + 1 + rng.integers(0, 3, L)) % 4          # every base differs from the anchor's ...
+            r[q:q + 19] = anchor[a0: a0 + 19]                                          # ... except the window
+            if q % 2:                                                                  # odd q: the read is the reverse strand
+                r = (3 - r)[::-1]
+            reads.append(lut[r.astype(np.uint8)].tobytes())
+        if len(reads) % 2:
+            reads.append(reads[-1])
+        batch = af.pack_pairs(reads[0::2], reads[1::2], pad_byte=index.pad_byte)
+        got = _scan_pairs_host(af, index, batch)
+        assert got.all(), (L, [qs[i] for i in np.flatnonzero(~got[: len(qs)])])

@@ -19,4 +19,4 @@ for f in ["n8", "config3_n8", "singlecell_n8"]:
     except Exception as ex:
         print(f, "ERR", ex)
 PY
-tail -3 gpurun_out/r02zz_bench_*.err
+for f in gpurun_out/r02zz_bench_*.err; do tail -3 $f; done
