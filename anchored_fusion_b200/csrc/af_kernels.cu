@@ -1440,7 +1440,9 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
     prof_span(ev, st, ST_COMPACT1);
     prof_mark(&ev, st);
     {
-    if (lay.words_per_read > 16) {                          // long reads (257..512 bases): the bitmap kernel with 32 words per read
+    // the shared-memory variant needs its half-size filter plus (W + 3) x 1024 words: fits up to W = 28 (448 bases)
+    const bool vsmem_fits = ((size_t)d->nb2 + (size_t)(lay.words_per_read + 3) * 1024) * 4 + 2048 <= (size_t)227 * 1024;
+    if (lay.words_per_read > 16 && !(g_verify_smem && !d->bloom && vsmem_fits)) {   // long reads without room (or a Bloom index): the bitmap kernel with 32 words per read
         long long vthreads = cand_cap < (long long)d->num_sms * 2048 ? cand_cap : (long long)d->num_sms * 2048;
         const unsigned vgrid = (unsigned)((vthreads + 255) / 256);
 #define AF_VERIFY_LONG_ARGS (const uint32_t *)b->packed, lay.words_per_read, lay.quads_per_pair, b->uniform_len, b->lens, \
@@ -1449,7 +1451,7 @@ static int anchor_batch_impl(const af_dev_index_t *d, const af_batch_t *b, void 
         if (d->kp == 12) k_verify<12, 32><<<vgrid, 256, 0, st>>>(AF_VERIFY_LONG_ARGS);
         else k_verify<13, 32><<<vgrid, 256, 0, st>>>(AF_VERIFY_LONG_ARGS);
     } else
-    if (g_verify_smem && !d->bloom) {                      // (a Bloom index's half-size fingerprint copy is saturated: k_verify's exact bitmap instead)
+    if (g_verify_smem && !d->bloom && vsmem_fits) {        // (a Bloom index's half-size fingerprint copy is saturated: k_verify's exact bitmap instead)
         const size_t vsmem = ((size_t)d->nb2 + (size_t)(lay.words_per_read + 3) * 1024) * 4;
         static bool vattr[64][2] = {{false}};
         if (!vattr[d->device & 63][d->kp == 12 ? 0 : 1]) {

@@ -158,7 +158,7 @@ def test_variable_length_reads_with_n(af):
     assert hits_equal(hits2, want)
 
 
-@pytest.mark.parametrize("read_len", [300, 257, 512])
+@pytest.mark.parametrize("read_len", [300, 257, 400, 448, 512])
 def test_long_reads_uniform(af, read_len):
     """Reads beyond 256 bases (2x300 MiSeq, merged pairs up to 512): the long-read instances of the scan (W = 20..32,
     no register double buffer), the bitmap verify with 32 words per read and the base-by-base extension masks --
