@@ -17,7 +17,7 @@ want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "DRAM r
 seen = set()
 with open("profiles/%s_stages_ncu.md" % tag, "w") as f:
     f.write("# %s -- `ncu --set full --clock-control none` of the small stages\n\n" % tag)
-    f.write("Command: `python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --slots 1` (10 M pairs per step, 362 k flagged, "
+    f.write("Command: `python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --slots 1` (10 M pairs per step, 341 k flagged (362 k before the offset sample grid), "
             "13.8 k seeded, 13.7 k anchored reads).  One launch per kernel; times under ncu are serialised and cold, the live "
             "CUDA-event times are in `%s_bench_n1.json` (`roofline.stage_ms_per_step`).\n\n" % tag)
     for r in data:
