@@ -12,14 +12,15 @@ def _write_fastq(path, names, seqs, quals, gz):
             fh.write("@%s\n%s\n+\n%s\n" % (n, s, q))
 
 
+@pytest.mark.parametrize("longest", [100, 300])           # 300: the long-read layout (W rounded up to 20 words, 512-bit N masks)
 @pytest.mark.parametrize("gz", [True, False])
-def test_reader_batches_equal_pack_pairs(tmp_path, gz):
+def test_reader_batches_equal_pack_pairs(tmp_path, gz, longest):
     import anchored_fusion_b200 as af
     from anchored_fusion_b200.stage import FastqPairReader, peek_max_read_len
     rng = np.random.default_rng(3)
     n = 2500
-    s1 = ["".join(rng.choice(list("ACGTN"), p=[.245, .245, .245, .245, .02], size=rng.integers(20, 101))) for _ in range(n)]
-    s2 = ["".join(rng.choice(list("ACGT"), size=rng.integers(20, 101))) for _ in range(n)]
+    s1 = ["".join(rng.choice(list("ACGTN"), p=[.245, .245, .245, .245, .02], size=rng.integers(20, longest + 1))) for _ in range(n)]
+    s2 = ["".join(rng.choice(list("ACGT"), size=rng.integers(20, longest + 1))) for _ in range(n)]
     q1 = ["".join(chr(33 + int(x)) for x in rng.integers(2, 40, len(s))) for s in s1]
     q2 = ["I" * len(s) for s in s2]
     names = ["frag%d extra comment" % i for i in range(n)]
@@ -27,7 +28,7 @@ def test_reader_batches_equal_pack_pairs(tmp_path, gz):
     p1, p2 = str(tmp_path / ("x_1" + ext)), str(tmp_path / ("x_2" + ext))
     _write_fastq(p1, [m + "/1" if i % 2 else m for i, m in enumerate(names)], s1, q1, gz)
     _write_fastq(p2, [("frag%d/2" % i) for i in range(n)], s2, q2, gz)
-    mrl = max(peek_max_read_len(p1, 50), 112)
+    mrl = max(peek_max_read_len(p1, 50), 112 if longest == 100 else 304)
     reader = FastqPairReader(p1, p2, mrl, 0xE4, 1000)
     seen = 0
     for bi in range(4):
