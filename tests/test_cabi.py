@@ -193,3 +193,16 @@ def test_wire_format_round_trip_on_the_host():
         assert wire.nbytes == af.wire_bytes(L, n) == ((n + 31) // 32) * ((4 * L + 31) // 32) * 128
         assert np.array_equal(af.wire_to_packed(wire, L, n, 0x6C), tiles), (L, n)
     assert af.wire_bytes(150, 10_000_000) == 760_000_000          # the algorithmic 76 bytes per 2 x 150 bp pair
+
+
+def test_python_constants_follow_the_header():
+    """_lib.py mirrors a few #defines of include/anchored_fusion.h (array strides, limits); a drift would corrupt the
+    N-mask arrays silently."""
+    import anchored_fusion_b200 as af  # noqa: F401
+    from anchored_fusion_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "anchored_fusion.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"^#define\s+(AF_[A-Z_]+)\s+(\d+)\b", text, flags=re.M)}
+    assert defs["AF_MAX_READ_LEN"] == _lib.MAX_READ_LEN == 512
+    assert defs["AF_NMASK_WORDS"] == _lib.NMASK_WORDS == defs["AF_MAX_READ_LEN"] // 32
+    assert defs["AF_GENOME_MAX_READ_LEN"] == _lib.GENOME_MAX_READ_LEN
+    assert defs["AF_ABI_VERSION"] == _lib.lib().af_abi_version()
