@@ -186,8 +186,9 @@ def fastq_rates(args, index, eng):
                 "threads": threads, "host_cores": os.cpu_count(),
                 "path": "two FASTQ files -> %d-worker reader (own DEFLATE decoder, newline index, CRC, SIMD 2-bit pack) -> pinned "
                         "tiles -> af_pipeline_run -> records" % threads,
-                "single_member_gzip": dict(out["gzip"], format="one gzip member per file (gzip / bcl2fastq style): a serial bit "
-                                           "stream, one inflate thread per file; index / CRC / pack on the workers"),
+                "single_member_gzip": dict(out["gzip"], format="one gzip member per file (gzip / bcl2fastq style): the serial bit "
+                                           "stream is cut at block starts found by bit search and decoded by several workers "
+                                           "(af_inflate_par.h; AF_GZIP_SERIAL=1 for one inflate thread per file)"),
                 "plain_text": out["plain"],
                 "input": "oracle/af_synth.cpp: Illumina-style read names, binned qualities (F : , #), deflate level 1"})
     return res
