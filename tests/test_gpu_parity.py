@@ -328,10 +328,11 @@ def test_robustness_set_n_bases_and_trimmed_reads(af):
     assert hits_equal(hits2, want)
 
 
+@pytest.mark.parametrize("read_len", [101, 300])
 @pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1025])
-def test_edge_batch_sizes(af, n):
+def test_edge_batch_sizes(af, n, read_len):
     from oracle import oracle
-    spec = af.synth_spec(seed=2, ref_len=20_000, anchor_start=5_000, anchor_len=4000, read_len=101, frag_mean=250)
+    spec = af.synth_spec(seed=2, ref_len=20_000, anchor_start=5_000, anchor_len=4000, read_len=read_len, frag_mean=2 * read_len + 50)
     anchor = af.synth_anchor(spec)
     index = af.AnchorIndex(anchor)
     eng = af.Anchorer(index, 0)
@@ -415,8 +416,8 @@ def test_capacity_overflow_is_reported_not_dropped(af):
         eng.anchor(dev, cand_cap=1000, hits_cap=1000)
 
 
-@pytest.mark.parametrize("modes", [(), (11,), (4,), (10,), (8,)])
-def test_kernels_stay_inside_their_buffers(af, modes):
+@pytest.mark.parametrize("modes,read_len", [((), 150), ((11,), 150), ((4,), 150), ((10,), 150), ((8,), 150), ((), 300), ((), 500)])
+def test_kernels_stay_inside_their_buffers(af, modes, read_len):
     """compute-sanitizer is not available on this pool, so out-of-bounds WRITES are looked for directly:
     workspace, hit list, counters and the packed batch sit between 64 KB canary zones, which must come
     back untouched (default path; the scan with the in-kernel refinement queue; the fused scan+verify kernel;
@@ -425,11 +426,11 @@ def test_kernels_stay_inside_their_buffers(af, modes):
     import ctypes
     import torch
     from anchored_fusion_b200._lib import check, lib
-    spec = af.synth_spec(seed=91, ref_len=300_000, anchor_start=100_000, anchor_len=5000, read_len=150,
-                         frag_mean=300, sub_ppm=15_000, fusion_ppm=50_000)
+    spec = af.synth_spec(seed=91, ref_len=300_000, anchor_start=100_000, anchor_len=5000, read_len=read_len,
+                         frag_mean=2 * read_len, sub_ppm=15_000, fusion_ppm=50_000)
     index = af.AnchorIndex(af.synth_anchor(spec))
     eng = af.Anchorer(index, 0)
-    n = 77_777
+    n = 77_777 if read_len == 150 else 33_333
     ref_hits, stats = eng.anchor(af.synth_pairs_device(spec, 0, n, index.pad_byte, 0))
     G, dev = 1 << 16, torch.device("cuda", 0)
 
@@ -437,17 +438,17 @@ def test_kernels_stay_inside_their_buffers(af, modes):
         big = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device=dev)
         return big, big[G: G + nbytes]
 
-    lay = af.layout(150, n)
+    lay = af.layout(read_len, n)
     src = af.synth_pairs_device(spec, 0, n, index.pad_byte, 0)
     big_p, packed = guarded(lay.packed_bytes)
     packed.copy_(src.packed.view(torch.uint8)[: lay.packed_bytes])
     cand_cap = stats["flagged"] + 1                      # just enough
     hits_cap = len(ref_hits)                             # exactly enough
-    ws_bytes = lib().af_workspace_bytes(n, cand_cap)
+    ws_bytes = lib().af_workspace_bytes_len(n, cand_cap, read_len)    # exactly what this read length needs
     big_w, ws = guarded(ws_bytes)
     big_h, hits = guarded(hits_cap * 16)
     big_c, counts = guarded(32)
-    batch = af.PackedBatch(packed.view(torch.int32), n, 150, 150)
+    batch = af.PackedBatch(packed.view(torch.int32), n, read_len, read_len)
     cb = batch.c_struct()
     for m in modes:
         check(lib().af_seed_scan_config(0, m))
